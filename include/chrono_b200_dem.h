@@ -1,0 +1,141 @@
+/* =============================================================================
+ * chrono_b200_dem.h -- C ABI of the B200-native smooth-contact (SMC) granular DEM engine.
+ *
+ * This is the drop-in boundary for the hot path of Chrono::Dem (a.k.a. chrono_gpu):
+ *     chrono::dem::ChSystemDem::Initialize / AdvanceSimulation / getters
+ *     (reference: src/chrono_dem/physics/ChSystemDem.h:40-393; impl loop src/chrono_dem/gpu/ChDemSMC.cu:619-691)
+ * The reference has no C ABI of its own (its seam is the pimpl pointer ChSystemDem::m_sys, ChSystemDem.h:350);
+ * these entry points are what a maintainer binds in place of ChSystemDem_impl -- see INTEGRATION.md.  The C++
+ * mirror of the reference class (include/chrono_dem/physics/ChSystemDem.h) is written on top of exactly this ABI.
+ *
+ * Arithmetic contract: fp64 state, the force law and collision semantics of Chrono::Multicore's
+ * ChSystemMulticoreSMC (src/chrono_multicore/solver/ChIterativeSolverMulticoreSMC.cpp:56-546,
+ * src/chrono/collision/multicore/*), which is the parity oracle (oracle/).
+ *
+ * All pointers are HOST pointers unless the name ends in _dev.  Every function returns 0 on success or a
+ * negative DEMB200_E* code; dem_b200_last_error() gives the text.  No function calls exit().  No CPU fallback:
+ * if no CUDA device / kernel image is available every entry point fails with DEMB200_ECUDA.
+ * ============================================================================= */
+#ifndef CHRONO_B200_DEM_H
+#define CHRONO_B200_DEM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dem_b200_system dem_b200_system; /* opaque */
+
+enum {
+    DEMB200_OK = 0,
+    DEMB200_ECUDA = -1,    /* CUDA runtime error (no device, launch failure, ...) */
+    DEMB200_EINVAL = -2,   /* bad argument / call order */
+    DEMB200_EGRID = -3,    /* bin edge < 2*Rmax, or a sphere left the hashable grid */
+    DEMB200_EHISTORY = -4, /* a sphere needs more contact-history slots than history_slots */
+    DEMB200_ENAN = -5,     /* non-finite state detected */
+    DEMB200_ECAPACITY = -6 /* a recording buffer (pairs) overflowed */
+};
+
+/* ChSystemSMC::ContactForceModel / AdhesionForceModel / TangentialDisplacementModel
+ * (src/chrono/physics/ChSystemSMC.h:34-53); CHDEM_FRICTION_MODE FRICTIONLESS/SINGLE_STEP/MULTI_STEP map to
+ * DEMB200_TANG_NONE/ONESTEP/MULTISTEP (src/chrono_dem/ChDemDefines.h:47). */
+enum { DEMB200_HOOKE = 0, DEMB200_HERTZ = 1, DEMB200_PLAINCOULOMB = 2, DEMB200_FLORES = 3 };
+enum { DEMB200_ADH_CONSTANT = 0, DEMB200_ADH_DMT = 1, DEMB200_ADH_PERKO = 2 };
+enum { DEMB200_TANG_NONE = 0, DEMB200_TANG_ONESTEP = 1, DEMB200_TANG_MULTISTEP = 2 };
+/* CHDEM_TIME_INTEGRATOR, same order as src/chrono_dem/ChDemDefines.h:44.  CENTERED_DIFFERENCE is the
+ * semi-implicit Euler of Chrono::Multicore (src/chrono/physics/ChBody.cpp:288-310) and the parity integrator. */
+enum { DEMB200_FORWARD_EULER = 0, DEMB200_CHUNG = 1, DEMB200_CENTERED_DIFFERENCE = 2, DEMB200_EXTENDED_TAYLOR = 3 };
+
+/* ChContactMaterialSMC (src/chrono/physics/ChContactMaterialSMC.h:85-98); float, as in the reference. */
+typedef struct dem_b200_material {
+    float young, poisson;
+    float mu_s, mu_roll, mu_spin, cr;
+    float adhesion, adhesion_dmt, adhesion_perko;
+    float kn, kt, gn, gt;
+} dem_b200_material;
+
+enum { DEMB200_MAT_SPHERE = 0, DEMB200_MAT_WALL = 1, DEMB200_MAT_MESH = 2 };
+
+typedef struct dem_b200_config {
+    int device;           /* CUDA device ordinal */
+    int force_model, adhesion_model, tangential_mode, use_mat_props;
+    int integrator;
+    int history_slots;    /* contact-history slots per sphere (reference Dem: 12, Multicore: 20); 0 -> 12 */
+    double char_vel, min_slip_vel, min_roll_vel, min_spin_vel; /* ChSettings.h:121-124 */
+    double dt;
+    double gravity[3];
+    int bins_per_axis[3]; /* broadphase grid resolution (collision_settings::bins_per_axis) */
+    dem_b200_material material[3]; /* [DEMB200_MAT_SPHERE|WALL|MESH] */
+    double mass_coef;     /* sphere mass = mass_coef * (r*r*r)  (= 4/3 pi rho for solid spheres) */
+    double wall_mass;     /* mass of the body carrying the walls; enters m_eff (Multicore Q9) */
+    double mesh_mass;     /* default mass of mesh bodies */
+} dem_b200_config;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------- */
+int dem_b200_create(const dem_b200_config* cfg, dem_b200_system** out);
+void dem_b200_destroy(dem_b200_system* s);
+const char* dem_b200_last_error(const dem_b200_system* s); /* s may be NULL: last create() error */
+int dem_b200_set_config(dem_b200_system* s, const dem_b200_config* cfg); /* model/material/dt changes mid-run */
+
+/* ---- scene (before initialize) -- ChSystemDem::SetParticles / CreateBC* ---------------------------------- */
+/* n spheres in user order; vel3/omega3/fixed may be NULL (zeros).  radius has n entries. */
+int dem_b200_set_spheres(dem_b200_system* s, size_t n, const double* pos3, const double* vel3,
+                         const double* omega3, const double* radius, const uint8_t* fixed);
+/* Box wall (Multicore box shape on the fixed wall body): world centre, quaternion (w,x,y,z), half dims.
+ * Returns the wall index (>= 0) or an error (< 0).  Shape id of wall k is k; spheres follow (Q12 numbering). */
+int dem_b200_add_box_wall(dem_b200_system* s, const double pos[3], const double rot[4], const double hdims[3]);
+/* Infinite plane wall (Chrono::Dem CreateBCPlane, src/chrono_dem/physics/ChSystemDem.h:228): point + unit normal
+ * pointing into the domain.  Contact iff distance < r; eff. radius = r. */
+int dem_b200_add_plane_wall(dem_b200_system* s, const double pos[3], const double normal[3]);
+int dem_b200_set_wall_velocity(dem_b200_system* s, int wall, const double pos[3], const double vel[3]);
+
+/* ---- run -- ChSystemDem::Initialize / AdvanceSimulation --------------------------------------------------- */
+int dem_b200_initialize(dem_b200_system* s);
+/* nsteps steps of size dt, asynchronous on the system's stream; errors surface at the next sync point. */
+int dem_b200_step(dem_b200_system* s, int nsteps);
+int dem_b200_sync(dem_b200_system* s);
+/* Same, bracketed by CUDA events on the launching stream; *ms = device time of the nsteps steps. */
+int dem_b200_step_timed(dem_b200_system* s, int nsteps, float* ms);
+/* Per-kernel device time (ms, summed over nsteps) in the order of dem_b200_kernel_name(); n_out <= 16. */
+int dem_b200_step_profile(dem_b200_system* s, int nsteps, float* ms_per_kernel, int* n_out);
+const char* dem_b200_kernel_name(int k);
+/* Host-buffer round trip of the hot path: upload state (user order), nsteps steps, download state.
+ * This is the call timed as "e2e" by bench.py.  Any of the out pointers may be NULL. */
+int dem_b200_advance_host(dem_b200_system* s, size_t n, const double* pos3_in, const double* vel3_in,
+                          const double* omega3_in, int nsteps, double* pos3_out, double* vel3_out,
+                          double* omega3_out);
+
+/* ---- state access (user order) -- GetParticlePosition / Velocity / AngVelocity ------------------------------- */
+size_t dem_b200_num_spheres(const dem_b200_system* s);
+int dem_b200_get_state(dem_b200_system* s, double* pos3, double* vel3, double* omega3);
+int dem_b200_set_state(dem_b200_system* s, const double* pos3, const double* vel3, const double* omega3);
+int dem_b200_get_sphere(dem_b200_system* s, size_t i, double pos[3], double vel[3], double omega[3]);
+double dem_b200_time(const dem_b200_system* s);
+
+/* ---- reductions -- GetMaxParticleZ, GetParticlesKineticEnergy, ... (ChSystemDem.h:246-262) ------------------ */
+enum { DEMB200_RED_MAX_Z = 0, DEMB200_RED_MIN_Z = 1, DEMB200_RED_KE = 2, DEMB200_RED_MAX_SPEED = 3,
+       DEMB200_RED_COUNT_ABOVE_Z = 4, DEMB200_RED_COUNT_ABOVE_X = 5, DEMB200_RED_NUM_CONTACTS = 6 };
+int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out);
+
+/* ---- parity / inspection (tests, smoke) ---------------------------------------------------------------------- */
+/* When enabled, each step also records per-sphere contact force & torque, the contact-pair list and the
+ * per-sphere bin ranges of that step.  max_pairs = capacity of the pair buffer. */
+int dem_b200_enable_recording(dem_b200_system* s, int enable, size_t max_pairs);
+int dem_b200_get_forces(dem_b200_system* s, double* force3, double* torque3); /* user order */
+/* pair key = (shapeA << 32) | shapeB with shapeA < shapeB; wall k is shape k, sphere i is shape num_walls + i */
+int dem_b200_get_pairs(dem_b200_system* s, uint64_t* pairs, size_t capacity, size_t* n);
+int dem_b200_get_bins(dem_b200_system* s, int32_t* gmin3, int32_t* gmax3); /* user order */
+int dem_b200_get_grid(dem_b200_system* s, double origin[3], double bin_size[3], double inv_bin_size[3]);
+/* history rows: owner shape id, other shape id, displacement, duration, initial normal speed */
+int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, double* disp3, double* duration,
+                         double* relvel_init, size_t capacity, size_t* n);
+int dem_b200_add_history(dem_b200_system* s, uint32_t owner_shape, uint32_t other_shape, const double disp[3],
+                         double duration, double relvel_init);
+int dem_b200_num_walls(const dem_b200_system* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHRONO_B200_DEM_H */

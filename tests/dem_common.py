@@ -1,0 +1,68 @@
+"""Shared builders: the same scene in the CPU oracle and in the CUDA engine (through its C ABI)."""
+import numpy as np
+
+from oracle import pyoracle as po
+
+RHO = 2000.0
+MASS_COEF = 4.0 / 3.0 * np.pi * RHO
+
+
+def sphere_mass(radius, mass_coef=MASS_COEF):
+    """Same expression (and rounding sequence) as sphere_mass() in chrono_b200/csrc/dem_kernels.cuh."""
+    r = np.asarray(radius, dtype=np.float64)
+    return mass_coef * (r * r * r)
+
+
+def settling_material(mu=0.4, cr=0.4, young=2e6, mu_roll=0.0, mu_spin=0.0, adhesion=0.0):
+    """btest_MCORE_settling.cpp:80-92"""
+    return dict(young=young, poisson=0.3, mu_s=mu, mu_roll=mu_roll, mu_spin=mu_spin, cr=cr, adhesion=adhesion)
+
+
+def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
+                num_threads=0, **model):
+    mat = mat or settling_material()
+    s = po.make_settings(dt=dt, bins=scene["bins"], gravity=gravity, num_threads=num_threads, **model)
+    o = po.Oracle(s)
+    m_s = o.add_material(po.make_material(**mat))
+    m_w = o.add_material(po.make_material(**(wall_mat or mat)))
+    # body 0: the container (fixed), boxes first -> shapes 0..nW-1
+    if scene["walls"]:
+        o.add_body(wall_mass, (1, 1, 1), (0, 0, 0), fixed=True)
+        for p, h in scene["walls"]:
+            o.add_box(0, m_w, p, h)
+    first = o.add_spheres(scene["pos"], scene["radius"], sphere_mass(scene["radius"]), m_s, vel=vel, omega=omega)
+    o.first_sphere_body = first
+    o.num_walls = len(scene["walls"])
+    return o
+
+
+def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
+             integrator=None, history_slots=12, **model):
+    from chrono_b200 import dem
+    mat = mat or settling_material()
+    kw = dict(model)
+    cfg = dem.config(dt=dt, bins=scene["bins"], gravity=gravity, mat_sphere=dem.material(**mat),
+                     mat_wall=dem.material(**(wall_mat or mat)), mass_coef=MASS_COEF, wall_mass=wall_mass,
+                     integrator=dem.CENTERED_DIFFERENCE if integrator is None else integrator,
+                     history_slots=history_slots, **kw)
+    g = dem.DemSystem(cfg)
+    for p, h in scene["walls"]:
+        g.add_box_wall(p, h)
+    g.set_spheres(scene["pos"], scene["radius"], vel=vel, omega=omega)
+    g.initialize()
+    return g
+
+
+def oracle_sphere_state(o):
+    pos, rot, vel, om = o.state()
+    f = o.first_sphere_body
+    return pos[f:], vel[f:], om[f:]
+
+
+def rel_err(a, b):
+    """max over spheres of |a-b| / max(|b|, floor) on vector norms (not on near-zero components)."""
+    a, b = np.asarray(a), np.asarray(b)
+    d = np.linalg.norm(a - b, axis=-1)
+    n = np.linalg.norm(b, axis=-1)
+    floor = max(n.max(), 1e-300) * 1e-6
+    return float((d / np.maximum(n, floor)).max())
