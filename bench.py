@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Benchmark of the SMC granular DEM hot path (sphere-steps/s), bench contract of the graft driver.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--spheres M] [--substeps S]
+
+Workload (BASELINE.json configs[1]): M = 1,000,000 monodisperse spheres (R = 0.02 m, rho = 2000, Y = 2e6, mu = 0.4,
+COR = 0.4), Hertz-Mindlin with MultiStep tangential history, five-wall box, h = 1e-4 s.  The packing is synthetic:
+a jittered HCP lattice at spacing 2R, i.e. about half of the 12 lattice neighbours overlap -> c_bar ~ 6 contacts per
+sphere from the first step, identical for the GPU arm and the CPU reference arm (no settling phase needed).
+
+One bench "step" = one AdvanceSimulation-style call of S DEM time steps (default 100, a typical output-frame
+cadence).  value = M*S*K / device time with the state resident in HBM; e2e = same through the host-buffer C-ABI
+call dem_b200_advance_host (H2D of pos/vel/omega + S steps + D2H, every bench step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+RADIUS = 0.02
+DT = 1e-4
+KERNELS_PER_TIMESTEP = 8  # launches of our own kernels per DEM time step (memset excluded)
+
+
+def build_scene(n):
+    from chrono_b200 import scenes
+    return scenes.settling_scene(n, radius=RADIUS, sep_factor=2.0, jitter=0.005, seed=12345 + 1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nme, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_oracle_run(scene, timesteps, threads=0):
+    """Times the CPU oracle (restatement of Chrono::Multicore SMC) on the same packing for `timesteps` steps."""
+    import dem_common as common
+    from oracle import pyoracle as po
+    o = common.make_oracle(scene, dt=DT, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP, num_threads=threads)
+    o.step(1)  # untimed: first-touch of all arrays
+    o.reset_timers()
+    t0 = time.perf_counter()
+    rc = o.step(timesteps)
+    t1 = time.perf_counter()
+    assert rc == 0
+    return scene["n"] * timesteps / (t1 - t0), po.lib().orc_max_threads() if threads == 0 else threads, o.timers()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port of ChSystemMulticoreSMC; the real
+    class cannot be built here because Chrono core needs Eigen3), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import dem_common as common
+    from oracle import pyoracle as po
+    n = args.spheres
+    scene = build_scene(n)
+    sample_steps = args.ref_substeps
+    o = common.make_oracle(scene, dt=DT, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP)
+    cores = po.lib().orc_max_threads()
+    for _ in range(args.warmup):
+        o.step(sample_steps)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step(sample_steps)
+    t1 = time.perf_counter()
+    val = n * sample_steps * args.steps / (t1 - t0)
+    line = {
+        "impl": "reference", "metric": "sphere-steps/sec", "value": val, "unit": "sphere-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, sample_steps, args.gpus),
+        "cpu_baseline": {"value": val, "unit": "sphere-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d spheres x %d time steps per bench step (same packing as the GPU arm)" % (n, sample_steps)},
+        "e2e": {"value": val, "unit": "sphere-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n, substeps, gpus):
+    return {"workload": "BASELINE configs[1]: %d spheres Hertz-Mindlin MultiStep history in a 5-wall box, jittered HCP "
+                        "packing at 2R spacing (c_bar~6), R=0.02 rho=2000 Y=2e6 mu=0.4 cr=0.4 h=1e-4" % n,
+            "spheres_per_gpu": n, "timesteps_per_step": substeps,
+            "l2_policy": "working set (>=300 B/sphere x %d spheres) exceeds the 126 MB L2; no explicit flush" % n,
+            "parallelism": "1 process per GPU" if gpus == 1 else "slab decomposition, %d ranks" % gpus}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from chrono_b200 import dem
+    import dem_common as common
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    n = args.spheres
+    S = args.substeps
+    scene = build_scene(n)
+    g = common.make_gpu(scene, dt=DT, force_model=dem.HERTZ, tangential_mode=dem.TANG_MULTISTEP)
+    g.L.dem_b200_step  # the CUDA extension is loaded; there is no other path
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        g.step(S, sync=False)
+    g.sync()
+    barrier()
+    # ---- timed region: K bench steps, device time from CUDA events on the engine's own stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms_total += g.step_timed(S)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * n * S * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, every bench step
+    pos, vel, om = g.state()
+    hp = [torch.from_numpy(a.copy()).pin_memory().numpy() for a in (pos, vel, om)]
+    ho = [torch.empty(a.shape, dtype=torch.float64).pin_memory().numpy() for a in (pos, vel, om)]
+    g.advance_host(hp[0], hp[1], hp[2], S, ho[0], ho[1], ho[2])  # warm
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g.advance_host(hp[0], hp[1], hp[2], S, ho[0], ho[1], ho[2])
+        for a, b in zip(hp, ho):
+            a[...] = b  # next call starts from this call's result (host side hand-over, as a caller would)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * n * S * e2e_steps / t_e2e
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    bytes_io = int(3 * pos.nbytes)
+
+    # ---- per-kernel split of one time step (events around every launch) and contact statistics
+    prof = g.step_profile(20)
+    prof = {k: v / 20 for k, v in prof.items()}
+    g.enable_recording(True, max_pairs=16 * n)
+    g.step(1)
+    npairs = len(g.pairs())
+    g.enable_recording(False)
+    import ctypes as C
+    cbar = None
+    try:
+        rows = g.reduce(dem.RED_NUM_CONTACTS)
+        cbar = 2.0 * npairs / n  # every pair is a contact for both partners (wall contacts count once; << 1 %)
+    except Exception:
+        rows = None
+    hbm, hbm_src = peaks()
+    dom = max(prof, key=prof.get)
+    # algorithmic bytes of the dominant kernel (narrowphase + force + integrate): state R+W 144, radius/id 16,
+    # history 32*c_bar (SURVEY 8d minus the 16 B/sphere that belong to the sort kernels)
+    B_kernel = 160.0 + 32.0 * (cbar or 6.0)
+    B_step = 176.0 + 32.0 * (cbar or 6.0)
+    achieved = B_kernel * n / (prof[dom] * 1e-3) / 1e9
+    step_ms = sum(prof.values())
+
+    if rank == 0:
+        cpu_val, cpu_cores, cpu_t = cpu_oracle_run(scene, args.cpu_steps) if args.cpu_steps > 0 else (None, 0, {})
+        line = {
+            "metric": "sphere-steps/sec", "value": value, "unit": "sphere-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n, S, world),
+            "contacts_per_sphere": cbar, "history_rows": rows,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "kernel": dom, "kernel_ms": prof[dom], "peak_source": hbm_src,
+                         "algorithmic_bytes_per_sphere": B_kernel,
+                         "whole_step_frac": B_step * (value / world) / 1e9 / hbm},
+            "kernel_ms_per_timestep": prof, "kernel_share": {k: v / step_ms for k, v in prof.items()},
+            "cpu_baseline": {"value": cpu_val, "unit": "sphere-steps/s", "cores": cpu_cores, "kind": "port",
+                             "sample": "%d spheres x %d time steps of the same packing" % (n, args.cpu_steps),
+                             "phase_seconds": cpu_t},
+            "e2e": {"value": e2e_value, "unit": "sphere-steps/s", "h2d_bytes_per_step": bytes_io,
+                    "d2h_bytes_per_step": bytes_io, "steps": e2e_steps},
+            "gpu_launches": int(args.steps * S * KERNELS_PER_TIMESTEP),
+            "clocks": sampler.result(), "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spheres", type=int, default=1000000, help="spheres per GPU")
+    ap.add_argument("--substeps", type=int, default=100, help="DEM time steps per bench step")
+    ap.add_argument("--ref-substeps", type=int, default=2, help="time steps per bench step of the reference arm")
+    ap.add_argument("--cpu-steps", type=int, default=4, help="time steps of the cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,7 +19,7 @@ def settling_material(mu=0.4, cr=0.4, young=2e6, mu_roll=0.0, mu_spin=0.0, adhes
 
 
 def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
-                num_threads=0, **model):
+                num_threads=0, history_slots=None, integrator=None, **model):
     mat = mat or settling_material()
     s = po.make_settings(dt=dt, bins=scene["bins"], gravity=gravity, num_threads=num_threads, **model)
     o = po.Oracle(s)
