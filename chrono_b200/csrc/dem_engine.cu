@@ -4,8 +4,9 @@
 // Replaces, for the hot path, ChSystemDem_impl::initializeSpheres / AdvanceSimulation / getters
 // (reference: src/chrono_dem/physics/ChSystemDem_impl.cpp:1130-1166, src/chrono_dem/gpu/ChDemSMC.cu:619-691).
 // Unlike the reference there is no managed memory, no device synchronisation between kernels and no host
-// round trip inside a step: the 9 launches of a step are enqueued on one stream and replayed from a CUDA graph
-// holding two steps (the contact-history double buffer has period two).
+// round trip inside a step: the launches of a step are enqueued on one stream and replayed from a CUDA graph.
+// Every per-step decision (rebuild the Verlet candidate lists or not, which ping-pong buffer is live) is taken on
+// the device (Ctrl block, k_step_begin), so the same one-step graph is valid for every step.
 // =============================================================================
 #include <cuda_runtime.h>
 
@@ -35,8 +36,8 @@ struct dem_b200_system {
     bool any_fixed = false;
     bool initialized = false;
     cudaStream_t stream = nullptr;
-    unsigned ncell = 0, ntiles = 0;
-    cudaGraphExec_t graph2 = nullptr;  // two steps
+    unsigned ntiles = 0;               // scan tiles covering the search-cell capacity
+    cudaGraphExec_t graph1 = nullptr;  // one step
     bool recording = false;
     size_t max_pairs = 0;
     bool use_hrel = false;
@@ -99,6 +100,7 @@ Comp make_comp(const dem_b200_material& m1, const dem_b200_material& m2) {
     double loge = (c.cr < eps) ? std::log(eps) : std::log(c.cr);
     double beta = loge / std::sqrt(loge * loge + kPI * kPI);
     c.hertz_damp = -2 * std::sqrt(5.0 / 6) * beta;
+    c.gt_ratio = std::sqrt(4.0 * c.G_eff / c.E_eff);  // sqrt(St / Sn), :279-280
     return c;
 }
 
@@ -115,7 +117,8 @@ void abs_rotate(const double q[4], const double v[3], double out[3]) {
 void refresh_params(dem_b200_system* s) {
     const dem_b200_config& c = s->cfg;
     Params& P = s->P;
-    P.K = c.history_slots > 0 ? c.history_slots : 12;
+    P.K = c.history_slots > 0 ? std::min(c.history_slots, kMaxSlots) : 16;
+    P.Kn = c.neighbor_slots > 0 ? std::min(c.neighbor_slots, kMaxNeighbors) : 32;
     P.force_model = c.force_model;
     P.adhesion_model = c.adhesion_model;
     P.tang_mode = c.tangential_mode;
@@ -157,6 +160,11 @@ void refresh_params(dem_b200_system* s) {
         P.has_wall_bb = 1;
     }
     P.shape_base = (unsigned)P.nW;
+    // Verlet skin: negative -> default 0.25 * largest radius (set at initialize, when radii are known)
+    if (c.verlet_skin >= 0)
+        P.skin = c.verlet_skin;
+    else
+        P.skin = 0.25 * P.rmax;
 }
 
 bool need_roll(const dem_b200_system* s) {
@@ -166,23 +174,34 @@ bool need_roll(const dem_b200_system* s) {
     return false;
 }
 
+bool fast_path(const dem_b200_system* s) {
+    return s->P.force_model == DEMB200_HERTZ && s->P.use_mat_props && s->P.adhesion_model == DEMB200_ADH_CONSTANT;
+}
+
 template <bool REC>
 void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks) {
     const Params& P = s->P;
     const bool hist = (P.tang_mode == DEMB200_TANG_MULTISTEP);
     const bool roll = need_roll(s);
-    if (hist) {
-        if (roll) k_force_integrate<true, true, REC><<<blocks, kForceThreads, 0, s->stream>>>(P, B);
-        else k_force_integrate<true, false, REC><<<blocks, kForceThreads, 0, s->stream>>>(P, B);
-    } else {
-        if (roll) k_force_integrate<false, true, REC><<<blocks, kForceThreads, 0, s->stream>>>(P, B);
-        else k_force_integrate<false, false, REC><<<blocks, kForceThreads, 0, s->stream>>>(P, B);
+    const bool fast = fast_path(s);
+    const int sel = (hist ? 4 : 0) | (roll ? 2 : 0) | (fast ? 1 : 0);
+#define LF(H, R, F) k_force_integrate<H, R, F, REC><<<blocks, kForceThreads, 0, s->stream>>>(P, B)
+    switch (sel) {
+        case 0: LF(false, false, false); break;
+        case 1: LF(false, false, true); break;
+        case 2: LF(false, true, false); break;
+        case 3: LF(false, true, true); break;
+        case 4: LF(true, false, false); break;
+        case 5: LF(true, false, true); break;
+        case 6: LF(true, true, false); break;
+        default: LF(true, true, true); break;
     }
+#undef LF
 }
 
 constexpr int kNumKernels = 9;
-const char* kKernelNames[kNumKernels] = {"k_grid_update", "memset_bin_count", "k_bin_count", "k_scan_tile_sums",
-                                         "k_scan_sums", "k_scan_apply", "k_scatter_perm", "k_gather_sorted",
+const char* kKernelNames[kNumKernels] = {"k_step_begin", "k_bin_count", "k_scan_tile_sums", "k_scan_sums",
+                                         "k_scan_apply", "k_scatter_perm", "k_gather_sorted", "k_build_list",
                                          "k_force_integrate"};
 
 // Enqueue one step.  ev: optional kNumKernels+1 events recorded around each launch (profiling).
@@ -198,52 +217,41 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
             cudaEventRecord(ev[k++], st);
     };
     mark();
-    k_grid_update<<<1, 32, 0, st>>>(P, B);
+    k_step_begin<<<1, 32, 0, st>>>(P, B);
     mark();
-    CU(cudaMemsetAsync(B.cell_count, 0, sizeof(uint32_t) * s->ncell, st));
-    if (s->recording) {
-        CU(cudaMemsetAsync(B.pair_count, 0, sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(B.n_contacts, 0, sizeof(unsigned long long), st));
-    }
+    // the rebuild kernels return immediately unless k_step_begin decided that the Verlet skin is used up
+    k_bin_count<<<nb256, 256, 0, st>>>(P, B);
     mark();
-    if (s->recording)
-        k_bin_count<true><<<nb256, 256, 0, st>>>(P, B);
-    else
-        k_bin_count<false><<<nb256, 256, 0, st>>>(P, B);
+    k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(B);
     mark();
-    k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(s->ncell, B.cell_count, B.block_sums);
+    k_scan_sums<<<1, kScanThreads, 0, st>>>(B);
     mark();
-    k_scan_sums<<<1, kScanThreads, 0, st>>>(s->ntiles, B.block_sums);
-    mark();
-    k_scan_apply<<<s->ntiles, kScanThreads, 0, st>>>(s->ncell, N, B.cell_count, B.block_sums, B.cell_start);
+    k_scan_apply<<<s->ntiles, kScanThreads, 0, st>>>(P, B);
     mark();
     k_scatter_perm<<<nb256, 256, 0, st>>>(P, B);
     mark();
-    if (P.integrator == DEMB200_CHUNG)
-        k_gather_sorted<true><<<nb256, 256, 0, st>>>(P, B);
-    else
-        k_gather_sorted<false><<<nb256, 256, 0, st>>>(P, B);
+    k_gather_sorted<<<nb256, 256, 0, st>>>(P, B);
+    mark();
+    k_build_list<<<(N + kListThreads - 1) / kListThreads, kListThreads, 0, st>>>(P, B);
     mark();
     const unsigned fb = (N + kForceThreads - 1) / kForceThreads;
-    if (s->recording)
+    if (s->recording) {
+        k_record_bins<<<nb256, 256, 0, st>>>(P, B);
         launch_force<true>(s, B, fb);
-    else
+    } else {
         launch_force<false>(s, B, fb);
+    }
     mark();
     CU(cudaGetLastError());
-    // the history written this step is next step's input
-    std::swap(B.hkey_old, B.hkey_new);
-    std::swap(B.hval_old, B.hval_new);
-    std::swap(B.hrel_old, B.hrel_new);
     s->time += P.dt;
     s->export_valid = false;
     return 0;
 }
 
 void drop_graph(dem_b200_system* s) {
-    if (s->graph2) {
-        cudaGraphExecDestroy(s->graph2);
-        s->graph2 = nullptr;
+    if (s->graph1) {
+        cudaGraphExecDestroy(s->graph1);
+        s->graph1 = nullptr;
     }
 }
 
@@ -252,8 +260,6 @@ int build_graph(dem_b200_system* s) {
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     double t = s->time;
     int rc = enqueue_step(s, nullptr);
-    if (rc == 0)
-        rc = enqueue_step(s, nullptr);
     s->time = t;  // capturing does not advance time
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
     if (rc)
@@ -262,25 +268,30 @@ int build_graph(dem_b200_system* s) {
         s->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e);
         return DEMB200_ECUDA;
     }
-    CU(cudaGraphInstantiate(&s->graph2, g, 0));
+    CU(cudaGraphInstantiate(&s->graph1, g, 0));
     cudaGraphDestroy(g);
     return 0;
 }
 
 int check_device_error(dem_b200_system* s) {
     unsigned e = 0;
-    CU(cudaMemcpyAsync(s->h_pin, s->B.err, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_pin, &s->B.ctrl->err, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(&e, s->h_pin, sizeof(unsigned));
     if (!e)
         return 0;
     if (e & ERR_NAN) { s->err = "non-finite sphere state"; return DEMB200_ENAN; }
-    if (e & ERR_GRID_BIN_TOO_SMALL) { s->err = "broadphase bin edge smaller than the largest sphere diameter"; return DEMB200_EGRID; }
-    if (e & ERR_GRID_OUT_OF_RANGE) { s->err = "sphere outside the broadphase grid"; return DEMB200_EGRID; }
-    if (e & (ERR_HISTORY_OVERFLOW | ERR_CONTACT_LIST_OVERFLOW)) { s->err = "contact history slots exhausted"; return DEMB200_EHISTORY; }
+    if (e & ERR_HISTORY_OVERFLOW) { s->err = "a sphere has more contacts than history_slots"; return DEMB200_EHISTORY; }
+    if (e & ERR_NEIGHBOR_OVERFLOW) { s->err = "a sphere has more neighbour candidates than neighbor_slots"; return DEMB200_ENEIGHBORS; }
     if (e & ERR_PAIR_CAPACITY) { s->err = "pair recording buffer overflow"; return DEMB200_ECAPACITY; }
     s->err = "unknown device error";
     return DEMB200_ECUDA;
+}
+
+int read_ctrl(dem_b200_system* s, Ctrl* out) {
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(out, s->B.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int recompute_bbox(dem_b200_system* s) {
@@ -289,9 +300,9 @@ int recompute_bbox(dem_b200_system* s) {
         init[k] = s->P.has_wall_bb ? enc_ord_h(s->P.wall_bb_min[k]) : enc_ord_h(INFINITY);
         init[3 + k] = s->P.has_wall_bb ? enc_ord_h(s->P.wall_bb_max[k]) : enc_ord_h(-INFINITY);
     }
-    CU(cudaMemcpyAsync(s->B.bbox, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->B.ctrl->bbox, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));  // init[] is on the stack
-    k_bbox_reduce<<<(s->P.N + 255) / 256, 256, 0, s->stream>>>(s->P.N, s->B.posA, s->B.bbox);
+    k_bbox_reduce<<<(s->P.N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B);
     CU(cudaGetLastError());
     return 0;
 }
@@ -312,14 +323,14 @@ int run_steps(dem_b200_system* s, int nsteps) {
     }
     int done = 0;
     if (!s->recording && nsteps >= 2) {
-        if (!s->graph2) {
+        if (!s->graph1) {
             int rc = build_graph(s);
             if (rc)
                 return rc;
         }
-        for (; done + 2 <= nsteps; done += 2) {
-            CU(cudaGraphLaunch(s->graph2, s->stream));
-            s->time += 2 * s->P.dt;
+        for (; done < nsteps; done++) {
+            CU(cudaGraphLaunch(s->graph1, s->stream));
+            s->time += s->P.dt;
         }
         s->export_valid = false;
     }
@@ -327,8 +338,6 @@ int run_steps(dem_b200_system* s, int nsteps) {
         int rc = enqueue_step(s, nullptr);
         if (rc)
             return rc;
-        // an odd direct step flips the history buffers relative to the captured graph
-        drop_graph(s);
     }
     return 0;
 }
@@ -394,18 +403,26 @@ int dem_b200_set_config(dem_b200_system* s, const dem_b200_config* cfg) {
         return DEMB200_EINVAL;
     if (s->initialized) {
         const dem_b200_config& o = s->cfg;
-        const int Kold = o.history_slots > 0 ? o.history_slots : 12, Knew = cfg->history_slots > 0 ? cfg->history_slots : 12;
-        if (Kold != Knew || o.bins_per_axis[0] != cfg->bins_per_axis[0] || o.bins_per_axis[1] != cfg->bins_per_axis[1] ||
-            o.bins_per_axis[2] != cfg->bins_per_axis[2] || o.device != cfg->device ||
+        if (o.history_slots != cfg->history_slots || o.neighbor_slots != cfg->neighbor_slots || o.device != cfg->device ||
             (o.integrator != cfg->integrator && (o.integrator == DEMB200_CHUNG || cfg->integrator == DEMB200_CHUNG)) ||
-            o.tangential_mode != cfg->tangential_mode) {
-            s->err = "set_config: history_slots, bins_per_axis, device, tangential_mode and (to/from) Chung cannot change after initialize";
+            o.tangential_mode != cfg->tangential_mode || o.force_model != cfg->force_model ||
+            o.use_mat_props != cfg->use_mat_props) {
+            s->err = "set_config: history_slots, neighbor_slots, device, tangential_mode, force_model, use_mat_props and "
+                     "(to/from) Chung cannot change after initialize";
             return DEMB200_EINVAL;
         }
     }
+    const double old_skin = s->P.skin;
     s->cfg = *cfg;
     refresh_params(s);
     drop_graph(s);
+    if (s->initialized && s->P.skin > old_skin) {
+        // a larger skin needs longer candidate lists: rebuild at the next step
+        CU(cudaSetDevice(s->cfg.device));
+        const unsigned one = 1;
+        CU(cudaMemcpyAsync(&s->B.ctrl->need_rebuild, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     return 0;
 }
 
@@ -498,107 +515,149 @@ int dem_b200_initialize(dem_b200_system* s) {
         return DEMB200_EINVAL;
     }
     CU(cudaSetDevice(s->cfg.device));
-    refresh_params(s);
     Params& P = s->P;
     Buffers& B = s->B;
     P.N = (unsigned)n;
-    const long long nc = (long long)P.bins[0] * P.bins[1] * P.bins[2];
-    if (P.bins[0] < 1 || P.bins[1] < 1 || P.bins[2] < 1 || nc >= (1ll << 31)) {
+    P.Np = (unsigned)((n + 31) / 32 * 32);
+    P.rmax = *std::max_element(s->h_rad.begin(), s->h_rad.end());
+    refresh_params(s);
+    if (P.bins[0] < 1 || P.bins[1] < 1 || P.bins[2] < 1) {
         s->err = "bad bins_per_axis";
         return DEMB200_EINVAL;
     }
-    s->ncell = (unsigned)nc;
-    s->ntiles = (s->ncell + kScanTile - 1) / kScanTile;
-    P.rmax = *std::max_element(s->h_rad.begin(), s->h_rad.end());
-    const size_t K = (size_t)P.K;
+    if (!(P.rmax > 0) || !(P.skin >= 0)) {
+        s->err = "bad radius / verlet_skin";
+        return DEMB200_EINVAL;
+    }
+    // capacity of the search grid: twice the cells of the initial bounding box (spheres + walls); if the bed ever
+    // spreads beyond that, k_step_begin coarsens the cells instead of overflowing
+    {
+        double mn[3], mx[3];
+        for (int k = 0; k < 3; k++) {
+            mn[k] = P.has_wall_bb ? P.wall_bb_min[k] : INFINITY;
+            mx[k] = P.has_wall_bb ? P.wall_bb_max[k] : -INFINITY;
+        }
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) {
+                mn[k] = std::min(mn[k], s->h_pos[3 * i + k] - s->h_rad[i]);
+                mx[k] = std::max(mx[k], s->h_pos[3 * i + k] + s->h_rad[i]);
+            }
+        const double e = 2.0 * P.rmax + P.skin;
+        double cells = 1.0;
+        for (int k = 0; k < 3; k++)
+            cells *= std::max(1.0, std::floor((mx[k] - mn[k]) / e) + 1.0);
+        cells = std::min(std::max(2.0 * cells, 4096.0), std::max(4096.0, 16.0 * (double)n));
+        P.cell_cap = (unsigned)cells;
+    }
+    s->ntiles = (P.cell_cap + kScanTile - 1) / kScanTile;
+    const size_t K = (size_t)P.K, Np = P.Np;
     const bool hist = (P.tang_mode == DEMB200_TANG_MULTISTEP);
     s->use_hrel = hist && P.use_mat_props && (P.force_model == DEMB200_HOOKE || P.force_model == DEMB200_FLORES);
 
     int rc = 0;
-    rc |= dev_alloc(s, &B.posA, n); rc |= dev_alloc(s, &B.posB, n);
-    rc |= dev_alloc(s, &B.velA, 6 * n); rc |= dev_alloc(s, &B.velB, 6 * n);
-    rc |= dev_alloc(s, &B.sidA, n); rc |= dev_alloc(s, &B.sidB, n);
-    if (P.integrator == DEMB200_CHUNG) {
-        rc |= dev_alloc(s, &B.accA, 6 * n); rc |= dev_alloc(s, &B.accB, 6 * n);
-    }
-    rc |= dev_alloc(s, &B.cell, n); rc |= dev_alloc(s, &B.rank, n); rc |= dev_alloc(s, &B.perm, n);
-    rc |= dev_alloc(s, &B.cell_count, (size_t)s->ncell + 8); rc |= dev_alloc(s, &B.cell_start, (size_t)s->ncell + 8);
-    rc |= dev_alloc(s, &B.block_sums, (size_t)s->ntiles + 8);
-    rc |= dev_alloc(s, &B.grid, 1); rc |= dev_alloc(s, &B.bbox, 8); rc |= dev_alloc(s, &B.err, 4);
-    rc |= dev_alloc(s, &B.n_contacts, 2); rc |= dev_alloc(s, &B.pair_count, 2);
-    if (hist) {
-        rc |= dev_alloc(s, &B.hkey_old, n * K); rc |= dev_alloc(s, &B.hkey_new, n * K);
-        rc |= dev_alloc(s, &B.hval_old, n * K); rc |= dev_alloc(s, &B.hval_new, n * K);
-        if (s->use_hrel) {
-            rc |= dev_alloc(s, &B.hrel_old, n * K); rc |= dev_alloc(s, &B.hrel_new, n * K);
+    rc |= dev_alloc(s, &B.ctrl, 1);
+    for (int b = 0; b < 2; b++) {
+        rc |= dev_alloc(s, &B.pos[b], Np);
+        rc |= dev_alloc(s, &B.vel[b], Np);
+        if (P.integrator == DEMB200_CHUNG)
+            rc |= dev_alloc(s, &B.acc[b], 6 * Np);
+        if (hist) {
+            rc |= dev_alloc(s, &B.hist[b], K * Np);
+            if (s->use_hrel)
+                rc |= dev_alloc(s, &B.hrel[b], K * Np);
         }
     }
-    if (s->any_fixed)
-        rc |= dev_alloc(s, &B.flags, n);
+    rc |= dev_alloc(s, &B.cell, Np); rc |= dev_alloc(s, &B.rank, Np); rc |= dev_alloc(s, &B.perm, Np);
+    rc |= dev_alloc(s, &B.cell_count, (size_t)P.cell_cap + 8); rc |= dev_alloc(s, &B.cell_start, (size_t)P.cell_cap + 8);
+    rc |= dev_alloc(s, &B.block_sums, (size_t)s->ntiles + 8);
+    rc |= dev_alloc(s, &B.nl, (size_t)P.Kn * Np); rc |= dev_alloc(s, &B.ncnt, Np);
     rc |= dev_alloc(s, &s->d_pos3, 3 * n); rc |= dev_alloc(s, &s->d_vel3, 3 * n); rc |= dev_alloc(s, &s->d_om3, 3 * n);
     rc |= dev_alloc(s, &s->d_red, 4);
     if (rc)
         return DEMB200_ECUDA;
 
-    // upload (storage order = user order initially; the first step sorts by bin)
+    // history supplied before initialize (checkpoint restart): every sphere taking part in a contact gets a record,
+    // columns ordered by key (walls first, then partner shape ids)
+    std::vector<std::vector<dem_b200_system::HRow>> rows;
+    if (hist && !s->h_hist.empty()) {
+        rows.resize(n);
+        for (auto& r : s->h_hist) {
+            if (r.owner < P.shape_base || r.owner - P.shape_base >= n) {
+                s->err = "add_history: owner is not a sphere shape";
+                return DEMB200_EINVAL;
+            }
+            const size_t so = r.owner - P.shape_base;
+            rows[so].push_back(r);  // key = other
+            if (r.other >= P.shape_base) {
+                if (r.other - P.shape_base >= n) {
+                    s->err = "add_history: bad partner shape id";
+                    return DEMB200_EINVAL;
+                }
+                dem_b200_system::HRow m = r;
+                m.other = r.owner;  // the partner's copy is keyed by the owner's shape id
+                rows[r.other - P.shape_base].push_back(m);
+            }
+        }
+        for (auto& v : rows) {
+            std::sort(v.begin(), v.end(), [](const dem_b200_system::HRow& a, const dem_b200_system::HRow& b) { return a.other < b.other; });
+            if (v.size() > K) {
+                s->err = "add_history: too many rows for one sphere";
+                return DEMB200_EHISTORY;
+            }
+        }
+    }
+
+    // upload (storage order = user order initially; the first step sorts by search cell)
     {
-        std::vector<double4> hp(n);
-        std::vector<double> hv(6 * n);
-        std::vector<uint32_t> hs(n);
+        std::vector<double4> hp(Np, make_double4(0, 0, 0, 1));
+        std::vector<VelRec> hv(Np);
+        memset(hv.data(), 0, Np * sizeof(VelRec));
         for (size_t i = 0; i < n; i++) {
             hp[i] = make_double4(s->h_pos[3 * i], s->h_pos[3 * i + 1], s->h_pos[3 * i + 2], s->h_rad[i]);
             for (int k = 0; k < 3; k++) {
-                hv[6 * i + k] = s->h_vel[3 * i + k];
-                hv[6 * i + 3 + k] = s->h_om[3 * i + k];
+                hv[i].v[k] = s->h_vel[3 * i + k];
+                hv[i].w[k] = s->h_om[3 * i + k];
             }
-            hs[i] = (uint32_t)i;
+            hv[i].sid = (uint32_t)i;
+            hv[i].meta = (rows.empty() ? 0u : (unsigned)rows[i].size()) | ((s->h_fixed[i] ? 1u : 0u) << 8);
         }
-        CU(cudaMemcpy(B.posA, hp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(B.velA, hv.data(), 6 * n * sizeof(double), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(B.sidA, hs.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        if (B.accA) {
-            CU(cudaMemset(B.accA, 0, 6 * n * sizeof(double)));
-            CU(cudaMemset(B.accB, 0, 6 * n * sizeof(double)));
+        for (int b = 0; b < 2; b++) {
+            CU(cudaMemcpy(B.pos[b], hp.data(), Np * sizeof(double4), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(B.vel[b], hv.data(), Np * sizeof(VelRec), cudaMemcpyHostToDevice));
+            if (B.acc[b])
+                CU(cudaMemset(B.acc[b], 0, 6 * Np * sizeof(double)));
+            if (B.hist[b])
+                CU(cudaMemset(B.hist[b], 0xFF, K * Np * sizeof(double4)));
+            if (B.hrel[b])
+                CU(cudaMemset(B.hrel[b], 0, K * Np * sizeof(double)));
         }
-        if (B.flags)
-            CU(cudaMemcpy(B.flags, s->h_fixed.data(), n, cudaMemcpyHostToDevice));
     }
-    CU(cudaMemset(B.err, 0, 4 * sizeof(unsigned)));
-    if (hist) {
-        CU(cudaMemset(B.hkey_old, 0xFF, n * K * sizeof(uint32_t)));
-        CU(cudaMemset(B.hkey_new, 0xFF, n * K * sizeof(uint32_t)));
-        CU(cudaMemset(B.hval_old, 0, n * K * sizeof(double4)));
-        CU(cudaMemset(B.hval_new, 0, n * K * sizeof(double4)));
-        if (s->use_hrel) {
-            CU(cudaMemset(B.hrel_old, 0, n * K * sizeof(double)));
-            CU(cudaMemset(B.hrel_new, 0, n * K * sizeof(double)));
-        }
-        // history supplied before initialize (checkpoint restart)
-        if (!s->h_hist.empty()) {
-            std::vector<uint32_t> keys(n * K, kEmptyKey);
-            std::vector<double4> vals(n * K, make_double4(0, 0, 0, 0));
-            std::vector<double> rels(n * K, 0.0);
-            std::vector<int> fill(n, 0);
-            for (auto& r : s->h_hist) {
-                if (r.owner < P.shape_base || r.owner - P.shape_base >= n) {
-                    s->err = "add_history: owner is not a sphere shape";
-                    return DEMB200_EINVAL;
-                }
-                size_t sid = r.owner - P.shape_base;
-                if (fill[sid] >= (int)K) {
-                    s->err = "add_history: too many rows for one sphere";
-                    return DEMB200_EHISTORY;
-                }
-                size_t at = sid * K + fill[sid]++;
-                keys[at] = r.other;
-                vals[at] = make_double4(r.d[0], r.d[1], r.d[2], r.dur);
-                rels[at] = r.rel;
+    if (!rows.empty()) {
+        std::vector<double4> hh(K * Np, make_double4(0, 0, 0, 0));
+        std::vector<double> hr(s->use_hrel ? K * Np : 0, 0.0);
+        for (size_t i = 0; i < n; i++)
+            for (size_t k = 0; k < rows[i].size(); k++) {
+                const auto& r = rows[i][k];
+                const unsigned steps = (unsigned)std::llround(r.dur / P.dt);
+                const unsigned long long bits = ((unsigned long long)steps << 32) | r.other;
+                double w;
+                memcpy(&w, &bits, 8);
+                hh[k * Np + i] = make_double4(r.d[0], r.d[1], r.d[2], w);
+                if (s->use_hrel)
+                    hr[k * Np + i] = r.rel;
             }
-            CU(cudaMemcpy(B.hkey_old, keys.data(), n * K * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(B.hval_old, vals.data(), n * K * sizeof(double4), cudaMemcpyHostToDevice));
-            if (s->use_hrel)
-                CU(cudaMemcpy(B.hrel_old, rels.data(), n * K * sizeof(double), cudaMemcpyHostToDevice));
-        }
+        CU(cudaMemcpy(B.hist[0], hh.data(), K * Np * sizeof(double4), cudaMemcpyHostToDevice));
+        if (s->use_hrel)
+            CU(cudaMemcpy(B.hrel[0], hr.data(), K * Np * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemset(B.cell_count, 0, ((size_t)P.cell_cap + 8) * sizeof(uint32_t)));
+    CU(cudaMemset(B.ncnt, 0, Np * sizeof(uint32_t)));
+    {
+        Ctrl c;
+        memset(&c, 0, sizeof(c));
+        c.cur = 0;
+        c.need_rebuild = 1;
+        CU(cudaMemcpy(B.ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice));
     }
     s->h_pos.clear(); s->h_pos.shrink_to_fit();
     s->h_vel.clear(); s->h_vel.shrink_to_fit();
@@ -751,24 +810,12 @@ int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out) {
         return DEMB200_EINVAL;
     CU(cudaSetDevice(s->cfg.device));
     const unsigned N = s->P.N;
-    if (which == DEMB200_RED_NUM_CONTACTS) {
-        if (s->P.tang_mode != DEMB200_TANG_MULTISTEP) {
-            s->err = "NUM_CONTACTS needs MultiStep history (or use recording)";
-            return DEMB200_EINVAL;
-        }
-        CU(cudaMemsetAsync(s->d_red, 0, 16, s->stream));
-        unsigned long long tot = (unsigned long long)N * s->P.K;
-        k_count_history<<<(unsigned)((tot + 255) / 256), 256, 0, s->stream>>>(tot, s->B.hkey_old,
-                                                                               (unsigned long long*)s->d_red);
-        CU(cudaMemcpyAsync(s->h_pin, s->d_red, 8, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        unsigned long long c;
-        memcpy(&c, s->h_pin, 8);
-        *out = (double)c;
-        return 0;
-    }
-    if (which < 0 || which > 5)
+    if (which < 0 || which > 6)
         return DEMB200_EINVAL;
+    if (which == DEMB200_RED_NUM_CONTACTS && s->P.tang_mode != DEMB200_TANG_MULTISTEP) {
+        s->err = "NUM_CONTACTS needs MultiStep history (or use recording)";
+        return DEMB200_EINVAL;
+    }
     unsigned long long init[2] = {0ull, enc_ord_h(-INFINITY)};
     memcpy(s->h_pin + 12, init, 16);
     CU(cudaMemcpyAsync(s->d_red, s->h_pin + 12, 16, cudaMemcpyHostToDevice, s->stream));
@@ -777,7 +824,7 @@ int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s->h_pin, s->d_red, 16, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    if (which == 2 || which == 4 || which == 5) {
+    if (which == 2 || which >= 4) {
         *out = s->h_pin[0];
     } else {
         unsigned long long u;
@@ -830,7 +877,7 @@ int dem_b200_get_pairs(dem_b200_system* s, uint64_t* pairs, size_t capacity, siz
     if (!s || !s->initialized || !s->B.pairs || !n)
         return DEMB200_EINVAL;
     CU(cudaSetDevice(s->cfg.device));
-    CU(cudaMemcpyAsync(s->h_pin, s->B.pair_count, 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_pin, &s->B.ctrl->pair_count, 8, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     unsigned long long c;
     memcpy(&c, s->h_pin, 8);
@@ -862,14 +909,30 @@ int dem_b200_get_grid(dem_b200_system* s, double origin[3], double bin_size[3], 
     if (!s || !s->initialized)
         return DEMB200_EINVAL;
     CU(cudaSetDevice(s->cfg.device));
-    GridDev g;
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaMemcpy(&g, s->B.grid, sizeof(GridDev), cudaMemcpyDeviceToHost));
+    Ctrl c;
+    int rc = read_ctrl(s, &c);
+    if (rc)
+        return rc;
     for (int k = 0; k < 3; k++) {
-        if (origin) origin[k] = g.origin[k];
-        if (bin_size) bin_size[k] = g.bin[k];
-        if (inv_bin_size) inv_bin_size[k] = g.inv[k];
+        if (origin) origin[k] = c.mc.origin[k];
+        if (bin_size) bin_size[k] = c.mc.bin[k];
+        if (inv_bin_size) inv_bin_size[k] = c.mc.inv[k];
     }
+    return 0;
+}
+
+int dem_b200_get_stats(dem_b200_system* s, unsigned long long* nsteps, unsigned long long* nrebuilds,
+                       unsigned long long* contacts_last_step) {
+    if (!s || !s->initialized)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    Ctrl c;
+    int rc = read_ctrl(s, &c);
+    if (rc)
+        return rc;
+    if (nsteps) *nsteps = c.nsteps;
+    if (nrebuilds) *nrebuilds = c.nrebuilds;
+    if (contacts_last_step) *contacts_last_step = c.n_contacts;
     return 0;
 }
 
@@ -881,33 +944,45 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
     if (s->P.tang_mode != DEMB200_TANG_MULTISTEP)
         return 0;
     CU(cudaSetDevice(s->cfg.device));
-    CU(cudaStreamSynchronize(s->stream));
-    const size_t N = s->P.N, K = s->P.K;
-    std::vector<uint32_t> keys(N * K);
-    std::vector<double4> vals(N * K);
+    Ctrl c;
+    int rc = read_ctrl(s, &c);
+    if (rc)
+        return rc;
+    const size_t N = s->P.N, K = s->P.K, Np = s->P.Np;
+    std::vector<VelRec> vr(N);
+    std::vector<double4> vals(K * Np);
     std::vector<double> rels;
-    CU(cudaMemcpy(keys.data(), s->B.hkey_old, N * K * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(vals.data(), s->B.hval_old, N * K * sizeof(double4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vr.data(), s->B.vel[c.cur], N * sizeof(VelRec), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vals.data(), s->B.hist[c.cur], K * Np * sizeof(double4), cudaMemcpyDeviceToHost));
     if (s->use_hrel) {
-        rels.resize(N * K);
-        CU(cudaMemcpy(rels.data(), s->B.hrel_old, N * K * sizeof(double), cudaMemcpyDeviceToHost));
+        rels.resize(K * Np);
+        CU(cudaMemcpy(rels.data(), s->B.hrel[c.cur], K * Np * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    size_t c = 0;
-    for (size_t i = 0; i < N; i++)
-        for (size_t k = 0; k < K; k++) {
-            if (keys[i * K + k] == kEmptyKey)
+    // Both partners of a sphere-sphere contact hold a copy; report the one of the higher shape id, which is where
+    // Chrono::Multicore keeps it (ChIterativeSolverMulticoreSMC.cpp:194-199).
+    size_t cnt = 0;
+    for (size_t i = 0; i < N; i++) {
+        const uint32_t me = s->P.shape_base + vr[i].sid;
+        const size_t hc = vr[i].meta & 0xFFu;
+        for (size_t k = 0; k < hc && k < K; k++) {
+            const double4 v = vals[k * Np + i];
+            unsigned long long bits;
+            memcpy(&bits, &v.w, 8);
+            const uint32_t key = (uint32_t)(bits & 0xFFFFFFFFull), steps = (uint32_t)(bits >> 32);
+            if (key == kEmptyKey || key > me)
                 continue;
-            if (c < capacity) {
-                if (owner) owner[c] = s->P.shape_base + (uint32_t)i;
-                if (other) other[c] = keys[i * K + k];
-                if (disp3) { disp3[3 * c] = vals[i * K + k].x; disp3[3 * c + 1] = vals[i * K + k].y; disp3[3 * c + 2] = vals[i * K + k].z; }
-                if (duration) duration[c] = vals[i * K + k].w;
-                if (relvel_init) relvel_init[c] = s->use_hrel ? rels[i * K + k] : 0.0;
+            if (cnt < capacity) {
+                if (owner) owner[cnt] = me;
+                if (other) other[cnt] = key;
+                if (disp3) { disp3[3 * cnt] = v.x; disp3[3 * cnt + 1] = v.y; disp3[3 * cnt + 2] = v.z; }
+                if (duration) duration[cnt] = (double)steps * s->P.dt;
+                if (relvel_init) relvel_init[cnt] = s->use_hrel ? rels[k * Np + i] : 0.0;
             }
-            c++;
+            cnt++;
         }
-    *n = c;
-    return (c > capacity && (owner || other || disp3)) ? DEMB200_ECAPACITY : 0;
+    }
+    *n = cnt;
+    return (cnt > capacity && (owner || other || disp3)) ? DEMB200_ECAPACITY : 0;
 }
 
 int dem_b200_add_history(dem_b200_system* s, uint32_t owner_shape, uint32_t other_shape, const double disp[3],

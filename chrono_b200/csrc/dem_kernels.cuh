@@ -1,17 +1,23 @@
 // =============================================================================
 // dem_kernels.cuh -- hand-written sm_100a kernels of the SMC granular DEM step.
 //
-// One step (see dem_engine.cu for the launch order):
-//   k_grid_update      1 thread    global AABB -> grid origin / bin size     (ChBroadphase.cpp:143-208)
-//   k_bin_count        N threads   sphere -> bin of its AABB min corner, histogram (ChCollisionUtils.h:44-65)
-//   k_scan_*           ncell       exclusive scan of the histogram (CSR bin starts)
+// One step = one replay of the same CUDA graph (see dem_engine.cu for the launch order):
+//   k_step_begin       1 thread    travel bookkeeping -> "rebuild this step?", Multicore grid of the step
+//                                  (ChBroadphase.cpp:143-208), search grid, ping-pong buffer indices
+//   -- only when the Verlet skin is used up (every kernel below returns at once otherwise) --
+//   k_bin_count        N threads   sphere -> search cell, histogram with warp-aggregated atomics
+//   k_scan_*           ncell       exclusive scan of the histogram (CSR cell starts), self-cleaning
 //   k_scatter_perm     N threads   counting-sort permutation
-//   k_gather_sorted    N threads   re-order posr/velw/sid by bin (deterministic order inside a bin: by sphere id)
-//   k_force_integrate  N threads   narrowphase (sphere-sphere over 27 bins, sphere-wall), Hertz/Hooke/... force law
-//                                  with pair-keyed tangential history, rolling/spinning resistance, gravity and
-//                                  the time integrator -- fused, one pass over the state
-// Everything that decides bin ids or contact-pair membership uses explicitly rounded fp64 intrinsics
-// (__dmul_rn/__dadd_rn/__dsub_rn) so no FMA contraction can change a bit w.r.t. the Multicore arithmetic.
+//   k_gather_sorted    N threads   re-order pos / vel / history columns into cell order
+//   k_build_list       N threads   27-cell scan -> candidate list (r_i + r_j + skin), sorted by stable id
+//   -- every step --
+//   k_force_integrate  N threads   exact narrowphase on the candidates (sphere_sphere, ChNarrowphasePRIMS.cpp:40-72;
+//                                  box_sphere :269-313), Hertz/Hooke/... force law with the pair-keyed tangential
+//                                  history (ChIterativeSolverMulticoreSMC.cpp:56-546), rolling/spinning resistance,
+//                                  gravity and the time integrator -- fused, one pass over the state
+// Everything that decides contact-pair membership or Multicore bin ids uses explicitly rounded fp64 intrinsics
+// (__dmul_rn/__dadd_rn/__dsub_rn) so no FMA contraction can change a bit w.r.t. the Multicore arithmetic.  The
+// force arithmetic itself is free to contract/reassociate: its bar is 1e-9 relative, not bit identity.
 // =============================================================================
 #pragma once
 #include <cuda_runtime.h>
@@ -74,6 +80,33 @@ __device__ __forceinline__ double sphere_mass(const Params& P, double r) {
     return __dmul_rn(P.mass_coef, __dmul_rn(__dmul_rn(r, r), r));
 }
 
+// ---- 64-byte velocity record access (4 x 16-byte transactions) ----
+struct VelVal {
+    V3 v, w;
+    unsigned sid, meta;
+};
+__device__ __forceinline__ VelVal load_vel(const VelRec* __restrict__ a, size_t i) {
+    const double2* q = reinterpret_cast<const double2*>(a + i);
+    const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    VelVal r;
+    r.v = mk(q0.x, q0.y, q1.x);
+    r.w = mk(q1.y, q2.x, q2.y);
+    r.sid = (unsigned)__double2loint(q3.x);
+    r.meta = (unsigned)__double2hiint(q3.x);
+    return r;
+}
+__device__ __forceinline__ void store_vel(VelRec* a, size_t i, V3 v, V3 w, unsigned sid, unsigned meta) {
+    double2* q = reinterpret_cast<double2*>(a + i);
+    q[0] = make_double2(v.x, v.y);
+    q[1] = make_double2(v.z, w.x);
+    q[2] = make_double2(w.y, w.z);
+    q[3] = make_double2(__hiloint2double((int)meta, (int)sid), 0.0);
+}
+// history record: (disp xyz, packed key | steps << 32)
+__device__ __forceinline__ double pack_key(unsigned key, unsigned steps) { return __hiloint2double((int)steps, (int)key); }
+__device__ __forceinline__ unsigned rec_key(double w) { return (unsigned)__double2loint(w); }
+__device__ __forceinline__ unsigned rec_steps(double w) { return (unsigned)__double2hiint(w); }
+
 // --------------------------------------------------------------------------------------------
 // bounding box of all sphere AABBs (init / after set_state); per step it is fused into k_force_integrate
 // --------------------------------------------------------------------------------------------
@@ -101,34 +134,44 @@ __device__ __forceinline__ void block_bbox_commit(double mnx, double mny, double
     }
 }
 
-__global__ void __launch_bounds__(256) k_bbox_reduce(unsigned N, const double4* __restrict__ posr,
-                                                     unsigned long long* bbox) {
+__global__ void __launch_bounds__(256) k_bbox_reduce(Params P, Buffers B) {
+    Ctrl& C = *B.ctrl;
+    const double4* __restrict__ posr = B.pos[C.cur];
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     double mnx = CUDART_INF, mny = CUDART_INF, mnz = CUDART_INF, mxx = -CUDART_INF, mxy = -CUDART_INF, mxz = -CUDART_INF;
-    if (i < N) {
+    if (i < P.N) {
         double4 p = posr[i];
         mnx = p.x - p.w; mny = p.y - p.w; mnz = p.z - p.w;
         mxx = p.x + p.w; mxy = p.y + p.w; mxz = p.z + p.w;
     }
-    block_bbox_commit(mnx, mny, mnz, mxx, mxy, mxz, bbox);
+    block_bbox_commit(mnx, mny, mnz, mxx, mxy, mxz, C.bbox);
 }
 
 // --------------------------------------------------------------------------------------------
-// grid of this step: ChBroadphase::DetermineBoundingBox + ComputeTopLevelResolution (ChBroadphase.cpp:143-208)
+// step control: runs as one thread at the head of every step
 // --------------------------------------------------------------------------------------------
-__global__ void k_grid_update(Params P, Buffers B) {
+__global__ void k_step_begin(Params P, Buffers B) {
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
+    Ctrl& C = *B.ctrl;
+    // ---- Verlet bookkeeping: every sphere moved at most `travel` since the lists were built ----
+    const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
+    C.max_dx2 = 0ull;
+    C.travel += dx;
+    const bool rebuild = (C.need_rebuild != 0) || !(C.travel < 0.499 * P.skin);
+
+    // ---- bounding box of all shapes at the start of this step ----
     double mn[3], mx[3];
     for (int k = 0; k < 3; k++) {
-        mn[k] = dec_ord(B.bbox[k]);
-        mx[k] = dec_ord(B.bbox[3 + k]);
+        mn[k] = dec_ord(C.bbox[k]);
+        mx[k] = dec_ord(C.bbox[3 + k]);
         if (P.has_wall_bb) {
             mn[k] = fmin(mn[k], P.wall_bb_min[k]);
             mx[k] = fmax(mx[k], P.wall_bb_max[k]);
         }
     }
-    GridDev& G = *B.grid;
+    // ---- Multicore grid: ChBroadphase::DetermineBoundingBox + ComputeTopLevelResolution (ChBroadphase.cpp:143-208)
+    GridDev& G = C.mc;
     unsigned err = 0;
     for (int k = 0; k < 3; k++) {
         const double fraction = 1e-3;
@@ -140,8 +183,6 @@ __global__ void k_grid_update(Params P, Buffers B) {
         G.origin[k] = lo;
         G.bin[k] = bin;
         G.inv[k] = __ddiv_rn(1.0, bin);
-        if (!(bin >= 2.0 * P.rmax))
-            err |= ERR_GRID_BIN_TOO_SMALL;
         if (!isfinite(lo) || !isfinite(hi))
             err |= ERR_NAN;
     }
@@ -151,65 +192,112 @@ __global__ void k_grid_update(Params P, Buffers B) {
             G.wmax[w][k] = __dsub_rn(P.walls[w].amax[k], G.origin[k]);
         }
     if (err)
-        atomicOr(B.err, err);
+        atomicOr(&C.err, err);
+
+    // ---- search grid for the rebuild: cells no smaller than the candidate cut-off 2 rmax + skin ----
+    if (rebuild) {
+        double e = (2.0 * P.rmax + P.skin) * (1.0 + 1e-9);
+        double ext[3];
+        for (int k = 0; k < 3; k++) {
+            ext[k] = (mx[k] - mn[k]) + 2e-6 * e;
+            if (!(ext[k] >= e))
+                ext[k] = e;
+        }
+        int dim[3];
+        for (int it = 0; it < 400; it++) {
+            double tot = 1.0;
+            for (int k = 0; k < 3; k++) {
+                double d = floor(ext[k] / e);
+                d = (d < 1.0) ? 1.0 : d;
+                d = (d > 2097152.0) ? 2097152.0 : d;
+                dim[k] = (int)d;
+                tot *= d;
+            }
+            if (tot <= (double)P.cell_cap)
+                break;
+            e *= 1.05;
+        }
+        unsigned long long tot = (unsigned long long)dim[0] * dim[1] * dim[2];
+        if (tot > P.cell_cap) {  // not reachable (400 x 5 % growth), but never index out of bounds
+            dim[0] = dim[1] = dim[2] = 1;
+            tot = 1;
+        }
+        for (int k = 0; k < 3; k++) {
+            C.s_org[k] = mn[k] - 1e-6 * e;
+            C.s_inv[k] = (double)dim[k] / ext[k];
+            C.s_dim[k] = dim[k];
+        }
+        C.s_ncell = (unsigned)tot;
+        C.travel = 0.0;
+        C.nrebuilds++;
+    }
+    C.rebuild_now = rebuild ? 1u : 0u;
+    C.need_rebuild = 0u;
+    C.rb_src = C.cur;
+    C.f_src = C.cur ^ (rebuild ? 1u : 0u);
+    C.cur = C.f_src ^ 1u;
+    C.nsteps++;
+    C.n_contacts = 0ull;
+    C.pair_count = 0ull;
     // restart the running sphere bounding box for the positions this step will produce
     for (int k = 0; k < 3; k++) {
-        B.bbox[k] = P.has_wall_bb ? enc_ord(P.wall_bb_min[k]) : enc_ord(CUDART_INF);
-        B.bbox[3 + k] = P.has_wall_bb ? enc_ord(P.wall_bb_max[k]) : enc_ord(-CUDART_INF);
+        C.bbox[k] = P.has_wall_bb ? enc_ord(P.wall_bb_min[k]) : enc_ord(CUDART_INF);
+        C.bbox[3 + k] = P.has_wall_bb ? enc_ord(P.wall_bb_max[k]) : enc_ord(-CUDART_INF);
     }
 }
 
 // HashMin of the sphere AABB lower corner, HashMax of the upper corner (ChCollisionUtils.h:44-60), computed on the
 // origin-offset AABB exactly as OffsetAABB + f_Count_AABB_BIN_Intersection do.
-struct BinRange {
-    int lo[3], hi[3];
-    double amin[3], amax[3];
-};
-__device__ __forceinline__ void sphere_bins(const double4& p, const double* org, const double* inv, BinRange& r) {
+__device__ __forceinline__ void sphere_aabb_offset(const double4& p, const double* org, double* amin, double* amax) {
     const double c[3] = {p.x, p.y, p.z};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        r.amin[k] = __dsub_rn(__dsub_rn(c[k], p.w), org[k]);
-        r.amax[k] = __dsub_rn(__dadd_rn(c[k], p.w), org[k]);
-        r.lo[k] = (int)floor(__dmul_rn(r.amin[k], inv[k]));
-        r.hi[k] = (int)ceil(__dmul_rn(r.amax[k], inv[k])) - 1;
+        amin[k] = __dsub_rn(__dsub_rn(c[k], p.w), org[k]);
+        amax[k] = __dsub_rn(__dadd_rn(c[k], p.w), org[k]);
+    }
+}
+
+// Parity output: Multicore bin range of every sphere at the start of the step (recording mode only).
+__global__ void __launch_bounds__(256) k_record_bins(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N)
+        return;
+    const double4 p = B.pos[C.f_src][i];
+    const unsigned sid = B.vel[C.f_src][i].sid;
+    double amin[3], amax[3];
+    sphere_aabb_offset(p, C.mc.origin, amin, amax);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        B.gmin[3 * (size_t)sid + k] = (int)floor(__dmul_rn(amin[k], C.mc.inv[k]));
+        B.gmax[3 * (size_t)sid + k] = (int)ceil(__dmul_rn(amax[k], C.mc.inv[k])) - 1;
     }
 }
 
 // --------------------------------------------------------------------------------------------
-// binning: bin id per sphere + histogram with warp-aggregated atomics
+// rebuild, part 1: search cell per sphere + histogram with warp-aggregated atomics
 // --------------------------------------------------------------------------------------------
-template <bool REC>
+__device__ __forceinline__ int cell_coord(double x, double org, double inv, int dim) {
+    int c = (int)floor((x - org) * inv);
+    return min(max(c, 0), dim - 1);
+}
+
 __global__ void __launch_bounds__(256) k_bin_count(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    const GridDev& G = *B.grid;
     const bool valid = i < P.N;
     unsigned h = 0xFFFFFFFFu;
     if (valid) {
-        double4 p = B.posA[i];
-        BinRange r;
-        sphere_bins(p, G.origin, G.inv, r);
-        if (REC) {
-            unsigned sid = B.sidA[i];
-            for (int k = 0; k < 3; k++) {
-                B.gmin[3 * sid + k] = r.lo[k];
-                B.gmax[3 * sid + k] = r.hi[k];
-            }
-        }
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            if (r.lo[k] < 0 || r.lo[k] >= P.bins[k]) {
-                bad = true;
-                r.lo[k] = min(max(r.lo[k], 0), P.bins[k] - 1);
-            }
-        }
-        if (bad)
-            atomicOr(B.err, ERR_GRID_OUT_OF_RANGE);
-        h = (unsigned)((r.lo[2] * P.bins[1] + r.lo[1]) * P.bins[0] + r.lo[0]);  // Hash_Index, z-major
+        const double4 p = B.pos[C.rb_src][i];
+        const int cx = cell_coord(p.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
+        const int cy = cell_coord(p.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
+        const int cz = cell_coord(p.z, C.s_org[2], C.s_inv[2], C.s_dim[2]);
+        h = (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
         B.cell[i] = h;
     }
-    // warp-aggregated histogram update: lanes that fall in the same bin elect a leader that issues one atomic;
+    // warp-aggregated histogram update: lanes that fall in the same cell elect a leader that issues one atomic;
     // the others derive their rank from their position inside the group.
     unsigned active = __ballot_sync(0xffffffffu, valid);
     if (valid) {
@@ -225,7 +313,7 @@ __global__ void __launch_bounds__(256) k_bin_count(Params P, Buffers B) {
 }
 
 // --------------------------------------------------------------------------------------------
-// exclusive scan over the bin histogram: reduce-then-scan, 3 launches, tiles of 256 threads x 8 items
+// exclusive scan over the cell histogram: reduce-then-scan, 3 launches, tiles of 256 threads x 8 items
 // --------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -263,8 +351,14 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
     return prefix + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(unsigned n, const uint32_t* __restrict__ in,
-                                                                 uint32_t* __restrict__ tile_sums) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
+    const unsigned n = C.s_ncell;
+    if (blockIdx.x * kScanTile >= n)
+        return;
+    const uint32_t* __restrict__ in = B.cell_count;
     const unsigned base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     unsigned s = 0;
     if (base + kScanItems <= n) {
@@ -279,10 +373,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(unsigned n, con
     unsigned total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0)
-        tile_sums[blockIdx.x] = total;
+        B.block_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(unsigned ntiles, uint32_t* tile_sums) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
+    const unsigned ntiles = (C.s_ncell + kScanTile - 1) / kScanTile;
+    uint32_t* tile_sums = B.block_sums;
     __shared__ unsigned carry_s;
     if (threadIdx.x == 0)
         carry_s = 0;
@@ -302,10 +401,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_sums(unsigned ntiles, uin
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(unsigned n, unsigned total_items,
-                                                             const uint32_t* __restrict__ in,
-                                                             const uint32_t* __restrict__ tile_sums,
-                                                             uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
+    const unsigned n = C.s_ncell;
+    if (blockIdx.x * kScanTile >= n)
+        return;
+    uint32_t* in = B.cell_count;
+    uint32_t* __restrict__ out = B.cell_start;
     const unsigned base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     unsigned v[kScanItems];
     unsigned s = 0;
@@ -314,70 +418,140 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(unsigned n, unsigne
         v[k] = (base + k < n) ? in[base + k] : 0;
         s += v[k];
     }
-    unsigned ex = block_exclusive_scan(s, nullptr) + tile_sums[blockIdx.x];
+    unsigned ex = block_exclusive_scan(s, nullptr) + B.block_sums[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
-        if (base + k < n)
+        if (base + k < n) {
             out[base + k] = ex;
+            in[base + k] = 0;  // self-cleaning histogram: ready for the next rebuild, no memset node in the graph
+        }
         ex += v[k];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        out[n] = total_items;
+        out[n] = P.N;
 }
 
 // --------------------------------------------------------------------------------------------
-// counting sort: permutation, then gather of the 84-byte sphere records into bin order
+// rebuild, part 2: counting-sort permutation, then gather of the sphere records and history columns
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter_perm(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N)
         return;
     B.perm[B.cell_start[B.cell[i]] + B.rank[i]] = i;
 }
 
-template <bool CHUNG>
 __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
     const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.N)
         return;
-    unsigned src = B.perm[s];
-    const unsigned c = B.cell[src];
-    const unsigned b = B.cell_start[c], e = B.cell_start[c + 1];
-    if (e - b > 1) {
-        // The atomics of k_bin_count leave an arbitrary order inside a bin.  Make it deterministic: slot b+r takes
-        // the sphere with the r-th smallest stable id of the bin (bins hold a handful of spheres).
-        const unsigned r = s - b;
-        for (unsigned a = b; a < e; a++) {
-            const unsigned ia = B.perm[a];
-            const unsigned sa = B.sidA[ia];
-            unsigned smaller = 0;
-            for (unsigned j = b; j < e; j++)
-                smaller += (B.sidA[B.perm[j]] < sa);
-            if (smaller == r) {
-                src = ia;
-                break;
-            }
-        }
+    const unsigned a = C.rb_src, b = a ^ 1u;
+    const unsigned src = B.perm[s];
+    B.pos[b][s] = B.pos[a][src];
+    const double2* vs = reinterpret_cast<const double2*>(B.vel[a] + src);
+    double2* vd = reinterpret_cast<double2*>(B.vel[b] + s);
+    const double2 q0 = vs[0], q1 = vs[1], q2 = vs[2], q3 = vs[3];
+    vd[0] = q0; vd[1] = q1; vd[2] = q2; vd[3] = q3;
+    if (B.acc[0]) {
+        const double2* as = reinterpret_cast<const double2*>(B.acc[a] + 6 * (size_t)src);
+        double2* ad = reinterpret_cast<double2*>(B.acc[b] + 6 * (size_t)s);
+        ad[0] = as[0]; ad[1] = as[1]; ad[2] = as[2];
     }
-    B.posB[s] = B.posA[src];
-    const double2* vs = reinterpret_cast<const double2*>(B.velA + 6 * (size_t)src);
-    double2* vd = reinterpret_cast<double2*>(B.velB + 6 * (size_t)s);
-    vd[0] = vs[0];
-    vd[1] = vs[1];
-    vd[2] = vs[2];
-    B.sidB[s] = B.sidA[src];
-    if (CHUNG) {
-        const double2* as = reinterpret_cast<const double2*>(B.accA + 6 * (size_t)src);
-        double2* ad = reinterpret_cast<double2*>(B.accB + 6 * (size_t)s);
-        ad[0] = as[0];
-        ad[1] = as[1];
-        ad[2] = as[2];
+    if (B.hist[0]) {
+        const unsigned hc = ((unsigned)__double2hiint(q3.x)) & 0xFFu;
+        for (unsigned k = 0; k < hc; k++) {
+            const size_t si = (size_t)k * P.Np + src, di = (size_t)k * P.Np + s;
+            const double2* hs = reinterpret_cast<const double2*>(B.hist[a] + si);
+            double2* hd = reinterpret_cast<double2*>(B.hist[b] + di);
+            hd[0] = hs[0];
+            hd[1] = hs[1];
+            if (B.hrel[0])
+                B.hrel[b][di] = B.hrel[a][si];
+        }
     }
 }
 
 // --------------------------------------------------------------------------------------------
-// contact force law: ChIterativeSolverMulticoreSMC.cpp:56-546, bodies without orientation (spheres: the body
-// frame can be taken parallel to the world frame), canonical orientation body1 = lower shape id.
+// rebuild, part 3: Verlet candidate list.  One thread per sphere (cell order), 3x3 rows of 3 contiguous cells.
+// --------------------------------------------------------------------------------------------
+constexpr int kListThreads = 128;
+
+__global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B) {
+    Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
+    const unsigned s = blockIdx.x * kListThreads + threadIdx.x;
+    if (s >= P.N)
+        return;
+    const double4* __restrict__ pos = B.pos[C.f_src];
+    const VelRec* __restrict__ vel = B.vel[C.f_src];
+    const double4 me = pos[s];
+    const int cx = cell_coord(me.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
+    const int cy = cell_coord(me.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
+    const int cz = cell_coord(me.z, C.s_org[2], C.s_inv[2], C.s_dim[2]);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, C.s_dim[0] - 1);
+    unsigned tj[kMaxNeighbors], ts[kMaxNeighbors];
+    int cnt = 0;
+    bool overflow = false;
+    for (int dz = -1; dz <= 1; dz++) {
+        const int z = cz + dz;
+        if (z < 0 || z >= C.s_dim[2])
+            continue;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int y = cy + dy;
+            if (y < 0 || y >= C.s_dim[1])
+                continue;
+            const unsigned row = (unsigned)((z * C.s_dim[1] + y) * C.s_dim[0]);
+            const unsigned jb = B.cell_start[row + x0], je = B.cell_start[row + x1 + 1];
+            for (unsigned j = jb; j < je; j++) {
+                if (j == s)
+                    continue;
+                const double4 pj = pos[j];
+                const double dx = pj.x - me.x, dy2 = pj.y - me.y, dz2 = pj.z - me.z;
+                const double d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
+                const double rs = me.w + pj.w + P.skin;
+                if (d2 > rs * rs * (1.0 + 1e-12))
+                    continue;
+                if (cnt < P.Kn) {
+                    tj[cnt] = j;
+                    ts[cnt] = vel[j].sid;
+                    cnt++;
+                } else {
+                    overflow = true;
+                }
+            }
+        }
+    }
+    if (overflow)
+        atomicOr(&C.err, ERR_NEIGHBOR_OVERFLOW);
+    // insertion sort by stable id: the per-step contact order (= summation order, history column order) becomes
+    // independent of the storage order
+    for (int a = 1; a < cnt; a++) {
+        const unsigned kj = tj[a], ks = ts[a];
+        int b = a - 1;
+        while (b >= 0 && ts[b] > ks) {
+            tj[b + 1] = tj[b];
+            ts[b + 1] = ts[b];
+            b--;
+        }
+        tj[b + 1] = kj;
+        ts[b + 1] = ks;
+    }
+    for (int k = 0; k < cnt; k++)
+        B.nl[(size_t)k * P.Np + s] = tj[k];
+    B.ncnt[s] = (unsigned)cnt;
+}
+
+// --------------------------------------------------------------------------------------------
+// contact force law, generic: ChIterativeSolverMulticoreSMC.cpp:56-546, bodies without orientation (spheres: the
+// body frame can be taken parallel to the world frame), canonical orientation body1 = lower shape id.
+// Used for wall contacts and for every model combination that has no specialised fast path.
 // --------------------------------------------------------------------------------------------
 struct Body {
     V3 pos, v, w;
@@ -394,8 +568,8 @@ struct Hist {
 };
 
 template <bool HIST, bool ROLL>
-__device__ __forceinline__ void contact_force(const Params& P, const Comp& cm, const Body& b1, const Body& b2,
-                                              const Geom& g, Hist& h, V3& F, V3& T1, V3& T2) {
+__device__ __noinline__ void contact_force(const Params& P, const Comp& cm, const Body& b1, const Body& b2,
+                                           const Geom& g, Hist& h, V3& F, V3& T1, V3& T2) {
     const double kPI = 3.141592653589793238462643383279;
     const double eps = 2.220446049250313e-16;
     const V3 pt1_loc = g.pt1 - b1.pos;
@@ -579,6 +753,116 @@ __device__ __forceinline__ void contact_force(const Params& P, const Comp& cm, c
     T2 = tq2;
 }
 
+// --------------------------------------------------------------------------------------------
+// Fast path of the same law for the headline configuration: Hertz, material properties, constant adhesion, sphere
+// against sphere.  Written in the frame of the evaluating sphere ("a" = me, "b" = partner, n from a to b).  All
+// expressions are odd/even under the exchange a <-> b with IEEE-exact sign symmetry (products are formed with
+// commutative roundings), so both partners obtain bit-identical magnitudes and equal-and-opposite forces, and their
+// two copies of the tangential history stay bit-identical.  The stored displacement is in canonical orientation
+// (body 1 = lower shape id, ChIterativeSolverMulticoreSMC.cpp:233-243): disp_ab = sgn * disp_canonical.
+// Divisions / square roots of the reference are replaced by rcp / rsqrt forms (<= 2 ulp); the bar is 1e-9.
+// --------------------------------------------------------------------------------------------
+template <bool HIST, bool ROLL>
+__device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp& cm, V3 n, double dist, double ra,
+                                                    double rb, V3 va, V3 wa, V3 vb, V3 wb, double ma, double mb,
+                                                    bool a_is_body1, V3& disp, unsigned& steps, bool isnew, V3& F_me,
+                                                    V3& T_me) {
+    const double eps = 2.220446049250313e-16;
+    const double radSum = __dadd_rn(ra, rb);
+    const double delta_n = radSum - dist;
+    const double erad = __dmul_rn(ra, rb) * __drcp_rn(radSum);
+    // velocity of b's contact point minus a's:  (vb + wb x (-n rb)) - (va + wa x (n ra))
+    const V3 wsum = mk(__dadd_rn(__dmul_rn(ra, wa.x), __dmul_rn(rb, wb.x)), __dadd_rn(__dmul_rn(ra, wa.y), __dmul_rn(rb, wb.y)),
+                       __dadd_rn(__dmul_rn(ra, wa.z), __dmul_rn(rb, wb.z)));
+    const V3 wxn = cross(wsum, n);
+    const V3 relvel = (vb - va) - wxn;
+    const double vn = dot(relvel, n);
+    const V3 relvel_t = relvel - vn * n;
+    const double m_eff = __dmul_rn(ma, mb) * __drcp_rn(__dadd_rn(ma, mb));
+
+    V3 delta_t = mk(0, 0, 0);
+    if (HIST) {
+        delta_t = relvel_t * P.dt;
+        if (isnew) {
+            disp = mk(0, 0, 0);
+            steps = 0;
+        } else {
+            steps++;
+        }
+        disp = disp - delta_t;
+        disp = disp - dot(disp, n) * n;
+        delta_t = -disp;
+    } else if (P.tang_mode == 1) {
+        delta_t = relvel_t * P.dt;
+    }
+
+    const double x = erad * delta_n;
+    const double sqrt_Rd = x * rsqrt(x);
+    const double Sn = 2 * cm.E_eff * sqrt_Rd;
+    const double St = 8 * cm.G_eff * sqrt_Rd;
+    const double kn = (2.0 / 3.0) * Sn;
+    const double kt = St;
+    const double y = Sn * m_eff;
+    const double gn = cm.hertz_damp * (y * rsqrt(y));
+    const double gt = gn * cm.gt_ratio;
+
+    const double fN = kn * delta_n - gn * vn;
+    const V3 fT_damp = gt * relvel_t;
+    V3 fT = kt * delta_t + fT_damp;
+    const double ft2 = dot(fT, fT);
+    const double slide = cm.mu * fabs(fN);
+    if (ft2 > slide * slide) {
+        if (dot(delta_t, delta_t) > eps * eps) {
+            const double ratio = slide * rsqrt(ft2);
+            fT = fT * ratio;
+            if (HIST) {
+                delta_t = (fT - fT_damp) * __drcp_rn(kt);
+                disp = -delta_t;
+            }
+        } else {
+            fT = mk(0, 0, 0);
+        }
+    }
+    // force on b = fN n - fT; on a (me) the opposite.  Torque on a: -(n ra) x (fN n - fT) = ra (n x fT)
+    V3 Fb = fN * n - fT;
+    V3 Ta = ra * cross(n, fT);
+
+    if (ROLL) {
+        const double kPI = 3.141592653589793238462643383279;
+        double muRoll = cm.mu_roll, muSpin = cm.mu_spin;
+        const double sq_d = sqrt(delta_n);
+        const double kn_simple = kn / sq_d;
+        const double gn_simple = gn / sqrt(sq_d);
+        const double d_coeff = gn_simple / (2.0 * m_eff * sqrt(kn_simple / m_eff));
+        if (d_coeff < 1.0) {
+            const double t_collision = kPI * sqrt(m_eff / (kn_simple * (1 - d_coeff * d_coeff)));
+            const double t_contact = HIST ? (double)steps * P.dt : 0.0;
+            if (t_contact <= t_collision) {
+                muRoll = 0.0;
+                muSpin = 0.0;
+            }
+        }
+        // v_rot = wb x (-n rb) - wa x (n ra) = -(wsum x n)
+        const V3 v_rot = -wxn;
+        const V3 rel_o = wb - wa;
+        const double lv = len(v_rot);
+        if (lv > P.min_roll && muRoll > eps)
+            Ta = Ta + (muRoll * fN * ra / lv) * cross(n, v_rot);
+        const double lo = len(rel_o);
+        if (lo > P.min_spin && muSpin > eps) {
+            // contact-circle radius, evaluated with body 1 = lower shape id as the reference does
+            const double r1 = a_is_body1 ? ra : rb, r2 = a_is_body1 ? rb : ra;
+            const double xc = (r1 * r1 - r2 * r2) / (2 * (r1 + r2 - delta_n)) + 0.5 * (r1 + r2 - delta_n);
+            double rc = r1 * r1 - xc * xc;
+            rc = (rc < eps) ? eps : sqrt(rc);
+            Ta = Ta + (muSpin * rc * (dot(rel_o, n) * fN) / lo) * n;
+        }
+    }
+    Fb = Fb - cm.adh * n;
+    F_me = -Fb;
+    T_me = Ta;
+}
+
 // box_sphere: ChNarrowphasePRIMS.cpp:269-313 with snap_to_box (ChCollisionUtils.h:546-563); rounding pinned.
 __device__ __forceinline__ bool box_sphere_dev(const Wall& W, V3 pos2, double r2, Geom& g) {
     const V3 qv = mk(W.rot[1], W.rot[2], W.rot[3]);
@@ -622,148 +906,268 @@ __device__ __forceinline__ bool plane_sphere_dev(const Wall& W, V3 pos2, double 
 }
 
 // --------------------------------------------------------------------------------------------
-// fused narrowphase + force + integrate.  One thread per sphere in bin order.
+// fused narrowphase + force + integrate.  One thread per sphere in storage (cell) order.
 // --------------------------------------------------------------------------------------------
 constexpr int kForceThreads = 128;
 
-template <bool HIST, bool ROLL, bool REC>
-__global__ void __launch_bounds__(kForceThreads) k_force_integrate(const __grid_constant__ Params P,
-                                                                   const __grid_constant__ Buffers B) {
-    __shared__ unsigned clist[kMaxContactsPerSphere * kForceThreads];
+// cursor over the sphere's own (old) history column; records are ordered by key (walls, then partner ids)
+struct HistCursor {
+    const double4* __restrict__ col;  // &hist_in[s]
+    const double* __restrict__ rel;   // &hrel_in[s] or null
+    size_t pitch;
+    unsigned t, n;
+    double2 a, b;  // record t (prefetched)
+    unsigned key;
+    __device__ __forceinline__ void fetch() {
+        if (t < n) {
+            const double2* q = reinterpret_cast<const double2*>(col + (size_t)t * pitch);
+            a = q[0];
+            b = q[1];
+            key = rec_key(b.y);
+        } else {
+            key = kEmptyKey;
+        }
+    }
+    // true if the sphere had a record for `k` last step; afterwards the cursor sits on the next record
+    __device__ __forceinline__ bool find(unsigned k, V3& disp, unsigned& steps, double& relvel0) {
+        while (key < k) {
+            t++;
+            fetch();
+        }
+        if (key != k)
+            return false;
+        disp = mk(a.x, a.y, b.x);
+        steps = rec_steps(b.y);
+        if (rel)
+            relvel0 = rel[(size_t)t * pitch];
+        t++;
+        fetch();
+        return true;
+    }
+};
+
+template <bool HIST, bool ROLL, bool FAST, bool REC>
+__global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __grid_constant__ Params P,
+                                                                      const __grid_constant__ Buffers B) {
+    __shared__ unsigned clist[kMaxSlots * kForceThreads];
+    Ctrl& C = *B.ctrl;
+    const unsigned src = C.f_src, dst = src ^ 1u;
+    const double4* __restrict__ pos_in = B.pos[src];
+    const VelRec* __restrict__ vel_in = B.vel[src];
     const unsigned tid = threadIdx.x;
     const unsigned s = blockIdx.x * kForceThreads + tid;
     const bool valid = s < P.N;
-    const GridDev& G = *B.grid;
+    const GridDev& G = C.mc;
 
-    double4 me = make_double4(0, 0, 0, 0);
-    V3 mv = mk(0, 0, 0), mw = mk(0, 0, 0);
-    unsigned sid = 0;
+    double4 me = make_double4(0, 0, 0, 1.0);
+    VelVal mv;
+    mv.v = mk(0, 0, 0); mv.w = mk(0, 0, 0); mv.sid = 0; mv.meta = 0;
     int cnt = 0;
-    BinRange br;
     if (valid) {
-        me = B.posB[s];
-        const double2* vp = reinterpret_cast<const double2*>(B.velB + 6 * (size_t)s);
-        double2 a = vp[0], b = vp[1], c = vp[2];
-        mv = mk(a.x, a.y, b.x);
-        mw = mk(b.y, c.x, c.y);
-        sid = B.sidB[s];
-        sphere_bins(me, G.origin, G.inv, br);
-        const int cx = min(max(br.lo[0], 0), P.bins[0] - 1);
-        const int cy = min(max(br.lo[1], 0), P.bins[1] - 1);
-        const int cz = min(max(br.lo[2], 0), P.bins[2] - 1);
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, P.bins[0] - 1);
-        // ---- phase 1: candidate scan over the 3x3 rows of 3 contiguous bins; keep touching spheres ----
-        for (int dz = -1; dz <= 1; dz++) {
-            const int z = cz + dz;
-            if (z < 0 || z >= P.bins[2])
+        me = pos_in[s];
+        mv = load_vel(vel_in, s);
+        // ---- phase 1: exact sphere_sphere test (ChNarrowphasePRIMS.cpp:50-59, separation = 0) on the candidates
+        const unsigned nc = B.ncnt[s];
+        const uint32_t* __restrict__ nl = B.nl + s;
+#pragma unroll 4
+        for (unsigned k = 0; k < nc; k++) {
+            const unsigned j = nl[(size_t)k * P.Np];
+            const double4 pj = pos_in[j];
+            const V3 d = mk(__dsub_rn(pj.x, me.x), __dsub_rn(pj.y, me.y), __dsub_rn(pj.z, me.z));
+            const double dist2 = dot_rn(d, d);
+            const double rs = __dadd_rn(me.w, pj.w);
+            if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
                 continue;
-            for (int dy = -1; dy <= 1; dy++) {
-                const int y = cy + dy;
-                if (y < 0 || y >= P.bins[1])
+            if (cnt < kMaxSlots)
+                clist[cnt * kForceThreads + tid] = j;
+            cnt++;
+        }
+        if (cnt > kMaxSlots) {
+            atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
+            cnt = kMaxSlots;
+        }
+    }
+    const unsigned sid = mv.sid;
+    const unsigned flags = (mv.meta >> 8) & 0xFFu;
+    const double my_mass = sphere_mass(P, me.w);
+    V3 Fsum = mk(0, 0, 0), Tsum = mk(0, 0, 0);
+    int nh = 0;  // history records written by this sphere
+    unsigned ncontacts = 0;
+    HistCursor hc;
+    hc.t = 0; hc.n = 0; hc.key = kEmptyKey; hc.rel = nullptr; hc.pitch = P.Np; hc.col = nullptr;
+    double4* hout = nullptr;
+    double* hrout = nullptr;
+    if (HIST && valid) {
+        hc.col = B.hist[src] + s;
+        hc.rel = B.hrel[src] ? B.hrel[src] + s : nullptr;
+        hc.n = mv.meta & 0xFFu;
+        hc.fetch();
+        hout = B.hist[dst] + s;
+        hrout = B.hrel[dst] ? B.hrel[dst] + s : nullptr;
+    }
+    const V3 mpos = mk(me.x, me.y, me.z);
+
+    if (valid) {
+        // ---- walls first (history keys 0..nW-1 sort before every sphere key): body 1 = wall body (lower id),
+        //      body 2 = this sphere
+        double amin[3], amax[3];
+        sphere_aabb_offset(me, G.origin, amin, amax);
+        for (int w = 0; w < P.nW; w++) {
+            const Wall& W = P.walls[w];
+            Geom g;
+            bool hit;
+            if (W.type == WALL_BOX) {
+                // broadphase AABB overlap on origin-offset boxes (ChCollisionUtils.h:83-87)
+                if (!(amin[0] <= G.wmax[w][0] && G.wmin[w][0] <= amax[0] && amin[1] <= G.wmax[w][1] &&
+                      G.wmin[w][1] <= amax[1] && amin[2] <= G.wmax[w][2] && G.wmin[w][2] <= amax[2]))
                     continue;
-                const unsigned row = (unsigned)((z * P.bins[1] + y) * P.bins[0]);
-                const unsigned jb = B.cell_start[row + x0], je = B.cell_start[row + x1 + 1];
-                for (unsigned j = jb; j < je; j++) {
-                    if (j == s)
-                        continue;
-                    const double4 pj = B.posB[j];
-                    // sphere_sphere test, ChNarrowphasePRIMS.cpp:50-59 (separation = 0)
-                    const V3 d = mk(__dsub_rn(pj.x, me.x), __dsub_rn(pj.y, me.y), __dsub_rn(pj.z, me.z));
-                    const double dist2 = dot_rn(d, d);
-                    const double rs = __dadd_rn(me.w, pj.w);
-                    if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
-                        continue;
-                    if (cnt < kMaxContactsPerSphere)
-                        clist[cnt * kForceThreads + tid] = j;
-                    cnt++;
+                hit = box_sphere_dev(W, mpos, me.w, g);
+            } else {
+                hit = plane_sphere_dev(W, mpos, me.w, g);
+            }
+            if (!hit)
+                continue;
+            ncontacts++;
+            if (REC) {
+                unsigned long long at = atomicAdd(&C.pair_count, 1ull);
+                if (at < B.pair_cap)
+                    B.pairs[at] = ((unsigned long long)w << 32) | (unsigned long long)(P.shape_base + sid);
+            }
+            if (g.depth >= 0)  // ChIterativeSolverMulticoreSMC.cpp:96-104: no force, no history
+                continue;
+            Hist h{mk(0, 0, 0), 0.0, 0.0, true};
+            unsigned steps = 0;
+            const unsigned key = (unsigned)w;
+            if (HIST) {
+                if (hc.find(key, h.disp, steps, h.relvel0)) {
+                    h.isnew = false;
+                    h.dur = (double)steps * P.dt;
+                    steps++;
                 }
             }
-        }
-        if (cnt > kMaxContactsPerSphere) {
-            atomicOr(B.err, ERR_CONTACT_LIST_OVERFLOW);
-            cnt = kMaxContactsPerSphere;
+            Body b1{mk(0, 0, 0), mk(W.vel[0], W.vel[1], W.vel[2]), mk(0, 0, 0), P.wall_mass};
+            Body b2{mpos, mv.v, mv.w, my_mass};
+            V3 F, T1, T2;
+            contact_force<HIST, ROLL>(P, P.comp[1], b1, b2, g, h, F, T1, T2);
+            Fsum = Fsum + F;
+            Tsum = Tsum + T2;
+            if (HIST) {
+                if (nh < P.K) {
+                    double2* q = reinterpret_cast<double2*>(hout + (size_t)nh * P.Np);
+                    q[0] = make_double2(h.disp.x, h.disp.y);
+                    q[1] = make_double2(h.disp.z, pack_key(key, steps));
+                    if (hrout)
+                        hrout[(size_t)nh * P.Np] = h.relvel0;
+                }
+                nh++;
+            }
         }
     }
 
-    // ---- phase 2: all lanes evaluate their k-th contact together ----
-    const double my_mass = sphere_mass(P, me.w);
-    V3 Fsum = mk(0, 0, 0), Tsum = mk(0, 0, 0);
-    int nh = 0;  // history slots written by this sphere
-    unsigned ncontacts = 0;
-    uint32_t* const my_hkey = HIST ? B.hkey_new + (size_t)sid * P.K : nullptr;
-    double4* const my_hval = HIST ? B.hval_new + (size_t)sid * P.K : nullptr;
+    // ---- phase 2: all lanes evaluate their k-th sphere contact together (contacts are in stable-id order) ----
     const int maxc = __reduce_max_sync(0xffffffffu, cnt);
     for (int k = 0; k < maxc; k++) {
         if (k >= cnt)
             continue;
         const unsigned j = clist[k * kForceThreads + tid];
-        const double4 pj = B.posB[j];
-        const double2* vp = reinterpret_cast<const double2*>(B.velB + 6 * (size_t)j);
-        const double2 a = vp[0], b = vp[1], c = vp[2];
-        const unsigned sj = B.sidB[j];
+        const double4 pj = pos_in[j];
+        const VelVal ov = load_vel(vel_in, j);
+        const unsigned sj = ov.sid;
         const bool me1 = sid < sj;  // canonical orientation: body 1 = lower shape id
-        Body b1, b2;
-        double r1, r2;
-        {
-            Body bm{mk(me.x, me.y, me.z), mv, mw, my_mass};
-            Body bo{mk(pj.x, pj.y, pj.z), mk(a.x, a.y, b.x), mk(b.y, c.x, c.y), sphere_mass(P, pj.w)};
-            b1 = me1 ? bm : bo;
-            b2 = me1 ? bo : bm;
-            r1 = me1 ? me.w : pj.w;
-            r2 = me1 ? pj.w : me.w;
-        }
-        // sphere_sphere contact geometry, ChNarrowphasePRIMS.cpp:61-69
-        Geom g;
-        {
-            const V3 delta = mk(__dsub_rn(b2.pos.x, b1.pos.x), __dsub_rn(b2.pos.y, b1.pos.y), __dsub_rn(b2.pos.z, b1.pos.z));
-            const double dist = sqrt(dot_rn(delta, delta));
-            g.n = mk(__ddiv_rn(delta.x, dist), __ddiv_rn(delta.y, dist), __ddiv_rn(delta.z, dist));
-            g.pt1 = mk(__dadd_rn(b1.pos.x, __dmul_rn(g.n.x, r1)), __dadd_rn(b1.pos.y, __dmul_rn(g.n.y, r1)),
-                       __dadd_rn(b1.pos.z, __dmul_rn(g.n.z, r1)));
-            g.pt2 = mk(__dsub_rn(b2.pos.x, __dmul_rn(g.n.x, r2)), __dsub_rn(b2.pos.y, __dmul_rn(g.n.y, r2)),
-                       __dsub_rn(b2.pos.z, __dmul_rn(g.n.z, r2)));
-            const double radSum = __dadd_rn(r1, r2);
-            g.depth = __dsub_rn(dist, radSum);
-            g.erad = __ddiv_rn(__dmul_rn(r1, r2), radSum);
-        }
         ncontacts++;
         if (REC && !me1) {
-            unsigned long long at = atomicAdd(B.pair_count, 1ull);
+            unsigned long long at = atomicAdd(&C.pair_count, 1ull);
             if (at < B.pair_cap)
                 B.pairs[at] = ((unsigned long long)(P.shape_base + sj) << 32) | (unsigned long long)(P.shape_base + sid);
         }
-        if (g.depth >= 0)  // ChIterativeSolverMulticoreSMC.cpp:96-104: no force, no history
-            continue;
-        Hist h{mk(0, 0, 0), 0.0, 0.0, true};
-        const unsigned key = P.shape_base + (me1 ? sid : sj);  // the non-owner's shape id
-        if (HIST) {
-            const size_t row = (size_t)(me1 ? sj : sid) * P.K;  // owner = higher id
-            for (int t = 0; t < P.K; t++) {
-                if (B.hkey_old[row + t] == key) {
-                    const double4 hv = B.hval_old[row + t];
-                    h.disp = mk(hv.x, hv.y, hv.z);
-                    h.dur = hv.w;
-                    if (B.hrel_old)
-                        h.relvel0 = B.hrel_old[row + t];
-                    h.isnew = false;
-                    break;
+        const unsigned key = P.shape_base + sj;
+        if (FAST) {
+            // sphere_sphere geometry in my own frame (n from me to the partner); |delta|^2 as in the contact test
+            const V3 delta = mk(__dsub_rn(pj.x, me.x), __dsub_rn(pj.y, me.y), __dsub_rn(pj.z, me.z));
+            const double d2 = dot_rn(delta, delta);
+            const double inv_d = rsqrt(d2);
+            const double dist = d2 * inv_d;
+            if (dist - __dadd_rn(me.w, pj.w) >= 0)
+                continue;
+            const V3 n = delta * inv_d;
+            V3 disp = mk(0, 0, 0);
+            unsigned steps = 0;
+            double rel0 = 0;
+            bool isnew = true;
+            if (HIST) {
+                if (hc.find(key, disp, steps, rel0)) {
+                    isnew = false;
+                    if (!me1)
+                        disp = -disp;  // canonical (body 1 -> body 2) to my frame
                 }
             }
-        }
-        V3 F, T1, T2;
-        contact_force<HIST, ROLL>(P, P.comp[0], b1, b2, g, h, F, T1, T2);
-        if (me1) {
-            Fsum = Fsum - F;
-            Tsum = Tsum + T1;
-        } else {
+            V3 F, T;
+            sphere_contact_fast<HIST, ROLL>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass,
+                                            sphere_mass(P, pj.w), me1, disp, steps, isnew, F, T);
             Fsum = Fsum + F;
-            Tsum = Tsum + T2;
+            Tsum = Tsum + T;
             if (HIST) {
                 if (nh < P.K) {
-                    my_hkey[nh] = key;
-                    my_hval[nh] = make_double4(h.disp.x, h.disp.y, h.disp.z, h.dur);
-                    if (B.hrel_new)
-                        B.hrel_new[(size_t)sid * P.K + nh] = h.relvel0;
+                    if (!me1)
+                        disp = -disp;
+                    double2* q = reinterpret_cast<double2*>(hout + (size_t)nh * P.Np);
+                    q[0] = make_double2(disp.x, disp.y);
+                    q[1] = make_double2(disp.z, pack_key(key, steps));
+                }
+                nh++;
+            }
+        } else {
+            Body b1, b2;
+            double r1, r2;
+            {
+                Body bm{mpos, mv.v, mv.w, my_mass};
+                Body bo{mk(pj.x, pj.y, pj.z), ov.v, ov.w, sphere_mass(P, pj.w)};
+                b1 = me1 ? bm : bo;
+                b2 = me1 ? bo : bm;
+                r1 = me1 ? me.w : pj.w;
+                r2 = me1 ? pj.w : me.w;
+            }
+            // sphere_sphere contact geometry, ChNarrowphasePRIMS.cpp:61-69
+            Geom g;
+            {
+                const V3 delta = mk(__dsub_rn(b2.pos.x, b1.pos.x), __dsub_rn(b2.pos.y, b1.pos.y), __dsub_rn(b2.pos.z, b1.pos.z));
+                const double dist = sqrt(dot_rn(delta, delta));
+                g.n = mk(__ddiv_rn(delta.x, dist), __ddiv_rn(delta.y, dist), __ddiv_rn(delta.z, dist));
+                g.pt1 = mk(__dadd_rn(b1.pos.x, __dmul_rn(g.n.x, r1)), __dadd_rn(b1.pos.y, __dmul_rn(g.n.y, r1)),
+                           __dadd_rn(b1.pos.z, __dmul_rn(g.n.z, r1)));
+                g.pt2 = mk(__dsub_rn(b2.pos.x, __dmul_rn(g.n.x, r2)), __dsub_rn(b2.pos.y, __dmul_rn(g.n.y, r2)),
+                           __dsub_rn(b2.pos.z, __dmul_rn(g.n.z, r2)));
+                const double radSum = __dadd_rn(r1, r2);
+                g.depth = __dsub_rn(dist, radSum);
+                g.erad = __ddiv_rn(__dmul_rn(r1, r2), radSum);
+            }
+            if (g.depth >= 0)  // ChIterativeSolverMulticoreSMC.cpp:96-104: no force, no history
+                continue;
+            Hist h{mk(0, 0, 0), 0.0, 0.0, true};
+            unsigned steps = 0;
+            if (HIST) {
+                if (hc.find(key, h.disp, steps, h.relvel0)) {
+                    h.isnew = false;
+                    h.dur = (double)steps * P.dt;
+                    steps++;
+                }
+            }
+            V3 F, T1, T2;
+            contact_force<HIST, ROLL>(P, P.comp[0], b1, b2, g, h, F, T1, T2);
+            if (me1) {
+                Fsum = Fsum - F;
+                Tsum = Tsum + T1;
+            } else {
+                Fsum = Fsum + F;
+                Tsum = Tsum + T2;
+            }
+            if (HIST) {
+                if (nh < P.K) {
+                    double2* q = reinterpret_cast<double2*>(hout + (size_t)nh * P.Np);
+                    q[0] = make_double2(h.disp.x, h.disp.y);
+                    q[1] = make_double2(h.disp.z, pack_key(key, steps));
+                    if (hrout)
+                        hrout[(size_t)nh * P.Np] = h.relvel0;
                 }
                 nh++;
             }
@@ -771,131 +1175,81 @@ __global__ void __launch_bounds__(kForceThreads) k_force_integrate(const __grid_
     }
 
     double nmnx = CUDART_INF, nmny = CUDART_INF, nmnz = CUDART_INF, nmxx = -CUDART_INF, nmxy = -CUDART_INF, nmxz = -CUDART_INF;
+    double dx2 = 0.0;
     if (valid) {
-        // ---- walls: body 1 = wall body (lower id), body 2 = this sphere, history on the sphere ----
-        for (int w = 0; w < P.nW; w++) {
-            const Wall& W = P.walls[w];
-            Geom g;
-            bool hit;
-            if (W.type == WALL_BOX) {
-                // broadphase AABB overlap on origin-offset boxes (ChCollisionUtils.h:83-87)
-                if (!(br.amin[0] <= G.wmax[w][0] && G.wmin[w][0] <= br.amax[0] && br.amin[1] <= G.wmax[w][1] &&
-                      G.wmin[w][1] <= br.amax[1] && br.amin[2] <= G.wmax[w][2] && G.wmin[w][2] <= br.amax[2]))
-                    continue;
-                hit = box_sphere_dev(W, mk(me.x, me.y, me.z), me.w, g);
-            } else {
-                hit = plane_sphere_dev(W, mk(me.x, me.y, me.z), me.w, g);
-            }
-            if (!hit)
-                continue;
-            ncontacts++;
-            if (REC) {
-                unsigned long long at = atomicAdd(B.pair_count, 1ull);
-                if (at < B.pair_cap)
-                    B.pairs[at] = ((unsigned long long)w << 32) | (unsigned long long)(P.shape_base + sid);
-            }
-            if (g.depth >= 0)
-                continue;
-            Hist h{mk(0, 0, 0), 0.0, 0.0, true};
-            const unsigned key = (unsigned)w;
-            if (HIST) {
-                const size_t row = (size_t)sid * P.K;
-                for (int t = 0; t < P.K; t++) {
-                    if (B.hkey_old[row + t] == key) {
-                        const double4 hv = B.hval_old[row + t];
-                        h.disp = mk(hv.x, hv.y, hv.z);
-                        h.dur = hv.w;
-                        if (B.hrel_old)
-                            h.relvel0 = B.hrel_old[row + t];
-                        h.isnew = false;
-                        break;
-                    }
-                }
-            }
-            Body b1{mk(0, 0, 0), mk(W.vel[0], W.vel[1], W.vel[2]), mk(0, 0, 0), P.wall_mass};
-            Body b2{mk(me.x, me.y, me.z), mv, mw, my_mass};
-            V3 F, T1, T2;
-            contact_force<HIST, ROLL>(P, P.comp[1], b1, b2, g, h, F, T1, T2);
-            Fsum = Fsum + F;
-            Tsum = Tsum + T2;
-            if (HIST) {
-                if (nh < P.K) {
-                    my_hkey[nh] = key;
-                    my_hval[nh] = make_double4(h.disp.x, h.disp.y, h.disp.z, h.dur);
-                    if (B.hrel_new)
-                        B.hrel_new[(size_t)sid * P.K + nh] = h.relvel0;
-                }
-                nh++;
-            }
-        }
-        if (HIST) {
-            if (nh > P.K) {
-                atomicOr(B.err, ERR_HISTORY_OVERFLOW);
-                nh = P.K;
-            }
-            for (int t = nh; t < P.K; t++)
-                my_hkey[t] = kEmptyKey;  // entries not touched this step are dropped (:677-685)
+        if (HIST && nh > P.K) {
+            atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
+            nh = P.K;
         }
         if (REC) {
             B.recF[3 * (size_t)sid + 0] = Fsum.x; B.recF[3 * (size_t)sid + 1] = Fsum.y; B.recF[3 * (size_t)sid + 2] = Fsum.z;
             B.recT[3 * (size_t)sid + 0] = Tsum.x; B.recT[3 * (size_t)sid + 1] = Tsum.y; B.recT[3 * (size_t)sid + 2] = Tsum.z;
-            atomicAdd(B.n_contacts, (unsigned long long)ncontacts);
+            atomicAdd(&C.n_contacts, (unsigned long long)ncontacts);
         }
 
         // ---- time integration ----
-        const bool fixed = B.flags && (B.flags[sid] & 1);
+        const bool fixed = (flags & 1u) != 0;
         const double hdt = P.dt;
         const double inv_m = 1.0 / my_mass;
         const double inv_I = 1.0 / (0.4 * my_mass * me.w * me.w);
         const V3 gv = mk(P.g[0], P.g[1], P.g[2]);
-        V3 x = mk(me.x, me.y, me.z);
-        V3 vn = mv, wn = mw;
+        V3 x = mpos;
+        V3 vn = mv.v, wn = mv.w;
         if (!fixed) {
             if (P.integrator == 2) {
                 // Multicore: hf = h*(g*m) + h*F; v+ = v + M^-1 hf; x+ = x + v+ h (ChBody.cpp:247-256,288-297)
                 V3 hf = hdt * (gv * my_mass) + hdt * Fsum;
-                vn = mv + inv_m * hf;
-                wn = mw + inv_I * (hdt * Tsum);
+                vn = mv.v + inv_m * hf;
+                wn = mv.w + inv_I * (hdt * Tsum);
                 x = x + vn * hdt;
             } else {
                 const V3 acc = gv + inv_m * Fsum;
                 const V3 alp = inv_I * Tsum;
                 if (P.integrator == 3) {         // extended Taylor (ChDemSMC.cuh:1347-1351)
-                    x = x + hdt * (mv + 0.5 * hdt * acc);
-                    vn = mv + hdt * acc;
-                    wn = mw + hdt * alp;
+                    x = x + hdt * (mv.v + 0.5 * hdt * acc);
+                    vn = mv.v + hdt * acc;
+                    wn = mv.w + hdt * alp;
                 } else if (P.integrator == 0) {  // forward Euler
-                    x = x + hdt * mv;
-                    vn = mv + hdt * acc;
-                    wn = mw + hdt * alp;
+                    x = x + hdt * mv.v;
+                    vn = mv.v + hdt * acc;
+                    wn = mv.w + hdt * alp;
                 } else {                         // Chung (ChDemSMC.cuh:1266-1277): beta = 28/27, gamma = 3/2
-                    const double2* ap = reinterpret_cast<const double2*>(B.accB + 6 * (size_t)s);
+                    const double2* ap = reinterpret_cast<const double2*>(B.acc[src] + 6 * (size_t)s);
                     const double2 o0 = ap[0], o1 = ap[1], o2 = ap[2];
                     const V3 ao = mk(o0.x, o0.y, o1.x), lo = mk(o1.y, o2.x, o2.y);
                     const double beta = 28.0 / 27.0;
-                    x = x + hdt * (mv + hdt * (beta * acc + (0.5 - beta) * ao));
-                    vn = mv + hdt * (1.5 * acc - 0.5 * ao);
-                    wn = mw + hdt * (1.5 * alp - 0.5 * lo);
-                    double2* aw = reinterpret_cast<double2*>(B.accA + 6 * (size_t)s);
+                    x = x + hdt * (mv.v + hdt * (beta * acc + (0.5 - beta) * ao));
+                    vn = mv.v + hdt * (1.5 * acc - 0.5 * ao);
+                    wn = mv.w + hdt * (1.5 * alp - 0.5 * lo);
+                    double2* aw = reinterpret_cast<double2*>(B.acc[dst] + 6 * (size_t)s);
                     aw[0] = make_double2(acc.x, acc.y);
                     aw[1] = make_double2(acc.z, alp.x);
                     aw[2] = make_double2(alp.y, alp.z);
                 }
             }
+        } else if (P.integrator == 1) {
+            double2* aw = reinterpret_cast<double2*>(B.acc[dst] + 6 * (size_t)s);
+            aw[0] = aw[1] = aw[2] = make_double2(0.0, 0.0);
         }
         if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z)))
-            atomicOr(B.err, ERR_NAN);
-        B.posA[s] = make_double4(x.x, x.y, x.z, me.w);
-        double2* vo = reinterpret_cast<double2*>(B.velA + 6 * (size_t)s);
-        vo[0] = make_double2(vn.x, vn.y);
-        vo[1] = make_double2(vn.z, wn.x);
-        vo[2] = make_double2(wn.y, wn.z);
-        B.sidA[s] = sid;
+            atomicOr(&C.err, ERR_NAN);
+        B.pos[dst][s] = make_double4(x.x, x.y, x.z, me.w);
+        store_vel(B.vel[dst], s, vn, wn, sid, (unsigned)nh | (flags << 8));
         nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
         nmxx = x.x + me.w; nmxy = x.y + me.w; nmxz = x.z + me.w;
+        const V3 dxv = x - mpos;
+        dx2 = dot(dxv, dxv);
     }
-    // running bounding box of the new sphere AABBs -> next step's grid (all lanes take part in the shuffles)
-    block_bbox_commit(nmnx, nmny, nmnz, nmxx, nmxy, nmxz, B.bbox);
+    // running bounding box of the new sphere AABBs -> next step's grids; largest displacement -> Verlet travel
+    block_bbox_commit(nmnx, nmny, nmnz, nmxx, nmxy, nmxz, C.bbox);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        dx2 = fmax(dx2, __shfl_xor_sync(0xffffffffu, dx2, o));
+    if ((tid & 31) == 0) {
+        const unsigned long long e = (unsigned long long)__double_as_longlong(dx2);  // non-negative: raw bits are ordered
+        if (e > C.max_dx2)
+            atomicMax(&C.max_dx2, e);
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -903,11 +1257,12 @@ __global__ void __launch_bounds__(kForceThreads) k_force_integrate(const __grid_
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_reduce(Params P, Buffers B, int which, double arg, double* out_sum,
                                                 unsigned long long* out_ext) {
+    const Ctrl& C = *B.ctrl;
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     double v = 0, ext = -CUDART_INF;
     if (i < P.N) {
-        double4 p = B.posA[i];
-        const double* vel = B.velA + 6 * (size_t)i;
+        double4 p = B.pos[C.cur][i];
+        const double* vel = B.vel[C.cur][i].v;  // v[3] followed by w[3]
         switch (which) {
             case 0: ext = p.z; break;
             case 1: ext = -p.z; break;
@@ -921,6 +1276,7 @@ __global__ void __launch_bounds__(256) k_reduce(Params P, Buffers B, int which, 
             case 3: ext = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]); break;
             case 4: v = (p.z > arg) ? 1.0 : 0.0; break;
             case 5: v = (p.x > arg) ? 1.0 : 0.0; break;
+            case 6: v = (double)(B.vel[C.cur][i].meta & 0xFFu); break;  // history records held by this sphere
         }
     }
 #pragma unroll
@@ -929,49 +1285,46 @@ __global__ void __launch_bounds__(256) k_reduce(Params P, Buffers B, int which, 
         ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        if (which == 2 || which == 4 || which == 5)
+        if (which == 2 || which >= 4)
             atomicAdd(out_sum, v);
         else
             atomicMax(out_ext, enc_ord(ext));
     }
 }
 
-__global__ void __launch_bounds__(256) k_count_history(unsigned long long n, const uint32_t* __restrict__ keys,
-                                                       unsigned long long* out) {
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned c = (i < n && keys[i] != kEmptyKey) ? 1u : 0u;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c)
-        atomicAdd(out, (unsigned long long)c);
-}
-
 // user order <-> storage order
 __global__ void __launch_bounds__(256) k_export_state(Params P, Buffers B, double* pos3, double* vel3, double* om3) {
+    const Ctrl& C = *B.ctrl;
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N)
         return;
-    unsigned sid = B.sidA[i];
-    double4 p = B.posA[i];
-    const double* v = B.velA + 6 * (size_t)i;
-    if (pos3) { pos3[3 * (size_t)sid] = p.x; pos3[3 * (size_t)sid + 1] = p.y; pos3[3 * (size_t)sid + 2] = p.z; }
-    if (vel3) { vel3[3 * (size_t)sid] = v[0]; vel3[3 * (size_t)sid + 1] = v[1]; vel3[3 * (size_t)sid + 2] = v[2]; }
-    if (om3) { om3[3 * (size_t)sid] = v[3]; om3[3 * (size_t)sid + 1] = v[4]; om3[3 * (size_t)sid + 2] = v[5]; }
+    const double4 p = B.pos[C.cur][i];
+    const VelVal r = load_vel(B.vel[C.cur], i);
+    const size_t o = 3 * (size_t)r.sid;
+    if (pos3) { pos3[o] = p.x; pos3[o + 1] = p.y; pos3[o + 2] = p.z; }
+    if (vel3) { vel3[o] = r.v.x; vel3[o + 1] = r.v.y; vel3[o + 2] = r.v.z; }
+    if (om3) { om3[o] = r.w.x; om3[o + 1] = r.w.y; om3[o + 2] = r.w.z; }
 }
 
 __global__ void __launch_bounds__(256) k_import_state(Params P, Buffers B, const double* pos3, const double* vel3,
                                                       const double* om3) {
+    Ctrl& C = *B.ctrl;
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N)
         return;
-    unsigned sid = B.sidA[i];
+    VelVal r = load_vel(B.vel[C.cur], i);
+    const size_t o = 3 * (size_t)r.sid;
     if (pos3) {
-        double4 p = B.posA[i];
-        p.x = pos3[3 * (size_t)sid]; p.y = pos3[3 * (size_t)sid + 1]; p.z = pos3[3 * (size_t)sid + 2];
-        B.posA[i] = p;
+        double4 p = B.pos[C.cur][i];
+        p.x = pos3[o]; p.y = pos3[o + 1]; p.z = pos3[o + 2];
+        B.pos[C.cur][i] = p;
     }
-    double* v = B.velA + 6 * (size_t)i;
-    if (vel3) { v[0] = vel3[3 * (size_t)sid]; v[1] = vel3[3 * (size_t)sid + 1]; v[2] = vel3[3 * (size_t)sid + 2]; }
-    if (om3) { v[3] = om3[3 * (size_t)sid]; v[4] = om3[3 * (size_t)sid + 1]; v[5] = om3[3 * (size_t)sid + 2]; }
+    if (vel3) r.v = mk(vel3[o], vel3[o + 1], vel3[o + 2]);
+    if (om3) r.w = mk(om3[o], om3[o + 1], om3[o + 2]);
+    if (vel3 || om3)
+        store_vel(B.vel[C.cur], i, r.v, r.w, r.sid, r.meta);
+    if (i == 0 && pos3)
+        C.need_rebuild = 1u;  // positions were replaced: the candidate lists are stale
 }
 
 }  // namespace demb200

@@ -1,15 +1,19 @@
 // =============================================================================
 // dem_types.h -- shared host/device declarations of the B200 SMC-DEM engine.
 //
-// HBM layout (fp64, one record per sphere, two copies "A"/"B" that ping-pong every step):
-//   posr : double4 (x, y, z, radius)            32 B, one DRAM sector per neighbour gather
-//   velw : double[6] (vx,vy,vz, wx,wy,wz)       48 B, gathered only for spheres actually in contact
-//   sid  : uint32  stable sphere id (= user index); shape id = shape_base + sid (Multicore numbering)
-// "A" is the state at the start of a step in last step's cell order; "B" is the same state re-sorted by
-// broadphase cell (z-major Multicore hash, src/chrono/collision/multicore/ChCollisionUtils.h:63-65).
-// Contact history (tangential displacement map keyed by contact pair) lives in rows of K slots indexed by the
-// STABLE id of the owning sphere (owner = higher shape id, as ChIterativeSolverMulticoreSMC.cpp:194-199), so it
-// never moves when spheres are re-sorted:  hkey: uint32[K] partner shape id, hval: double4[K] (disp.xyz, duration).
+// HBM layout (fp64; every per-sphere array is in STORAGE order = search-cell order of the last neighbour-list
+// rebuild; two copies [0]/[1] that ping-pong every step, the live one is Ctrl::cur):
+//   pos  : double4 (x, y, z, radius)                    32 B  one DRAM sector per neighbour gather
+//   vel  : VelRec  (v xyz, omega xyz, sid, meta)        64 B  two aligned sectors, gathered only for real contacts
+//   hist : double4[K][Np] column-major (slot k of sphere s at k*Np + s): tangential displacement of one contact
+//          in canonical orientation (as stored by the higher shape id, ChIterativeSolverMulticoreSMC.cpp:233-243)
+//          + packed (partner shape id | steps in contact).  EVERY sphere keeps a record of EVERY contact it takes
+//          part in (both partners hold bit-identical copies), so a thread only ever touches its own column, rows
+//          migrate with their sphere, and ghosts need no history.
+//   nl   : uint32[Kn][Np] column-major Verlet candidate list (storage slots of spheres within r_i+r_j+skin at the
+//          last rebuild), each sphere's entries sorted by the partner's stable id so the summation order -- and
+//          therefore every bit of the result -- does not depend on storage order, rebuild cadence or partition.
+// sid = stable sphere id (= user index); shape id = shape_base + sid (Multicore numbering).
 // =============================================================================
 #pragma once
 #include <cstdint>
@@ -18,14 +22,13 @@ namespace demb200 {
 
 constexpr int kMaxWalls = 16;
 constexpr unsigned kEmptyKey = 0xFFFFFFFFu;
-constexpr int kMaxContactsPerSphere = 24;  // sphere-sphere contacts a thread can stage (monodisperse max is 12)
+constexpr int kMaxSlots = 32;      // upper bound of history slots K (contacts of one sphere, walls included)
+constexpr int kMaxNeighbors = 64;  // upper bound of Verlet candidate slots Kn
 
 // device error bits (dem_b200 error codes are derived from these at sync points)
 enum : unsigned {
-    ERR_GRID_BIN_TOO_SMALL = 1u,
-    ERR_GRID_OUT_OF_RANGE = 2u,
     ERR_HISTORY_OVERFLOW = 4u,
-    ERR_CONTACT_LIST_OVERFLOW = 8u,
+    ERR_NEIGHBOR_OVERFLOW = 8u,
     ERR_NAN = 16u,
     ERR_PAIR_CAPACITY = 32u
 };
@@ -36,8 +39,9 @@ enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1 };
 // (src/chrono/physics/ChContactMaterialSMC.cpp:107-130).
 struct Comp {
     double E_eff, G_eff, mu, mu_roll, mu_spin, cr, adh, adh_dmt, adh_perko, kn, kt, gn, gt;
-    // hoisted, material-only factors of the Hertz / PlainCoulomb / Flores damping (ChIterativeSolverMulticoreSMC.cpp:283-287)
+    // hoisted, material-only factors of the Hertz damping (ChIterativeSolverMulticoreSMC.cpp:283-287)
     double hertz_damp;  // -2*sqrt(5/6)*beta
+    double gt_ratio;    // sqrt(St/Sn) = sqrt(4 G_eff / E_eff):  gt = gn * gt_ratio
 };
 
 struct Wall {
@@ -50,50 +54,78 @@ struct Wall {
 };
 
 struct Params {
-    unsigned N;
+    unsigned N;   // spheres
+    unsigned Np;  // N rounded up to a multiple of 32: pitch of the column-major arrays
     int nW;
-    int K;
+    int K;        // history slots per sphere
+    int Kn;       // Verlet candidate slots per sphere
     int force_model, adhesion_model, tang_mode, use_mat_props, integrator;
     double char_vel, min_slip, min_roll, min_spin, dt;
     double g[3];
     double mass_coef, wall_mass;
     Comp comp[3];
     Wall walls[kMaxWalls];
-    int bins[3];
+    int bins[3];          // Multicore broadphase resolution (parity output only; the search grid is our own)
     unsigned shape_base;  // shape id of sphere sid is shape_base + sid
-    double rmax;          // largest sphere radius (grid validity check)
+    double rmax;          // largest sphere radius
+    double skin;          // Verlet skin: candidates are spheres closer than r_i + r_j + skin at rebuild time
+    unsigned cell_cap;    // capacity of the search-cell arrays
     double wall_bb_min[3], wall_bb_max[3];  // union of wall AABBs (infinite planes excluded)
     int has_wall_bb;
 };
 
-// Broadphase grid of the current step (device memory, written by k_grid_update)
+// 64-byte velocity record.  meta = history count (bits 0-7) | flags (bits 8-15: 1 = fixed)
+struct __align__(16) VelRec {
+    double v[3];
+    double w[3];
+    unsigned sid, meta;
+    double spare;
+};
+
+// Multicore broadphase grid of the current step (ChBroadphase.cpp:143-208)
 struct GridDev {
     double origin[3], bin[3], inv[3];
     double wmin[kMaxWalls][3], wmax[kMaxWalls][3];  // wall AABBs offset by the grid origin (ChBroadphase.cpp:168-176)
 };
 
+// Device-resident control block: everything a step needs to know about itself, so the same CUDA graph can be
+// replayed for every step (no host decision inside AdvanceSimulation).
+struct Ctrl {
+    unsigned cur;           // buffer index holding the state once all enqueued work has run
+    unsigned rb_src;        // this step: buffer the rebuild kernels read (they write rb_src ^ 1)
+    unsigned f_src;         // this step: buffer the force kernel reads (it writes f_src ^ 1)
+    unsigned rebuild_now;   // this step rebuilds the search grid and the candidate lists
+    unsigned need_rebuild;  // request (host: initialize / set_state)
+    unsigned err;
+    unsigned long long nsteps, nrebuilds;
+    unsigned long long bbox[6];   // order-preserving encoded doubles: min xyz, max xyz of the sphere AABBs
+    unsigned long long max_dx2;   // raw bits of max |x_new - x_old|^2 over the spheres, last step
+    double travel;                // sum of per-step max displacements since the last rebuild
+    // search grid (cells >= 2 rmax + skin), x fastest
+    double s_org[3], s_inv[3];
+    int s_dim[3];
+    unsigned s_ncell;
+    GridDev mc;
+    unsigned long long n_contacts, pair_count;
+};
+
 struct Buffers {
-    // state
-    double4* posA; double4* posB;
-    double* velA; double* velB;
-    uint32_t* sidA; uint32_t* sidB;
-    double* accA; double* accB;      // previous-step acceleration (Chung only), 6 per sphere
-    uint8_t* flags;                  // by sid: bit0 = fixed; may be null
-    // broadphase
+    Ctrl* ctrl;
+    // state, ping-pong
+    double4* pos[2];
+    VelRec* vel[2];
+    double* acc[2];       // previous-step acceleration (Chung only), 6 per sphere
+    double4* hist[2];     // [K][Np]
+    double* hrel[2];      // [K][Np] initial normal speed (only Hooke/Flores with material properties)
+    // neighbour search
     uint32_t* cell; uint32_t* rank; uint32_t* perm;
     uint32_t* cell_count; uint32_t* cell_start; uint32_t* block_sums;
-    GridDev* grid;
-    unsigned long long* bbox;        // 6 order-preserving encoded doubles: min xyz, max xyz of sphere AABBs
-    // history (rows by sid)
-    uint32_t* hkey_old; uint32_t* hkey_new;
-    double4* hval_old; double4* hval_new;
-    double* hrel_old; double* hrel_new;  // initial normal speed (only Hooke/Flores with material properties)
-    // diagnostics / recording
-    unsigned* err;
-    unsigned long long* n_contacts;  // running count of sphere-sphere + sphere-wall contacts of the last step
+    uint32_t* nl;         // [Kn][Np]
+    uint32_t* ncnt;       // [Np]
+    // recording (parity tests / smoke)
     double* recF; double* recT;      // by sid, 3 each
-    unsigned long long* pairs; unsigned long long* pair_count; unsigned long long pair_cap;
-    int* gmin; int* gmax;            // by sid, 3 each
+    unsigned long long* pairs; unsigned long long pair_cap;
+    int* gmin; int* gmax;            // by sid, 3 each: Multicore HashMin / HashMax of the sphere AABB
 };
 
 }  // namespace demb200

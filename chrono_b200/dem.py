@@ -30,7 +30,8 @@ class Config(C.Structure):
                 ("history_slots", C.c_int), ("char_vel", C.c_double), ("min_slip_vel", C.c_double),
                 ("min_roll_vel", C.c_double), ("min_spin_vel", C.c_double), ("dt", C.c_double),
                 ("gravity", C.c_double * 3), ("bins_per_axis", C.c_int * 3), ("material", Material * 3),
-                ("mass_coef", C.c_double), ("wall_mass", C.c_double), ("mesh_mass", C.c_double)]
+                ("mass_coef", C.c_double), ("wall_mass", C.c_double), ("mesh_mass", C.c_double),
+                ("verlet_skin", C.c_double), ("neighbor_slots", C.c_int)]
 
 
 def material(young=2e5, poisson=0.3, mu_s=0.6, mu_roll=0.0, mu_spin=0.0, cr=0.4, adhesion=0.0, adhesion_dmt=0.0,
@@ -39,10 +40,10 @@ def material(young=2e5, poisson=0.3, mu_s=0.6, mu_roll=0.0, mu_spin=0.0, cr=0.4,
 
 
 def config(device=0, force_model=HERTZ, adhesion_model=ADH_CONSTANT, tangential_mode=TANG_MULTISTEP,
-           use_mat_props=True, integrator=CENTERED_DIFFERENCE, history_slots=12, char_vel=1.0, min_slip_vel=1e-4,
+           use_mat_props=True, integrator=CENTERED_DIFFERENCE, history_slots=16, char_vel=1.0, min_slip_vel=1e-4,
            min_roll_vel=1e-4, min_spin_vel=1e-4, dt=1e-3, gravity=(0, 0, -9.81), bins=(10, 10, 10),
            mat_sphere=None, mat_wall=None, mat_mesh=None, mass_coef=4.0 / 3.0 * np.pi * 2000.0, wall_mass=1.0,
-           mesh_mass=1.0):
+           mesh_mass=1.0, verlet_skin=-1.0, neighbor_slots=0):
     c = Config()
     c.device = device
     c.force_model, c.adhesion_model, c.tangential_mode = force_model, adhesion_model, tangential_mode
@@ -56,6 +57,7 @@ def config(device=0, force_model=HERTZ, adhesion_model=ADH_CONSTANT, tangential_
     c.material[MAT_WALL] = mat_wall or ms
     c.material[MAT_MESH] = mat_mesh or ms
     c.mass_coef, c.wall_mass, c.mesh_mass = mass_coef, wall_mass, mesh_mass
+    c.verlet_skin, c.neighbor_slots = verlet_skin, neighbor_slots
     return c
 
 
@@ -243,6 +245,11 @@ class DemSystem:
                                                  _dp(out["duration"]), _dp(out["relvel_init"]), C.c_size_t(m),
                                                  C.byref(n)))
         return out
+
+    def stats(self):
+        a, b, c = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+        self._ck(self.L.dem_b200_get_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(steps=a.value, rebuilds=b.value, contacts_last_step=c.value)
 
     def add_history(self, owner_shape, other_shape, disp, duration=0.0, relvel_init=0.0):
         d = _f64(disp)

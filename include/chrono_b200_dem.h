@@ -32,10 +32,11 @@ enum {
     DEMB200_OK = 0,
     DEMB200_ECUDA = -1,    /* CUDA runtime error (no device, launch failure, ...) */
     DEMB200_EINVAL = -2,   /* bad argument / call order */
-    DEMB200_EGRID = -3,    /* bin edge < 2*Rmax, or a sphere left the hashable grid */
-    DEMB200_EHISTORY = -4, /* a sphere needs more contact-history slots than history_slots */
+    DEMB200_EGRID = -3,    /* reserved (the search grid adapts itself; kept for ABI stability) */
+    DEMB200_EHISTORY = -4, /* a sphere has more simultaneous contacts than history_slots */
     DEMB200_ENAN = -5,     /* non-finite state detected */
-    DEMB200_ECAPACITY = -6 /* a recording buffer (pairs) overflowed */
+    DEMB200_ECAPACITY = -6, /* a recording buffer (pairs) overflowed */
+    DEMB200_ENEIGHBORS = -7 /* a sphere has more neighbour candidates than neighbor_slots */
 };
 
 /* ChSystemSMC::ContactForceModel / AdhesionForceModel / TangentialDisplacementModel
@@ -62,15 +63,21 @@ typedef struct dem_b200_config {
     int device;           /* CUDA device ordinal */
     int force_model, adhesion_model, tangential_mode, use_mat_props;
     int integrator;
-    int history_slots;    /* contact-history slots per sphere (reference Dem: 12, Multicore: 20); 0 -> 12 */
+    int history_slots;    /* contact records per sphere, walls included (reference Dem: 12, Multicore: 20 on the
+                             higher-id body only); every sphere keeps a record of each of its contacts; 0 -> 16, max 32 */
     double char_vel, min_slip_vel, min_roll_vel, min_spin_vel; /* ChSettings.h:121-124 */
     double dt;
     double gravity[3];
-    int bins_per_axis[3]; /* broadphase grid resolution (collision_settings::bins_per_axis) */
+    int bins_per_axis[3]; /* Multicore broadphase resolution (collision_settings::bins_per_axis): defines the bin ids
+                             reported by dem_b200_get_bins/get_grid; the engine's own search grid is independent */
     dem_b200_material material[3]; /* [DEMB200_MAT_SPHERE|WALL|MESH] */
     double mass_coef;     /* sphere mass = mass_coef * (r*r*r)  (= 4/3 pi rho for solid spheres) */
     double wall_mass;     /* mass of the body carrying the walls; enters m_eff (Multicore Q9) */
     double mesh_mass;     /* default mass of mesh bodies */
+    double verlet_skin;   /* neighbour candidates = spheres closer than r_i + r_j + skin when the lists are built; the
+                             lists are rebuilt (on the device, no host round trip) before any sphere can have moved
+                             skin/2.  < 0 -> 0.25 * largest radius; 0 -> rebuild every step */
+    int neighbor_slots;   /* candidate slots per sphere; 0 -> 32, max 64 */
 } dem_b200_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------- */
@@ -116,7 +123,8 @@ double dem_b200_time(const dem_b200_system* s);
 
 /* ---- reductions -- GetMaxParticleZ, GetParticlesKineticEnergy, ... (ChSystemDem.h:246-262) ------------------ */
 enum { DEMB200_RED_MAX_Z = 0, DEMB200_RED_MIN_Z = 1, DEMB200_RED_KE = 2, DEMB200_RED_MAX_SPEED = 3,
-       DEMB200_RED_COUNT_ABOVE_Z = 4, DEMB200_RED_COUNT_ABOVE_X = 5, DEMB200_RED_NUM_CONTACTS = 6 };
+       DEMB200_RED_COUNT_ABOVE_Z = 4, DEMB200_RED_COUNT_ABOVE_X = 5,
+       DEMB200_RED_NUM_CONTACTS = 6 /* sum over spheres of their force-carrying contacts (MultiStep only) */ };
 int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out);
 
 /* ---- parity / inspection (tests, smoke) ---------------------------------------------------------------------- */
@@ -134,6 +142,10 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
 int dem_b200_add_history(dem_b200_system* s, uint32_t owner_shape, uint32_t other_shape, const double disp[3],
                          double duration, double relvel_init);
 int dem_b200_num_walls(const dem_b200_system* s);
+/* steps executed, neighbour-list rebuilds among them, contacts (sphere-sphere counted from both sides + sphere-wall)
+ * seen by the last recorded step */
+int dem_b200_get_stats(dem_b200_system* s, unsigned long long* nsteps, unsigned long long* nrebuilds,
+                       unsigned long long* contacts_last_step);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None
 
 
 def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
-             integrator=None, history_slots=12, **model):
+             integrator=None, history_slots=16, **model):
     from chrono_b200 import dem
     mat = mat or settling_material()
     kw = dict(model)

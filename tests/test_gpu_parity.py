@@ -183,12 +183,45 @@ def test_reductions_and_single_sphere_access():
     assert np.array_equal(p7, pos[7]) and np.array_equal(v7, v[7]) and np.array_equal(w7, w[7])
 
 
-def test_grid_error_is_reported():
-    """Bins smaller than a sphere diameter must fail loudly, not silently miss contacts."""
+def test_bins_smaller_than_a_sphere():
+    """Multicore registers a shape in every bin its AABB overlaps, so a resolution with bins smaller than a sphere
+    diameter is legal there.  The engine's own search grid is independent of bins_per_axis: pair lists, bin ranges
+    and forces must still match the oracle."""
+    scene = scenes.settling_scene(600, sep_factor=1.97, seed=3)
+    scene = dict(scene, bins=(60, 60, 30))
+    vel, om = kinematics(600, 12)
+    compare_step(scene, vel, om, steps=2, dt=1e-4)
+
+
+@pytest.mark.parametrize("skin", [0.0, 0.1, 2.0])
+def test_verlet_skin_does_not_change_a_bit(skin):
+    """The candidate lists only bound the search: any skin (0 = rebuild every step) gives bit-identical states, and
+    the rebuild count drops as the skin grows."""
     from chrono_b200 import dem
-    scene = scenes.settling_scene(500, seed=3)
-    scene = dict(scene, bins=(400, 400, 200))
-    g = common.make_gpu(scene)
+    scene = scenes.settling_scene(3000, sep_factor=1.99, seed=31)
+    vel, om = kinematics(3000, 7, vscale=0.3)
+    ref = common.make_gpu(scene, vel=vel, omega=om, dt=1e-4, verlet_skin=0.25 * 0.02)
+    g = common.make_gpu(scene, vel=vel, omega=om, dt=1e-4, verlet_skin=skin * 0.02, neighbor_slots=64)
+    ref.step(60)
+    g.step(60)
+    for x, y in zip(ref.state(), g.state()):
+        assert np.array_equal(x, y)
+    st = g.stats()
+    assert st["steps"] == 60
+    if skin == 0.0:
+        assert st["rebuilds"] == 60
+    else:
+        assert 1 <= st["rebuilds"] < 60
+    hr, hg = ref.history(), g.history()
+    kr = np.argsort((hr["owner"].astype(np.int64) << 32) | hr["other"]); kg = np.argsort((hg["owner"].astype(np.int64) << 32) | hg["other"])
+    assert np.array_equal(hr["owner"][kr], hg["owner"][kg]) and np.array_equal(hr["disp"][kr], hg["disp"][kg])
+
+
+def test_history_overflow_is_reported():
+    """More simultaneous contacts than history_slots must fail loudly, not silently drop a contact."""
+    from chrono_b200 import dem
+    scene = scenes.settling_scene(500, sep_factor=1.9, seed=3)
+    g = common.make_gpu(scene, history_slots=4)
     with pytest.raises(dem.DemError) as e:
         g.step(1)
-    assert e.value.code == -3
+    assert e.value.code == -4
