@@ -555,16 +555,21 @@ int dem_b200_initialize(dem_b200_system* s) {
     s->use_hrel = hist && P.use_mat_props && (P.force_model == DEMB200_HOOKE || P.force_model == DEMB200_FLORES);
 
     int rc = 0;
+    const size_t HS = (size_t)P.Kn + (size_t)P.nW;  // history slots per sphere: one per candidate + one per wall
     rc |= dev_alloc(s, &B.ctrl, 1);
     for (int b = 0; b < 2; b++) {
         rc |= dev_alloc(s, &B.pos[b], Np);
         rc |= dev_alloc(s, &B.vel[b], Np);
         if (P.integrator == DEMB200_CHUNG)
             rc |= dev_alloc(s, &B.acc[b], 6 * Np);
-        if (hist) {
-            rc |= dev_alloc(s, &B.hist[b], K * Np);
-            if (s->use_hrel)
-                rc |= dev_alloc(s, &B.hrel[b], K * Np);
+    }
+    if (hist) {
+        rc |= dev_alloc(s, &B.hist, HS * Np);
+        rc |= dev_alloc(s, &B.stage, K * Np);
+        rc |= dev_alloc(s, &B.stage_cnt, Np);
+        if (s->use_hrel) {
+            rc |= dev_alloc(s, &B.hrel, HS * Np);
+            rc |= dev_alloc(s, &B.stage_rel, K * Np);
         }
     }
     rc |= dev_alloc(s, &B.cell, Np); rc |= dev_alloc(s, &B.rank, Np); rc |= dev_alloc(s, &B.perm, Np);
@@ -576,8 +581,8 @@ int dem_b200_initialize(dem_b200_system* s) {
     if (rc)
         return DEMB200_ECUDA;
 
-    // history supplied before initialize (checkpoint restart): every sphere taking part in a contact gets a record,
-    // columns ordered by key (walls first, then partner shape ids)
+    // history supplied before initialize (checkpoint restart): every sphere taking part in a contact gets a record
+    // (keyed by the partner's shape id); the first rebuild moves them into the candidate slots
     std::vector<std::vector<dem_b200_system::HRow>> rows;
     if (hist && !s->h_hist.empty()) {
         rows.resize(n);
@@ -598,13 +603,17 @@ int dem_b200_initialize(dem_b200_system* s) {
                 rows[r.other - P.shape_base].push_back(m);
             }
         }
-        for (auto& v : rows) {
-            std::sort(v.begin(), v.end(), [](const dem_b200_system::HRow& a, const dem_b200_system::HRow& b) { return a.other < b.other; });
+        for (auto& v : rows)
             if (v.size() > K) {
                 s->err = "add_history: too many rows for one sphere";
                 return DEMB200_EHISTORY;
             }
-        }
+        rc |= dev_alloc(s, &B.stage_init, K * Np);
+        rc |= dev_alloc(s, &B.stage_cnt_init, Np);
+        if (s->use_hrel)
+            rc |= dev_alloc(s, &B.stage_rel_init, K * Np);
+        if (rc)
+            return DEMB200_ECUDA;
     }
 
     // upload (storage order = user order initially; the first step sorts by search cell)
@@ -619,23 +628,28 @@ int dem_b200_initialize(dem_b200_system* s) {
                 hv[i].w[k] = s->h_om[3 * i + k];
             }
             hv[i].sid = (uint32_t)i;
-            hv[i].meta = (rows.empty() ? 0u : (unsigned)rows[i].size()) | ((s->h_fixed[i] ? 1u : 0u) << 8);
+            hv[i].meta = s->h_fixed[i] ? 1u : 0u;
+            hv[i].amask = 0ull;
         }
         for (int b = 0; b < 2; b++) {
             CU(cudaMemcpy(B.pos[b], hp.data(), Np * sizeof(double4), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(B.vel[b], hv.data(), Np * sizeof(VelRec), cudaMemcpyHostToDevice));
             if (B.acc[b])
                 CU(cudaMemset(B.acc[b], 0, 6 * Np * sizeof(double)));
-            if (B.hist[b])
-                CU(cudaMemset(B.hist[b], 0xFF, K * Np * sizeof(double4)));
-            if (B.hrel[b])
-                CU(cudaMemset(B.hrel[b], 0, K * Np * sizeof(double)));
         }
+        if (B.hist) {
+            CU(cudaMemset(B.hist, 0, HS * Np * sizeof(double4)));
+            CU(cudaMemset(B.stage_cnt, 0, Np * sizeof(uint32_t)));
+        }
+        if (B.hrel)
+            CU(cudaMemset(B.hrel, 0, HS * Np * sizeof(double)));
     }
     if (!rows.empty()) {
         std::vector<double4> hh(K * Np, make_double4(0, 0, 0, 0));
         std::vector<double> hr(s->use_hrel ? K * Np : 0, 0.0);
-        for (size_t i = 0; i < n; i++)
+        std::vector<uint32_t> hcn(Np, 0);
+        for (size_t i = 0; i < n; i++) {
+            hcn[i] = (uint32_t)rows[i].size();
             for (size_t k = 0; k < rows[i].size(); k++) {
                 const auto& r = rows[i][k];
                 const unsigned steps = (unsigned)std::llround(r.dur / P.dt);
@@ -646,9 +660,11 @@ int dem_b200_initialize(dem_b200_system* s) {
                 if (s->use_hrel)
                     hr[k * Np + i] = r.rel;
             }
-        CU(cudaMemcpy(B.hist[0], hh.data(), K * Np * sizeof(double4), cudaMemcpyHostToDevice));
+        }
+        CU(cudaMemcpy(B.stage_init, hh.data(), K * Np * sizeof(double4), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(B.stage_cnt_init, hcn.data(), Np * sizeof(uint32_t), cudaMemcpyHostToDevice));
         if (s->use_hrel)
-            CU(cudaMemcpy(B.hrel[0], hr.data(), K * Np * sizeof(double), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(B.stage_rel_init, hr.data(), K * Np * sizeof(double), cudaMemcpyHostToDevice));
     }
     CU(cudaMemset(B.cell_count, 0, ((size_t)P.cell_cap + 8) * sizeof(uint32_t)));
     CU(cudaMemset(B.ncnt, 0, Np * sizeof(uint32_t)));
@@ -657,6 +673,7 @@ int dem_b200_initialize(dem_b200_system* s) {
         memset(&c, 0, sizeof(c));
         c.cur = 0;
         c.need_rebuild = 1;
+        c.init_stage = rows.empty() ? 0u : 1u;
         CU(cudaMemcpy(B.ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice));
     }
     s->h_pos.clear(); s->h_pos.shrink_to_fit();
@@ -948,37 +965,46 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
     int rc = read_ctrl(s, &c);
     if (rc)
         return rc;
-    const size_t N = s->P.N, K = s->P.K, Np = s->P.Np;
+    const size_t N = s->P.N, Np = s->P.Np, Kn = s->P.Kn, HS = Kn + (size_t)s->P.nW;
     std::vector<VelRec> vr(N);
-    std::vector<double4> vals(K * Np);
+    std::vector<double4> vals(HS * Np);
+    std::vector<uint32_t> nl(Kn * Np);
     std::vector<double> rels;
     CU(cudaMemcpy(vr.data(), s->B.vel[c.cur], N * sizeof(VelRec), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(vals.data(), s->B.hist[c.cur], K * Np * sizeof(double4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vals.data(), s->B.hist, HS * Np * sizeof(double4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(nl.data(), s->B.nl, Kn * Np * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (s->use_hrel) {
-        rels.resize(K * Np);
-        CU(cudaMemcpy(rels.data(), s->B.hrel[c.cur], K * Np * sizeof(double), cudaMemcpyDeviceToHost));
+        rels.resize(HS * Np);
+        CU(cudaMemcpy(rels.data(), s->B.hrel, HS * Np * sizeof(double), cudaMemcpyDeviceToHost));
     }
     // Both partners of a sphere-sphere contact hold a copy; report the one of the higher shape id, which is where
     // Chrono::Multicore keeps it (ChIterativeSolverMulticoreSMC.cpp:194-199).
     size_t cnt = 0;
-    for (size_t i = 0; i < N; i++) {
-        const uint32_t me = s->P.shape_base + vr[i].sid;
-        const size_t hc = vr[i].meta & 0xFFu;
-        for (size_t k = 0; k < hc && k < K; k++) {
-            const double4 v = vals[k * Np + i];
+    auto emit = [&](uint32_t me, uint32_t key, size_t at) {
+        if (cnt < capacity) {
+            const double4 v = vals[at];
             unsigned long long bits;
             memcpy(&bits, &v.w, 8);
-            const uint32_t key = (uint32_t)(bits & 0xFFFFFFFFull), steps = (uint32_t)(bits >> 32);
-            if (key == kEmptyKey || key > me)
+            if (owner) owner[cnt] = me;
+            if (other) other[cnt] = key;
+            if (disp3) { disp3[3 * cnt] = v.x; disp3[3 * cnt + 1] = v.y; disp3[3 * cnt + 2] = v.z; }
+            if (duration) duration[cnt] = (double)(uint32_t)(bits >> 32) * s->P.dt;
+            if (relvel_init) relvel_init[cnt] = s->use_hrel ? rels[at] : 0.0;
+        }
+        cnt++;
+    };
+    for (size_t i = 0; i < N; i++) {
+        const uint32_t me = s->P.shape_base + vr[i].sid;
+        const unsigned wmask = (vr[i].meta >> 8) & 0xFFFFu;
+        for (int w = 0; w < s->P.nW; w++)
+            if ((wmask >> w) & 1u)
+                emit(me, (uint32_t)w, (Kn + (size_t)w) * Np + i);
+        for (size_t k = 0; k < Kn; k++) {
+            if (!((vr[i].amask >> k) & 1ull))
                 continue;
-            if (cnt < capacity) {
-                if (owner) owner[cnt] = me;
-                if (other) other[cnt] = key;
-                if (disp3) { disp3[3 * cnt] = v.x; disp3[3 * cnt + 1] = v.y; disp3[3 * cnt + 2] = v.z; }
-                if (duration) duration[cnt] = (double)steps * s->P.dt;
-                if (relvel_init) relvel_init[cnt] = s->use_hrel ? rels[k * Np + i] : 0.0;
-            }
-            cnt++;
+            const uint32_t key = s->P.shape_base + vr[nl[k * Np + i]].sid;
+            if (key < me)
+                emit(me, key, k * Np + i);
         }
     }
     *n = cnt;

@@ -84,6 +84,7 @@ __device__ __forceinline__ double sphere_mass(const Params& P, double r) {
 struct VelVal {
     V3 v, w;
     unsigned sid, meta;
+    unsigned long long amask;
 };
 __device__ __forceinline__ VelVal load_vel(const VelRec* __restrict__ a, size_t i) {
     const double2* q = reinterpret_cast<const double2*>(a + i);
@@ -93,19 +94,40 @@ __device__ __forceinline__ VelVal load_vel(const VelRec* __restrict__ a, size_t 
     r.w = mk(q1.y, q2.x, q2.y);
     r.sid = (unsigned)__double2loint(q3.x);
     r.meta = (unsigned)__double2hiint(q3.x);
+    r.amask = (unsigned long long)__double_as_longlong(q3.y);
     return r;
 }
-__device__ __forceinline__ void store_vel(VelRec* a, size_t i, V3 v, V3 w, unsigned sid, unsigned meta) {
+__device__ __forceinline__ void store_vel(VelRec* a, size_t i, V3 v, V3 w, unsigned sid, unsigned meta,
+                                          unsigned long long amask) {
     double2* q = reinterpret_cast<double2*>(a + i);
     q[0] = make_double2(v.x, v.y);
     q[1] = make_double2(v.z, w.x);
     q[2] = make_double2(w.y, w.z);
-    q[3] = make_double2(__hiloint2double((int)meta, (int)sid), 0.0);
+    q[3] = make_double2(__hiloint2double((int)meta, (int)sid), __longlong_as_double((long long)amask));
 }
-// history record: (disp xyz, packed key | steps << 32)
+// history record: (disp xyz, packed key | steps << 32); the key is only meaningful in the staging buffers
 __device__ __forceinline__ double pack_key(unsigned key, unsigned steps) { return __hiloint2double((int)steps, (int)key); }
 __device__ __forceinline__ unsigned rec_key(double w) { return (unsigned)__double2loint(w); }
 __device__ __forceinline__ unsigned rec_steps(double w) { return (unsigned)__double2hiint(w); }
+
+// Fast reciprocal / reciprocal square root for normal, positive, well-scaled arguments: hardware seed
+// (MUFU.RCP64H / MUFU.RSQ64H, ~2^-23) + one cubically convergent correction, error <= ~1 ulp, no special-case branch.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = y * y;
+    const double e = fma(x, -t, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double q = y * e;
+    return fma(p, q, y);
+}
 
 // --------------------------------------------------------------------------------------------
 // bounding box of all sphere AABBs (init / after set_state); per step it is fused into k_force_integrate
@@ -159,6 +181,8 @@ __global__ void k_step_begin(Params P, Buffers B) {
     C.max_dx2 = 0ull;
     C.travel += dx;
     const bool rebuild = (C.need_rebuild != 0) || !(C.travel < 0.499 * P.skin);
+    if (C.nrebuilds >= 1)
+        C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
 
     // ---- bounding box of all shapes at the start of this step ----
     double mn[3], mx[3];
@@ -445,7 +469,7 @@ __global__ void __launch_bounds__(256) k_scatter_perm(Params P, Buffers B) {
 }
 
 __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
-    const Ctrl& C = *B.ctrl;
+    Ctrl& C = *B.ctrl;
     if (!C.rebuild_now)
         return;
     const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,24 +481,61 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
     const double2* vs = reinterpret_cast<const double2*>(B.vel[a] + src);
     double2* vd = reinterpret_cast<double2*>(B.vel[b] + s);
     const double2 q0 = vs[0], q1 = vs[1], q2 = vs[2], q3 = vs[3];
-    vd[0] = q0; vd[1] = q1; vd[2] = q2; vd[3] = q3;
+    vd[0] = q0; vd[1] = q1; vd[2] = q2; vd[3] = q3;  // masks are rewritten by k_build_list
     if (B.acc[0]) {
         const double2* as = reinterpret_cast<const double2*>(B.acc[a] + 6 * (size_t)src);
         double2* ad = reinterpret_cast<double2*>(B.acc[b] + 6 * (size_t)s);
         ad[0] = as[0]; ad[1] = as[1]; ad[2] = as[2];
     }
-    if (B.hist[0]) {
-        const unsigned hc = ((unsigned)__double2hiint(q3.x)) & 0xFFu;
-        for (unsigned k = 0; k < hc; k++) {
-            const size_t si = (size_t)k * P.Np + src, di = (size_t)k * P.Np + s;
-            const double2* hs = reinterpret_cast<const double2*>(B.hist[a] + si);
-            double2* hd = reinterpret_cast<double2*>(B.hist[b] + di);
-            hd[0] = hs[0];
-            hd[1] = hs[1];
-            if (B.hrel[0])
-                B.hrel[b][di] = B.hrel[a][si];
+    if (!B.hist)
+        return;
+    // Live history records leave the old candidate slots: compact them, keyed by partner shape id, into the staging
+    // column of the sphere's NEW storage slot; k_build_list drops them into the slots of the new candidate list.
+    unsigned cnt = 0;
+    if (C.init_stage && B.stage_init) {
+        cnt = B.stage_cnt_init[src];
+        for (unsigned k = 0; k < cnt; k++) {
+            B.stage[(size_t)k * P.Np + s] = B.stage_init[(size_t)k * P.Np + src];
+            if (B.stage_rel)
+                B.stage_rel[(size_t)k * P.Np + s] = B.stage_rel_init[(size_t)k * P.Np + src];
+        }
+    } else {
+        const unsigned meta = (unsigned)__double2hiint(q3.x);
+        unsigned wmask = (meta >> 8) & 0xFFFFu;
+        unsigned long long amask = (unsigned long long)__double_as_longlong(q3.y);
+        while (wmask) {
+            const int w = __ffs(wmask) - 1;
+            wmask &= wmask - 1;
+            const size_t si = (size_t)(P.Kn + w) * P.Np + src;
+            if (cnt < (unsigned)P.K) {
+                double4 r = B.hist[si];
+                r.w = pack_key((unsigned)w, rec_steps(r.w));
+                B.stage[(size_t)cnt * P.Np + s] = r;
+                if (B.stage_rel)
+                    B.stage_rel[(size_t)cnt * P.Np + s] = B.hrel[si];
+            }
+            cnt++;
+        }
+        while (amask) {
+            const int k = __ffsll((long long)amask) - 1;
+            amask &= amask - 1;
+            const size_t si = (size_t)k * P.Np + src;
+            if (cnt < (unsigned)P.K) {
+                const unsigned jo = B.nl[si];  // old storage slot of the partner
+                double4 r = B.hist[si];
+                r.w = pack_key(P.shape_base + B.vel[a][jo].sid, rec_steps(r.w));
+                B.stage[(size_t)cnt * P.Np + s] = r;
+                if (B.stage_rel)
+                    B.stage_rel[(size_t)cnt * P.Np + s] = B.hrel[si];
+            }
+            cnt++;
+        }
+        if (cnt > (unsigned)P.K) {
+            atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
+            cnt = P.K;
         }
     }
+    B.stage_cnt[s] = cnt;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -490,7 +551,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     if (s >= P.N)
         return;
     const double4* __restrict__ pos = B.pos[C.f_src];
-    const VelRec* __restrict__ vel = B.vel[C.f_src];
+    const VelRec* vel = B.vel[C.f_src];
     const double4 me = pos[s];
     const int cx = cell_coord(me.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
     const int cy = cell_coord(me.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
@@ -546,6 +607,37 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     for (int k = 0; k < cnt; k++)
         B.nl[(size_t)k * P.Np + s] = tj[k];
     B.ncnt[s] = (unsigned)cnt;
+    // staged history -> slots of the new list (a record whose partner is no longer a candidate is dropped: that
+    // contact has broken)
+    if (B.hist) {
+        unsigned long long amask = 0ull;
+        unsigned wmask = 0u;
+        const unsigned sc = B.stage_cnt[s];
+        for (unsigned c = 0; c < sc; c++) {
+            const double4 r = B.stage[(size_t)c * P.Np + s];
+            const unsigned key = rec_key(r.w);
+            size_t di;
+            if (key < P.shape_base) {
+                di = (size_t)(P.Kn + key) * P.Np + s;
+                wmask |= 1u << key;
+            } else {
+                const unsigned ps = key - P.shape_base;
+                int k = 0;
+                while (k < cnt && ts[k] != ps)
+                    k++;
+                if (k == cnt)
+                    continue;
+                di = (size_t)k * P.Np + s;
+                amask |= 1ull << k;
+            }
+            B.hist[di] = r;
+            if (B.hrel)
+                B.hrel[di] = B.stage_rel[(size_t)c * P.Np + s];
+        }
+        VelRec* vr = B.vel[C.f_src] + s;
+        vr->meta = (vr->meta & 0xFFu) | (wmask << 8);
+        vr->amask = amask;
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -770,7 +862,7 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     const double eps = 2.220446049250313e-16;
     const double radSum = __dadd_rn(ra, rb);
     const double delta_n = radSum - dist;
-    const double erad = __dmul_rn(ra, rb) * __drcp_rn(radSum);
+    const double erad = __dmul_rn(ra, rb) * fast_rcp(radSum);
     // velocity of b's contact point minus a's:  (vb + wb x (-n rb)) - (va + wa x (n ra))
     const V3 wsum = mk(__dadd_rn(__dmul_rn(ra, wa.x), __dmul_rn(rb, wb.x)), __dadd_rn(__dmul_rn(ra, wa.y), __dmul_rn(rb, wb.y)),
                        __dadd_rn(__dmul_rn(ra, wa.z), __dmul_rn(rb, wb.z)));
@@ -778,7 +870,7 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     const V3 relvel = (vb - va) - wxn;
     const double vn = dot(relvel, n);
     const V3 relvel_t = relvel - vn * n;
-    const double m_eff = __dmul_rn(ma, mb) * __drcp_rn(__dadd_rn(ma, mb));
+    const double m_eff = __dmul_rn(ma, mb) * fast_rcp(__dadd_rn(ma, mb));
 
     V3 delta_t = mk(0, 0, 0);
     if (HIST) {
@@ -797,13 +889,13 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     }
 
     const double x = erad * delta_n;
-    const double sqrt_Rd = x * rsqrt(x);
+    const double sqrt_Rd = x * fast_rsqrt(x);
     const double Sn = 2 * cm.E_eff * sqrt_Rd;
     const double St = 8 * cm.G_eff * sqrt_Rd;
     const double kn = (2.0 / 3.0) * Sn;
     const double kt = St;
     const double y = Sn * m_eff;
-    const double gn = cm.hertz_damp * (y * rsqrt(y));
+    const double gn = cm.hertz_damp * (y * fast_rsqrt(y));
     const double gt = gn * cm.gt_ratio;
 
     const double fN = kn * delta_n - gn * vn;
@@ -813,10 +905,10 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     const double slide = cm.mu * fabs(fN);
     if (ft2 > slide * slide) {
         if (dot(delta_t, delta_t) > eps * eps) {
-            const double ratio = slide * rsqrt(ft2);
+            const double ratio = slide * fast_rsqrt(ft2);
             fT = fT * ratio;
             if (HIST) {
-                delta_t = (fT - fT_damp) * __drcp_rn(kt);
+                delta_t = (fT - fT_damp) * fast_rcp(kt);
                 disp = -delta_t;
             }
         } else {
@@ -910,46 +1002,11 @@ __device__ __forceinline__ bool plane_sphere_dev(const Wall& W, V3 pos2, double 
 // --------------------------------------------------------------------------------------------
 constexpr int kForceThreads = 128;
 
-// cursor over the sphere's own (old) history column; records are ordered by key (walls, then partner ids)
-struct HistCursor {
-    const double4* __restrict__ col;  // &hist_in[s]
-    const double* __restrict__ rel;   // &hrel_in[s] or null
-    size_t pitch;
-    unsigned t, n;
-    double2 a, b;  // record t (prefetched)
-    unsigned key;
-    __device__ __forceinline__ void fetch() {
-        if (t < n) {
-            const double2* q = reinterpret_cast<const double2*>(col + (size_t)t * pitch);
-            a = q[0];
-            b = q[1];
-            key = rec_key(b.y);
-        } else {
-            key = kEmptyKey;
-        }
-    }
-    // true if the sphere had a record for `k` last step; afterwards the cursor sits on the next record
-    __device__ __forceinline__ bool find(unsigned k, V3& disp, unsigned& steps, double& relvel0) {
-        while (key < k) {
-            t++;
-            fetch();
-        }
-        if (key != k)
-            return false;
-        disp = mk(a.x, a.y, b.x);
-        steps = rec_steps(b.y);
-        if (rel)
-            relvel0 = rel[(size_t)t * pitch];
-        t++;
-        fetch();
-        return true;
-    }
-};
-
 template <bool HIST, bool ROLL, bool FAST, bool REC>
 __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __grid_constant__ Params P,
                                                                       const __grid_constant__ Buffers B) {
-    __shared__ unsigned clist[kMaxSlots * kForceThreads];
+    __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
+    __shared__ unsigned char cslot[kMaxSlots * kForceThreads];  // its index in the candidate list (= history slot)
     Ctrl& C = *B.ctrl;
     const unsigned src = C.f_src, dst = src ^ 1u;
     const double4* __restrict__ pos_in = B.pos[src];
@@ -961,7 +1018,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
 
     double4 me = make_double4(0, 0, 0, 1.0);
     VelVal mv;
-    mv.v = mk(0, 0, 0); mv.w = mk(0, 0, 0); mv.sid = 0; mv.meta = 0;
+    mv.v = mk(0, 0, 0); mv.w = mk(0, 0, 0); mv.sid = 0; mv.meta = 0; mv.amask = 0ull;
     int cnt = 0;
     if (valid) {
         me = pos_in[s];
@@ -969,18 +1026,30 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
         // ---- phase 1: exact sphere_sphere test (ChNarrowphasePRIMS.cpp:50-59, separation = 0) on the candidates
         const unsigned nc = B.ncnt[s];
         const uint32_t* __restrict__ nl = B.nl + s;
-#pragma unroll 4
-        for (unsigned k = 0; k < nc; k++) {
-            const unsigned j = nl[(size_t)k * P.Np];
-            const double4 pj = pos_in[j];
-            const V3 d = mk(__dsub_rn(pj.x, me.x), __dsub_rn(pj.y, me.y), __dsub_rn(pj.z, me.z));
-            const double dist2 = dot_rn(d, d);
-            const double rs = __dadd_rn(me.w, pj.w);
-            if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
-                continue;
-            if (cnt < kMaxSlots)
-                clist[cnt * kForceThreads + tid] = j;
-            cnt++;
+        // batches of 4: the 4 candidate ids, then the 4 positions, are independent loads in flight together
+        for (unsigned k0 = 0; k0 < nc; k0 += 4) {
+            unsigned jj[4];
+            double4 pp[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                jj[u] = (k0 + u < nc) ? nl[(size_t)(k0 + u) * P.Np] : s;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                pp[u] = pos_in[jj[u]];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const V3 d = mk(__dsub_rn(pp[u].x, me.x), __dsub_rn(pp[u].y, me.y), __dsub_rn(pp[u].z, me.z));
+                const double dist2 = dot_rn(d, d);
+                const double rs = __dadd_rn(me.w, pp[u].w);
+                // (a padding lane compares the sphere with itself: dist2 = 0 < 1e-12, rejected)
+                if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
+                    continue;
+                if (cnt < kMaxSlots) {
+                    clist[cnt * kForceThreads + tid] = jj[u];
+                    cslot[cnt * kForceThreads + tid] = (unsigned char)(k0 + u);
+                }
+                cnt++;
+            }
         }
         if (cnt > kMaxSlots) {
             atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
@@ -988,28 +1057,20 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
         }
     }
     const unsigned sid = mv.sid;
-    const unsigned flags = (mv.meta >> 8) & 0xFFu;
+    const unsigned flags = mv.meta & 0xFFu;
+    const unsigned wmask_old = (mv.meta >> 8) & 0xFFFFu;
+    const unsigned long long amask_old = mv.amask;
+    unsigned wmask_new = 0u;
+    unsigned long long amask_new = 0ull;
     const double my_mass = sphere_mass(P, me.w);
     V3 Fsum = mk(0, 0, 0), Tsum = mk(0, 0, 0);
-    int nh = 0;  // history records written by this sphere
     unsigned ncontacts = 0;
-    HistCursor hc;
-    hc.t = 0; hc.n = 0; hc.key = kEmptyKey; hc.rel = nullptr; hc.pitch = P.Np; hc.col = nullptr;
-    double4* hout = nullptr;
-    double* hrout = nullptr;
-    if (HIST && valid) {
-        hc.col = B.hist[src] + s;
-        hc.rel = B.hrel[src] ? B.hrel[src] + s : nullptr;
-        hc.n = mv.meta & 0xFFu;
-        hc.fetch();
-        hout = B.hist[dst] + s;
-        hrout = B.hrel[dst] ? B.hrel[dst] + s : nullptr;
-    }
+    double4* const hcol = HIST ? B.hist + s : nullptr;            // my column of history records
+    double* const rcol = (HIST && B.hrel) ? B.hrel + s : nullptr;
     const V3 mpos = mk(me.x, me.y, me.z);
 
     if (valid) {
-        // ---- walls first (history keys 0..nW-1 sort before every sphere key): body 1 = wall body (lower id),
-        //      body 2 = this sphere
+        // ---- walls first: body 1 = wall body (lower id), body 2 = this sphere
         double amin[3], amax[3];
         sphere_aabb_offset(me, G.origin, amin, amax);
         for (int w = 0; w < P.nW; w++) {
@@ -1037,13 +1098,16 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
                 continue;
             Hist h{mk(0, 0, 0), 0.0, 0.0, true};
             unsigned steps = 0;
-            const unsigned key = (unsigned)w;
-            if (HIST) {
-                if (hc.find(key, h.disp, steps, h.relvel0)) {
-                    h.isnew = false;
-                    h.dur = (double)steps * P.dt;
-                    steps++;
-                }
+            const size_t hi = (size_t)(P.Kn + w) * P.Np;
+            if (HIST && ((wmask_old >> w) & 1u)) {
+                const double4 r = hcol[hi];
+                h.disp = mk(r.x, r.y, r.z);
+                steps = rec_steps(r.w);
+                h.dur = (double)steps * P.dt;
+                if (rcol)
+                    h.relvel0 = rcol[hi];
+                h.isnew = false;
+                steps++;
             }
             Body b1{mk(0, 0, 0), mk(W.vel[0], W.vel[1], W.vel[2]), mk(0, 0, 0), P.wall_mass};
             Body b2{mpos, mv.v, mv.w, my_mass};
@@ -1052,69 +1116,77 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             Fsum = Fsum + F;
             Tsum = Tsum + T2;
             if (HIST) {
-                if (nh < P.K) {
-                    double2* q = reinterpret_cast<double2*>(hout + (size_t)nh * P.Np);
-                    q[0] = make_double2(h.disp.x, h.disp.y);
-                    q[1] = make_double2(h.disp.z, pack_key(key, steps));
-                    if (hrout)
-                        hrout[(size_t)nh * P.Np] = h.relvel0;
-                }
-                nh++;
+                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, pack_key((unsigned)w, steps));
+                if (rcol)
+                    rcol[hi] = h.relvel0;
+                wmask_new |= 1u << w;
             }
         }
     }
 
-    // ---- phase 2: all lanes evaluate their k-th sphere contact together (contacts are in stable-id order) ----
+    // ---- phase 2: all lanes evaluate their k-th sphere contact together (contacts are in stable-id order).
+    //      Software pipeline: partner state and history record of contact k+1 are in flight while k is evaluated.
     const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+    double4 pj_next = me;
+    VelVal ov_next = mv;
+    double4 hr_next = make_double4(0, 0, 0, 0);
+    unsigned slot_next = 0;
+    if (cnt > 0) {
+        const unsigned j0 = clist[tid];
+        slot_next = cslot[tid];
+        pj_next = pos_in[j0];
+        ov_next = load_vel(vel_in, j0);
+        if (HIST && ((amask_old >> slot_next) & 1ull))
+            hr_next = hcol[(size_t)slot_next * P.Np];
+    }
     for (int k = 0; k < maxc; k++) {
         if (k >= cnt)
             continue;
-        const unsigned j = clist[k * kForceThreads + tid];
-        const double4 pj = pos_in[j];
-        const VelVal ov = load_vel(vel_in, j);
+        const double4 pj = pj_next;
+        const VelVal ov = ov_next;
+        const double4 hr = hr_next;
+        const unsigned slot = slot_next;
+        if (k + 1 < cnt) {
+            const unsigned jn = clist[(k + 1) * kForceThreads + tid];
+            slot_next = cslot[(k + 1) * kForceThreads + tid];
+            pj_next = pos_in[jn];
+            ov_next = load_vel(vel_in, jn);
+            if (HIST && ((amask_old >> slot_next) & 1ull))
+                hr_next = hcol[(size_t)slot_next * P.Np];
+        }
         const unsigned sj = ov.sid;
         const bool me1 = sid < sj;  // canonical orientation: body 1 = lower shape id
+        const bool had = HIST && ((amask_old >> slot) & 1ull);
+        const size_t hi = (size_t)slot * P.Np;
         ncontacts++;
         if (REC && !me1) {
             unsigned long long at = atomicAdd(&C.pair_count, 1ull);
             if (at < B.pair_cap)
                 B.pairs[at] = ((unsigned long long)(P.shape_base + sj) << 32) | (unsigned long long)(P.shape_base + sid);
         }
-        const unsigned key = P.shape_base + sj;
         if (FAST) {
             // sphere_sphere geometry in my own frame (n from me to the partner); |delta|^2 as in the contact test
             const V3 delta = mk(__dsub_rn(pj.x, me.x), __dsub_rn(pj.y, me.y), __dsub_rn(pj.z, me.z));
             const double d2 = dot_rn(delta, delta);
-            const double inv_d = rsqrt(d2);
+            const double inv_d = fast_rsqrt(d2);
             const double dist = d2 * inv_d;
             if (dist - __dadd_rn(me.w, pj.w) >= 0)
                 continue;
             const V3 n = delta * inv_d;
-            V3 disp = mk(0, 0, 0);
-            unsigned steps = 0;
-            double rel0 = 0;
-            bool isnew = true;
-            if (HIST) {
-                if (hc.find(key, disp, steps, rel0)) {
-                    isnew = false;
-                    if (!me1)
-                        disp = -disp;  // canonical (body 1 -> body 2) to my frame
-                }
-            }
+            V3 disp = mk(hr.x, hr.y, hr.z);
+            unsigned steps = rec_steps(hr.w);
+            if (had && !me1)
+                disp = -disp;  // canonical (body 1 -> body 2) to my frame
             V3 F, T;
             sphere_contact_fast<HIST, ROLL>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass,
-                                            sphere_mass(P, pj.w), me1, disp, steps, isnew, F, T);
+                                            sphere_mass(P, pj.w), me1, disp, steps, !had, F, T);
             Fsum = Fsum + F;
             Tsum = Tsum + T;
             if (HIST) {
-                if (nh < P.K) {
-                    if (!me1)
-                        disp = -disp;
-                    double2* q = reinterpret_cast<double2*>(hout + (size_t)nh * P.Np);
-                    q[0] = make_double2(disp.x, disp.y);
-                    q[1] = make_double2(disp.z, pack_key(key, steps));
-                }
-                nh++;
+                if (!me1)
+                    disp = -disp;
+                hcol[hi] = make_double4(disp.x, disp.y, disp.z, pack_key(P.shape_base + sj, steps));
+                amask_new |= 1ull << slot;
             }
         } else {
             Body b1, b2;
@@ -1145,12 +1217,14 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
                 continue;
             Hist h{mk(0, 0, 0), 0.0, 0.0, true};
             unsigned steps = 0;
-            if (HIST) {
-                if (hc.find(key, h.disp, steps, h.relvel0)) {
-                    h.isnew = false;
-                    h.dur = (double)steps * P.dt;
-                    steps++;
-                }
+            if (had) {
+                h.disp = mk(hr.x, hr.y, hr.z);
+                steps = rec_steps(hr.w);
+                h.dur = (double)steps * P.dt;
+                if (rcol)
+                    h.relvel0 = rcol[hi];
+                h.isnew = false;
+                steps++;
             }
             V3 F, T1, T2;
             contact_force<HIST, ROLL>(P, P.comp[0], b1, b2, g, h, F, T1, T2);
@@ -1162,14 +1236,10 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
                 Tsum = Tsum + T2;
             }
             if (HIST) {
-                if (nh < P.K) {
-                    double2* q = reinterpret_cast<double2*>(hout + (size_t)nh * P.Np);
-                    q[0] = make_double2(h.disp.x, h.disp.y);
-                    q[1] = make_double2(h.disp.z, pack_key(key, steps));
-                    if (hrout)
-                        hrout[(size_t)nh * P.Np] = h.relvel0;
-                }
-                nh++;
+                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, pack_key(P.shape_base + sj, steps));
+                if (rcol)
+                    rcol[hi] = h.relvel0;
+                amask_new |= 1ull << slot;
             }
         }
     }
@@ -1177,10 +1247,8 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
     double nmnx = CUDART_INF, nmny = CUDART_INF, nmnz = CUDART_INF, nmxx = -CUDART_INF, nmxy = -CUDART_INF, nmxz = -CUDART_INF;
     double dx2 = 0.0;
     if (valid) {
-        if (HIST && nh > P.K) {
+        if (HIST && __popcll(amask_new) + __popc(wmask_new) > P.K)
             atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
-            nh = P.K;
-        }
         if (REC) {
             B.recF[3 * (size_t)sid + 0] = Fsum.x; B.recF[3 * (size_t)sid + 1] = Fsum.y; B.recF[3 * (size_t)sid + 2] = Fsum.z;
             B.recT[3 * (size_t)sid + 0] = Tsum.x; B.recT[3 * (size_t)sid + 1] = Tsum.y; B.recT[3 * (size_t)sid + 2] = Tsum.z;
@@ -1234,7 +1302,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
         if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z)))
             atomicOr(&C.err, ERR_NAN);
         B.pos[dst][s] = make_double4(x.x, x.y, x.z, me.w);
-        store_vel(B.vel[dst], s, vn, wn, sid, (unsigned)nh | (flags << 8));
+        store_vel(B.vel[dst], s, vn, wn, sid, flags | (wmask_new << 8), amask_new);
         nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
         nmxx = x.x + me.w; nmxy = x.y + me.w; nmxz = x.z + me.w;
         const V3 dxv = x - mpos;
@@ -1276,7 +1344,7 @@ __global__ void __launch_bounds__(256) k_reduce(Params P, Buffers B, int which, 
             case 3: ext = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]); break;
             case 4: v = (p.z > arg) ? 1.0 : 0.0; break;
             case 5: v = (p.x > arg) ? 1.0 : 0.0; break;
-            case 6: v = (double)(B.vel[C.cur][i].meta & 0xFFu); break;  // history records held by this sphere
+            case 6: v = (double)(__popcll(B.vel[C.cur][i].amask) + __popc((B.vel[C.cur][i].meta >> 8) & 0xFFFFu)); break;  // live contacts
         }
     }
 #pragma unroll
@@ -1322,7 +1390,7 @@ __global__ void __launch_bounds__(256) k_import_state(Params P, Buffers B, const
     if (vel3) r.v = mk(vel3[o], vel3[o + 1], vel3[o + 2]);
     if (om3) r.w = mk(om3[o], om3[o + 1], om3[o + 2]);
     if (vel3 || om3)
-        store_vel(B.vel[C.cur], i, r.v, r.w, r.sid, r.meta);
+        store_vel(B.vel[C.cur], i, r.v, r.w, r.sid, r.meta, r.amask);
     if (i == 0 && pos3)
         C.need_rebuild = 1u;  // positions were replaced: the candidate lists are stale
 }

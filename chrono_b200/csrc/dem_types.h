@@ -5,14 +5,17 @@
 // rebuild; two copies [0]/[1] that ping-pong every step, the live one is Ctrl::cur):
 //   pos  : double4 (x, y, z, radius)                    32 B  one DRAM sector per neighbour gather
 //   vel  : VelRec  (v xyz, omega xyz, sid, meta)        64 B  two aligned sectors, gathered only for real contacts
-//   hist : double4[K][Np] column-major (slot k of sphere s at k*Np + s): tangential displacement of one contact
-//          in canonical orientation (as stored by the higher shape id, ChIterativeSolverMulticoreSMC.cpp:233-243)
-//          + packed (partner shape id | steps in contact).  EVERY sphere keeps a record of EVERY contact it takes
-//          part in (both partners hold bit-identical copies), so a thread only ever touches its own column, rows
-//          migrate with their sphere, and ghosts need no history.
 //   nl   : uint32[Kn][Np] column-major Verlet candidate list (storage slots of spheres within r_i+r_j+skin at the
 //          last rebuild), each sphere's entries sorted by the partner's stable id so the summation order -- and
 //          therefore every bit of the result -- does not depend on storage order, rebuild cadence or partition.
+//   hist : double4[Kn + nW][Np] column-major, ONE RECORD PER CANDIDATE SLOT (slot k of sphere s at k*Np + s, wall w
+//          at (Kn+w)*Np + s): tangential displacement of that contact in canonical orientation (as stored by the
+//          higher shape id, ChIterativeSolverMulticoreSMC.cpp:233-243) + steps in contact.  A 64-bit mask in the
+//          sphere's VelRec says which slots are live.  No keys, no search: the address of a contact's history is
+//          known as soon as the candidate is known, it is updated in place, and EVERY sphere keeps a record of EVERY
+//          contact it takes part in (both partners hold bit-identical copies), so a thread only ever touches its own
+//          column, records migrate with their sphere, and ghosts need no history.  When the lists are rebuilt the
+//          live records travel through `stage` (keyed by partner shape id) into the slots of the new lists.
 // sid = stable sphere id (= user index); shape id = shape_base + sid (Multicore numbering).
 // =============================================================================
 #pragma once
@@ -22,8 +25,8 @@ namespace demb200 {
 
 constexpr int kMaxWalls = 16;
 constexpr unsigned kEmptyKey = 0xFFFFFFFFu;
-constexpr int kMaxSlots = 32;      // upper bound of history slots K (contacts of one sphere, walls included)
-constexpr int kMaxNeighbors = 64;  // upper bound of Verlet candidate slots Kn
+constexpr int kMaxSlots = 32;      // upper bound of K = simultaneous contacts of one sphere, walls included
+constexpr int kMaxNeighbors = 64;  // upper bound of Verlet candidate slots Kn (live mask is 64 bits)
 
 // device error bits (dem_b200 error codes are derived from these at sync points)
 enum : unsigned {
@@ -57,7 +60,7 @@ struct Params {
     unsigned N;   // spheres
     unsigned Np;  // N rounded up to a multiple of 32: pitch of the column-major arrays
     int nW;
-    int K;        // history slots per sphere
+    int K;        // most simultaneous contacts one sphere may have (staging slots at rebuild)
     int Kn;       // Verlet candidate slots per sphere
     int force_model, adhesion_model, tang_mode, use_mat_props, integrator;
     double char_vel, min_slip, min_roll, min_spin, dt;
@@ -74,12 +77,13 @@ struct Params {
     int has_wall_bb;
 };
 
-// 64-byte velocity record.  meta = history count (bits 0-7) | flags (bits 8-15: 1 = fixed)
+// 64-byte velocity record.  meta = flags (bits 0-7: 1 = fixed) | live wall-contact mask (bits 8-23);
+// amask bit k = the contact with candidate k of the sphere's Verlet list carried force last step (history live).
 struct __align__(16) VelRec {
     double v[3];
     double w[3];
     unsigned sid, meta;
-    double spare;
+    unsigned long long amask;
 };
 
 // Multicore broadphase grid of the current step (ChBroadphase.cpp:143-208)
@@ -96,6 +100,7 @@ struct Ctrl {
     unsigned f_src;         // this step: buffer the force kernel reads (it writes f_src ^ 1)
     unsigned rebuild_now;   // this step rebuilds the search grid and the candidate lists
     unsigned need_rebuild;  // request (host: initialize / set_state)
+    unsigned init_stage;    // first rebuild takes the contact history from Buffers::stage_init (checkpoint restart)
     unsigned err;
     unsigned long long nsteps, nrebuilds;
     unsigned long long bbox[6];   // order-preserving encoded doubles: min xyz, max xyz of the sphere AABBs
@@ -115,8 +120,11 @@ struct Buffers {
     double4* pos[2];
     VelRec* vel[2];
     double* acc[2];       // previous-step acceleration (Chung only), 6 per sphere
-    double4* hist[2];     // [K][Np]
-    double* hrel[2];      // [K][Np] initial normal speed (only Hooke/Flores with material properties)
+    double4* hist;        // [Kn + nW][Np], updated in place
+    double* hrel;         // [Kn + nW][Np] initial normal speed (only Hooke/Flores with material properties)
+    // history in transit during a rebuild: (disp xyz, partner shape id | steps << 32), keyed, compact
+    double4* stage; double* stage_rel; uint32_t* stage_cnt;                  // [K][Np], [K][Np], [Np]
+    double4* stage_init; double* stage_rel_init; uint32_t* stage_cnt_init;   // same, user order; null unless add_history
     // neighbour search
     uint32_t* cell; uint32_t* rank; uint32_t* perm;
     uint32_t* cell_count; uint32_t* cell_start; uint32_t* block_sums;
