@@ -498,6 +498,13 @@ int dem_b200_set_wall_velocity(dem_b200_system* s, int w, const double pos[3], c
     }
     refresh_params(s);
     drop_graph(s);
+    if (s->initialized) {
+        // the per-sphere wall candidate masks were computed for the old wall position
+        CU(cudaSetDevice(s->cfg.device));
+        const unsigned one = 1;
+        CU(cudaMemcpyAsync(&s->B.ctrl->need_rebuild, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     return 0;
 }
 int dem_b200_num_walls(const dem_b200_system* s) { return s ? s->P.nW : 0; }
@@ -983,12 +990,10 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
     auto emit = [&](uint32_t me, uint32_t key, size_t at) {
         if (cnt < capacity) {
             const double4 v = vals[at];
-            unsigned long long bits;
-            memcpy(&bits, &v.w, 8);
             if (owner) owner[cnt] = me;
             if (other) other[cnt] = key;
             if (disp3) { disp3[3 * cnt] = v.x; disp3[3 * cnt + 1] = v.y; disp3[3 * cnt + 2] = v.z; }
-            if (duration) duration[cnt] = (double)(uint32_t)(bits >> 32) * s->P.dt;
+            if (duration) duration[cnt] = v.w * s->P.dt;  // 4th component = steps in contact
             if (relvel_init) relvel_init[cnt] = s->use_hrel ? rels[at] : 0.0;
         }
         cnt++;

@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
             const size_t si = (size_t)(P.Kn + w) * P.Np + src;
             if (cnt < (unsigned)P.K) {
                 double4 r = B.hist[si];
-                r.w = pack_key((unsigned)w, rec_steps(r.w));
+                r.w = pack_key((unsigned)w, (unsigned)r.w);
                 B.stage[(size_t)cnt * P.Np + s] = r;
                 if (B.stage_rel)
                     B.stage_rel[(size_t)cnt * P.Np + s] = B.hrel[si];
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
             if (cnt < (unsigned)P.K) {
                 const unsigned jo = B.nl[si];  // old storage slot of the partner
                 double4 r = B.hist[si];
-                r.w = pack_key(P.shape_base + B.vel[a][jo].sid, rec_steps(r.w));
+                r.w = pack_key(P.shape_base + B.vel[a][jo].sid, (unsigned)r.w);
                 B.stage[(size_t)cnt * P.Np + s] = r;
                 if (B.stage_rel)
                     B.stage_rel[(size_t)cnt * P.Np + s] = B.hrel[si];
@@ -606,7 +606,25 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     }
     for (int k = 0; k < cnt; k++)
         B.nl[(size_t)k * P.Np + s] = tj[k];
-    B.ncnt[s] = (unsigned)cnt;
+    // walls the sphere can touch before the next rebuild: it moves less than skin/2 until then (walls only move
+    // through dem_b200_set_wall_velocity, which requests a rebuild)
+    unsigned wc = 0;
+    {
+        const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
+        for (int w = 0; w < P.nW; w++) {
+            const Wall& W = P.walls[w];
+            bool near;
+            if (W.type == WALL_BOX) {
+                near = me.x - reach <= W.amax[0] && W.amin[0] <= me.x + reach && me.y - reach <= W.amax[1] &&
+                       W.amin[1] <= me.y + reach && me.z - reach <= W.amax[2] && W.amin[2] <= me.z + reach;
+            } else {
+                near = (me.x - W.pos[0]) * W.hdims[0] + (me.y - W.pos[1]) * W.hdims[1] + (me.z - W.pos[2]) * W.hdims[2] < reach;
+            }
+            if (near)
+                wc |= 1u << w;
+        }
+    }
+    B.ncnt[s] = (unsigned)cnt | (wc << 8);
     // staged history -> slots of the new list (a record whose partner is no longer a candidate is dropped: that
     // contact has broken)
     if (B.hist) {
@@ -614,8 +632,9 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         unsigned wmask = 0u;
         const unsigned sc = B.stage_cnt[s];
         for (unsigned c = 0; c < sc; c++) {
-            const double4 r = B.stage[(size_t)c * P.Np + s];
+            double4 r = B.stage[(size_t)c * P.Np + s];
             const unsigned key = rec_key(r.w);
+            r.w = (double)rec_steps(r.w);  // in the candidate slots the 4th component is the step count as a double
             size_t di;
             if (key < P.shape_base) {
                 di = (size_t)(P.Kn + key) * P.Np + s;
@@ -857,7 +876,7 @@ __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, cons
 template <bool HIST, bool ROLL>
 __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp& cm, V3 n, double dist, double ra,
                                                     double rb, V3 va, V3 wa, V3 vb, V3 wb, double ma, double mb,
-                                                    bool a_is_body1, V3& disp, unsigned& steps, bool isnew, V3& F_me,
+                                                    bool a_is_body1, V3& disp, double& steps, bool isnew, V3& F_me,
                                                     V3& T_me) {
     const double eps = 2.220446049250313e-16;
     const double radSum = __dadd_rn(ra, rb);
@@ -877,9 +896,9 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
         delta_t = relvel_t * P.dt;
         if (isnew) {
             disp = mk(0, 0, 0);
-            steps = 0;
+            steps = 0.0;
         } else {
-            steps++;
+            steps += 1.0;
         }
         disp = disp - delta_t;
         disp = disp - dot(disp, n) * n;
@@ -928,7 +947,7 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
         const double d_coeff = gn_simple / (2.0 * m_eff * sqrt(kn_simple / m_eff));
         if (d_coeff < 1.0) {
             const double t_collision = kPI * sqrt(m_eff / (kn_simple * (1 - d_coeff * d_coeff)));
-            const double t_contact = HIST ? (double)steps * P.dt : 0.0;
+            const double t_contact = HIST ? steps * P.dt : 0.0;
             if (t_contact <= t_collision) {
                 muRoll = 0.0;
                 muSpin = 0.0;
@@ -1020,22 +1039,32 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
     VelVal mv;
     mv.v = mk(0, 0, 0); mv.w = mk(0, 0, 0); mv.sid = 0; mv.meta = 0; mv.amask = 0ull;
     int cnt = 0;
+    unsigned wcand = 0;  // walls this sphere can reach before the next rebuild (k_build_list)
     if (valid) {
         me = pos_in[s];
         mv = load_vel(vel_in, s);
         // ---- phase 1: exact sphere_sphere test (ChNarrowphasePRIMS.cpp:50-59, separation = 0) on the candidates
-        const unsigned nc = B.ncnt[s];
+        const unsigned ncw = B.ncnt[s];
+        const unsigned nc = ncw & 0xFFu;
+        wcand = ncw >> 8;
         const uint32_t* __restrict__ nl = B.nl + s;
-        // batches of 4: the 4 candidate ids, then the 4 positions, are independent loads in flight together
+        // batches of 4 candidates: the ids of the next batch and the 4 positions of this batch are in flight together
+        unsigned jn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            jn[u] = ((unsigned)u < nc) ? nl[(size_t)u * P.Np] : s;
         for (unsigned k0 = 0; k0 < nc; k0 += 4) {
             unsigned jj[4];
             double4 pp[4];
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                jj[u] = (k0 + u < nc) ? nl[(size_t)(k0 + u) * P.Np] : s;
+                jj[u] = jn[u];
 #pragma unroll
             for (int u = 0; u < 4; u++)
                 pp[u] = pos_in[jj[u]];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                jn[u] = (k0 + 4 + u < nc) ? nl[(size_t)(k0 + 4 + u) * P.Np] : s;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const V3 d = mk(__dsub_rn(pp[u].x, me.x), __dsub_rn(pp[u].y, me.y), __dsub_rn(pp[u].z, me.z));
@@ -1072,8 +1101,11 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
     if (valid) {
         // ---- walls first: body 1 = wall body (lower id), body 2 = this sphere
         double amin[3], amax[3];
-        sphere_aabb_offset(me, G.origin, amin, amax);
-        for (int w = 0; w < P.nW; w++) {
+        if (wcand)
+            sphere_aabb_offset(me, G.origin, amin, amax);
+        while (wcand) {
+            const int w = __ffs(wcand) - 1;
+            wcand &= wcand - 1;
             const Wall& W = P.walls[w];
             Geom g;
             bool hit;
@@ -1097,17 +1129,17 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             if (g.depth >= 0)  // ChIterativeSolverMulticoreSMC.cpp:96-104: no force, no history
                 continue;
             Hist h{mk(0, 0, 0), 0.0, 0.0, true};
-            unsigned steps = 0;
+            double steps = 0.0;
             const size_t hi = (size_t)(P.Kn + w) * P.Np;
             if (HIST && ((wmask_old >> w) & 1u)) {
                 const double4 r = hcol[hi];
                 h.disp = mk(r.x, r.y, r.z);
-                steps = rec_steps(r.w);
-                h.dur = (double)steps * P.dt;
+                steps = r.w;
+                h.dur = steps * P.dt;
                 if (rcol)
                     h.relvel0 = rcol[hi];
                 h.isnew = false;
-                steps++;
+                steps += 1.0;
             }
             Body b1{mk(0, 0, 0), mk(W.vel[0], W.vel[1], W.vel[2]), mk(0, 0, 0), P.wall_mass};
             Body b2{mpos, mv.v, mv.w, my_mass};
@@ -1116,7 +1148,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             Fsum = Fsum + F;
             Tsum = Tsum + T2;
             if (HIST) {
-                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, pack_key((unsigned)w, steps));
+                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, steps);
                 if (rcol)
                     rcol[hi] = h.relvel0;
                 wmask_new |= 1u << w;
@@ -1144,7 +1176,10 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             continue;
         const double4 pj = pj_next;
         const VelVal ov = ov_next;
-        const double4 hr = hr_next;
+        double4 hr = hr_next;
+        // Keep the consumer of the prefetched record HERE: without this the compiler copies the freshly loaded
+        // registers into their loop-carried homes right behind the load below and stalls on it (ncu r01d).
+        asm volatile("" : "+d"(hr.x), "+d"(hr.y), "+d"(hr.z), "+d"(hr.w));
         const unsigned slot = slot_next;
         if (k + 1 < cnt) {
             const unsigned jn = clist[(k + 1) * kForceThreads + tid];
@@ -1174,7 +1209,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
                 continue;
             const V3 n = delta * inv_d;
             V3 disp = mk(hr.x, hr.y, hr.z);
-            unsigned steps = rec_steps(hr.w);
+            double steps = hr.w;
             if (had && !me1)
                 disp = -disp;  // canonical (body 1 -> body 2) to my frame
             V3 F, T;
@@ -1185,7 +1220,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             if (HIST) {
                 if (!me1)
                     disp = -disp;
-                hcol[hi] = make_double4(disp.x, disp.y, disp.z, pack_key(P.shape_base + sj, steps));
+                hcol[hi] = make_double4(disp.x, disp.y, disp.z, steps);
                 amask_new |= 1ull << slot;
             }
         } else {
@@ -1216,15 +1251,15 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             if (g.depth >= 0)  // ChIterativeSolverMulticoreSMC.cpp:96-104: no force, no history
                 continue;
             Hist h{mk(0, 0, 0), 0.0, 0.0, true};
-            unsigned steps = 0;
+            double steps = 0.0;
             if (had) {
                 h.disp = mk(hr.x, hr.y, hr.z);
-                steps = rec_steps(hr.w);
-                h.dur = (double)steps * P.dt;
+                steps = hr.w;
+                h.dur = steps * P.dt;
                 if (rcol)
                     h.relvel0 = rcol[hi];
                 h.isnew = false;
-                steps++;
+                steps += 1.0;
             }
             V3 F, T1, T2;
             contact_force<HIST, ROLL>(P, P.comp[0], b1, b2, g, h, F, T1, T2);
@@ -1236,7 +1271,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
                 Tsum = Tsum + T2;
             }
             if (HIST) {
-                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, pack_key(P.shape_base + sj, steps));
+                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, steps);
                 if (rcol)
                     rcol[hi] = h.relvel0;
                 amask_new |= 1ull << slot;
