@@ -4,12 +4,13 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libchrono_b200_dem.so")
-SOURCES = [os.path.join(HERE, "csrc", "dem_engine.cu")]
+LIB_PATH = os.environ.get("DEMB200_LIB") or os.path.join(HERE, "libchrono_b200_dem.so")  # DEMB200_LIB: tuning variants
+SOURCES = [os.path.join(HERE, "csrc", "dem_engine.cu"), os.path.join(HERE, "csrc", "ChSystemDem.cpp")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("dem_kernels.cuh", "dem_types.h")] + [
-    os.path.join(ROOT, "include", "chrono_b200_dem.h")]
+    os.path.join(ROOT, "include", "chrono_b200_dem.h"), os.path.join(ROOT, "include", "chrono_dem", "physics", "ChSystemDem.h"),
+    os.path.join(ROOT, "include", "chrono_dem", "ChDemDefines.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-I", os.path.join(ROOT, "include"), "-Xcompiler", "-fPIC", "-shared"]
 
 
 def needs_build():
@@ -23,6 +24,7 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("DEMB200_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     subprocess.check_call(cmd)
     return LIB_PATH

@@ -1,0 +1,884 @@
+// =============================================================================
+// ChSystemDem.cpp -- host-side mirror of chrono::dem::ChSystemDem (reference: src/chrono_dem/physics/ChSystemDem.cpp,
+// ChSystemDem_impl.cpp) written on top of the C ABI in include/chrono_b200_dem.h.  No CUDA in this file: everything
+// that touches the device goes through dem_b200_* entry points.
+// =============================================================================
+#include "chrono_dem/physics/ChSystemDem.h"
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "chrono_b200_dem.h"
+
+namespace chrono {
+namespace dem {
+
+namespace {
+constexpr double kPi = 3.141592653589793238462643383279;
+
+[[noreturn]] void fail(const std::string& msg) {
+    // the reference prints and calls exit(1) (CHDEM_ERROR, src/chrono_dem/utils/ChDemUtilities.h:20-26)
+    throw std::runtime_error("ChSystemDem: " + msg);
+}
+}  // namespace
+
+enum class BCKind { PLANE, ZCYL, UNSUPPORTED };
+
+struct BCInfo {
+    BCKind kind = BCKind::PLANE;
+    double pos[3] = {0, 0, 0};     // reference position (plane point / cylinder axis point), user units
+    double normal[3] = {0, 0, 1};  // plane normal
+    double radius = 0;             // cylinder
+    bool spheres_inside = true;
+    bool track_forces = false;
+    bool enabled = true;
+    bool has_offset = false;
+    GranPositionFunction offset = GranPosFunction_default;
+    int wall = -1;  // engine wall index
+};
+
+class ChSystemDem_impl {
+  public:
+    dem_b200_system* h = nullptr;
+    bool initialized = false;
+    // geometry / material (user units)
+    float radius = 0, density = 0;
+    float box[3] = {0, 0, 0};
+    float O[3] = {0, 0, 0};
+    bool BD_fixed = true;
+    float step = 1e-4f;
+    float grav[3] = {0, 0, 0};
+    double elapsed = 0;
+    CHDEM_VERBOSITY verbosity = CHDEM_VERBOSITY::INFO;
+    CHDEM_OUTPUT_MODE out_mode = CHDEM_OUTPUT_MODE::CSV;
+    unsigned int out_flags = ABSV;
+    CHDEM_TIME_INTEGRATOR integrator = CHDEM_TIME_INTEGRATOR::EXTENDED_TAYLOR;
+    CHDEM_FRICTION_MODE friction = CHDEM_FRICTION_MODE::FRICTIONLESS;
+    CHDEM_ROLLING_MODE rolling = CHDEM_ROLLING_MODE::NO_RESISTANCE;
+    bool use_mat_based = false;
+    bool use_min_length = true, defragment = true, record_contacts = false;
+    unsigned psi_T = 32, psi_L = 16;
+    float psi_R = 1.f, max_safe_vel = (float)UINT_MAX;
+    // per-class user coefficients: [0] sphere-sphere, [1] sphere-wall, [2] sphere-mesh
+    double Kn[3] = {0, 0, 0}, Kt[3] = {0, 0, 0}, Gn[3] = {0, 0, 0}, Gt[3] = {0, 0, 0};
+    double mu[3] = {0, 0, 0}, mu_roll[3] = {0, 0, 0}, mu_spin[3] = {0, 0, 0};
+    double cohesion_over_g = 0, adhesion_over_g[3] = {0, 0, 0};
+    double young[3] = {0, 0, 0}, poisson[3] = {0, 0, 0}, cor[3] = {0, 0, 0};
+    // particles (staged until Initialize)
+    std::vector<double> pos, vel, omg, rad;
+    std::vector<uint8_t> fixed;
+    struct HistRow { uint32_t sphere, partner; bool is_bc; double d[3]; };
+    std::vector<HistRow> hist;  // staged contact history (checkpoint): sphere index, partner sphere index or BC id
+    std::vector<BCInfo> bcs;
+    bool any_offset = false;
+
+    size_t n() const { return rad.empty() ? pos.size() / 3 : rad.size(); }
+
+    void check(int rc, const char* what) const {
+        if (rc < 0)
+            fail(std::string(what) + ": " + dem_b200_last_error(h));
+    }
+    double sphere_mass() const { return 4.0 / 3.0 * kPi * (double)radius * radius * radius * density; }
+    double gmag() const { return std::sqrt((double)grav[0] * grav[0] + (double)grav[1] * grav[1] + (double)grav[2] * grav[2]); }
+
+    // Dem F = K d^{3/2} R^{-1/2}  <->  engine (Multicore Hertz, user coefficients)
+    // F = kn R* d^{3/2}; R* = R/2 sphere-sphere, R sphere-wall / sphere-mesh.
+    dem_b200_contact_class make_class(int c) const {
+        dem_b200_contact_class k{};
+        const double R = radius;
+        const double f = ((c == 0) ? 2.0 : 1.0) / std::pow(R, 1.5);
+        k.kn = f * Kn[c]; k.kt = f * Kt[c]; k.gn = f * Gn[c]; k.gt = f * Gt[c];
+        const bool fr = friction != CHDEM_FRICTION_MODE::FRICTIONLESS;
+        k.mu = fr ? mu[c] : 0.0;
+        const bool roll = fr && rolling == CHDEM_ROLLING_MODE::SCHWARTZ;
+        k.mu_roll = roll ? mu_roll[c] : 0.0;
+        k.mu_spin = 0.0;  // accepted but unused by the reference
+        k.cr = std::min(cor[0], cor[c == 0 ? 0 : c]);
+        // constant cohesion: ratio * m * |g| (ChSystemDem_impl.cpp:1444-1445)
+        k.adhesion = ((c == 0) ? cohesion_over_g : adhesion_over_g[c]) * sphere_mass() * gmag();
+        // material-based model (utils/ChDemUtilities.h:65-70)
+        const int w = (c == 0) ? 0 : c;
+        if (young[0] > 0 && young[w] > 0) {
+            const double invE = (1 - poisson[0] * poisson[0]) / young[0] + (1 - poisson[w] * poisson[w]) / young[w];
+            const double invG = 2 * (2 - poisson[0]) * (1 + poisson[0]) / young[0] + 2 * (2 - poisson[w]) * (1 + poisson[w]) / young[w];
+            k.E_eff = 1 / invE;
+            k.G_eff = 1 / invG;
+        }
+        return k;
+    }
+
+    dem_b200_config make_config() const {
+        dem_b200_config c{};
+        c.device = 0;
+        c.force_model = DEMB200_HERTZ;
+        c.adhesion_model = DEMB200_ADH_CONSTANT;
+        c.tangential_mode = friction == CHDEM_FRICTION_MODE::MULTI_STEP ? DEMB200_TANG_MULTISTEP
+                            : friction == CHDEM_FRICTION_MODE::SINGLE_STEP ? DEMB200_TANG_ONESTEP : DEMB200_TANG_NONE;
+        c.use_mat_props = use_mat_based ? 1 : 0;
+        c.integrator = (int)integrator;  // same order as CHDEM_TIME_INTEGRATOR
+        c.history_slots = 16;
+        c.char_vel = 1.0; c.min_slip_vel = 1e-4; c.min_roll_vel = 1e-4; c.min_spin_vel = 1e-4;
+        c.dt = step;
+        for (int k = 0; k < 3; k++) c.gravity[k] = grav[k];
+        // Multicore bins only matter for the parity inspection calls
+        c.bins_per_axis[0] = c.bins_per_axis[1] = c.bins_per_axis[2] = 10;
+        for (int k = 0; k < 3; k++) {
+            dem_b200_material& m = c.material[k];
+            m.young = (float)std::max(young[k], 1.0); m.poisson = (float)poisson[k];
+            m.mu_s = (float)mu[k]; m.cr = (float)cor[k];
+        }
+        c.mass_coef = 4.0 / 3.0 * kPi * density;
+        c.wall_mass = 1e30;  // Dem walls are infinitely heavy: m_eff = m (ChDemBoundaryConditions.cuh:446)
+        c.mesh_mass = 1e30;
+        c.verlet_skin = -1.0;
+        c.neighbor_slots = 0;
+        return c;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+
+ChSystemDem::ChSystemDem(float sphere_rad, float density, const ChVector3f& boxDims, ChVector3f O) : m_RTF(0) {
+    m_sys = new ChSystemDem_impl();
+    m_sys->radius = sphere_rad;
+    m_sys->density = density;
+    m_sys->box[0] = boxDims.x(); m_sys->box[1] = boxDims.y(); m_sys->box[2] = boxDims.z();
+    m_sys->O[0] = O.x(); m_sys->O[1] = O.y(); m_sys->O[2] = O.z();
+    m_sys->bcs.resize(NUM_RESERVED_BC_IDS);  // big-domain walls, created at Initialize (ChSystemDem_impl.cpp:102-132)
+}
+
+ChSystemDem::ChSystemDem(const std::string& checkpoint) : m_RTF(0) {
+    m_sys = new ChSystemDem_impl();
+    m_sys->bcs.resize(NUM_RESERVED_BC_IDS);
+    ReadCheckpointFile(checkpoint, true);
+}
+
+ChSystemDem::~ChSystemDem() {
+    if (m_sys) {
+        if (m_sys->h)
+            dem_b200_destroy(m_sys->h);
+        delete m_sys;
+    }
+}
+
+void* ChSystemDem::GetEngineHandle() const { return m_sys->h; }
+
+// ---- setters ---------------------------------------------------------------------------------------------------------
+void ChSystemDem::SetGravitationalAcceleration(const ChVector3f& g) {
+    m_sys->grav[0] = g.x(); m_sys->grav[1] = g.y(); m_sys->grav[2] = g.z();
+}
+
+void ChSystemDem::SetParticles(const std::vector<ChVector3f>& points, const std::vector<ChVector3f>& vels,
+                               const std::vector<ChVector3f>& ang_vels) {
+    if (m_sys->initialized)
+        fail("SetParticles after Initialize");
+    if (!vels.empty() && vels.size() != points.size())
+        fail("SetParticles: velocities and positions differ in size");
+    if (!ang_vels.empty() && ang_vels.size() != points.size())
+        fail("SetParticles: angular velocities and positions differ in size");
+    const size_t n = points.size();
+    m_sys->pos.resize(3 * n);
+    m_sys->vel.assign(3 * n, 0.0);
+    m_sys->omg.assign(3 * n, 0.0);
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            m_sys->pos[3 * i + k] = points[i][k];
+            if (!vels.empty()) m_sys->vel[3 * i + k] = vels[i][k];
+            if (!ang_vels.empty()) m_sys->omg[3 * i + k] = ang_vels[i][k];
+        }
+    if (m_sys->rad.size() != n)
+        m_sys->rad.assign(n, m_sys->radius);
+    if (m_sys->fixed.size() != n)
+        m_sys->fixed.assign(n, 0);
+}
+
+void ChSystemDem::SetParticleRadii(const std::vector<float>& radii) {
+    if (m_sys->initialized)
+        fail("SetParticleRadii after Initialize");
+    m_sys->rad.assign(radii.begin(), radii.end());
+}
+
+void ChSystemDem::SetBDFixed(bool fixed) { m_sys->BD_fixed = fixed; }
+void ChSystemDem::SetBDCenter(const ChVector3f& O) { m_sys->O[0] = O.x(); m_sys->O[1] = O.y(); m_sys->O[2] = O.z(); }
+void ChSystemDem::SetParticleFixed(const std::vector<bool>& fixed) {
+    m_sys->fixed.resize(fixed.size());
+    for (size_t i = 0; i < fixed.size(); i++) m_sys->fixed[i] = fixed[i] ? 1 : 0;
+}
+void ChSystemDem::SetParticleOutputMode(CHDEM_OUTPUT_MODE mode) { m_sys->out_mode = mode; }
+void ChSystemDem::SetParticleOutputFlags(unsigned int flags) { m_sys->out_flags = flags; }
+void ChSystemDem::SetFixedStepSize(float size_UU) { m_sys->step = size_UU; }
+float ChSystemDem::GetFixedStepSize() const { return m_sys->step; }
+void ChSystemDem::SetDefragmentOnInitialize(bool defragment) { m_sys->defragment = defragment; }
+void ChSystemDem::EnableMinLength(bool useMinLen) { m_sys->use_min_length = useMinLen; }
+void ChSystemDem::SetTimeIntegrator(CHDEM_TIME_INTEGRATOR new_integrator) { m_sys->integrator = new_integrator; }
+void ChSystemDem::SetFrictionMode(CHDEM_FRICTION_MODE new_mode) { m_sys->friction = new_mode; }
+void ChSystemDem::SetRollingMode(CHDEM_ROLLING_MODE new_mode) {
+    if (new_mode == CHDEM_ROLLING_MODE::ELASTIC_PLASTIC)
+        fail("ELASTIC_PLASTIC rolling is not implemented (nor in the reference, ChDemHelpers.cuh:236-240)");
+    m_sys->rolling = new_mode;
+}
+void ChSystemDem::SetStaticFrictionCoeff_SPH2SPH(float mu) { m_sys->mu[0] = mu; }
+void ChSystemDem::SetStaticFrictionCoeff_SPH2WALL(float mu) { m_sys->mu[1] = mu; }
+void ChSystemDem::SetRollingCoeff_SPH2SPH(float mu) { m_sys->mu_roll[0] = mu; }
+void ChSystemDem::SetRollingCoeff_SPH2WALL(float mu) { m_sys->mu_roll[1] = mu; }
+void ChSystemDem::SetSpinningCoeff_SPH2SPH(float mu) { m_sys->mu_spin[0] = mu; }
+void ChSystemDem::SetSpinningCoeff_SPH2WALL(float mu) { m_sys->mu_spin[1] = mu; }
+void ChSystemDem::SetKn_SPH2SPH(double v) { m_sys->Kn[0] = v; }
+void ChSystemDem::SetKn_SPH2WALL(double v) { m_sys->Kn[1] = v; }
+void ChSystemDem::SetGn_SPH2SPH(double v) { m_sys->Gn[0] = v; }
+void ChSystemDem::SetGn_SPH2WALL(double v) { m_sys->Gn[1] = v; }
+void ChSystemDem::SetKt_SPH2SPH(double v) { m_sys->Kt[0] = v; }
+void ChSystemDem::SetGt_SPH2SPH(double v) { m_sys->Gt[0] = v; }
+void ChSystemDem::SetKt_SPH2WALL(double v) { m_sys->Kt[1] = v; }
+void ChSystemDem::SetGt_SPH2WALL(double v) { m_sys->Gt[1] = v; }
+void ChSystemDem::SetCohesionRatio(float v) { m_sys->cohesion_over_g = v; }
+void ChSystemDem::SetAdhesionRatio_SPH2WALL(float v) { m_sys->adhesion_over_g[1] = v; }
+void ChSystemDem::UseMaterialBasedModel(bool val) { m_sys->use_mat_based = val; }
+void ChSystemDem::SetYoungModulus_SPH(double v) { m_sys->young[0] = v; }
+void ChSystemDem::SetYoungModulus_WALL(double v) { m_sys->young[1] = v; }
+void ChSystemDem::SetPoissonRatio_SPH(double v) { m_sys->poisson[0] = v; }
+void ChSystemDem::SetPoissonRatio_WALL(double v) { m_sys->poisson[1] = v; }
+void ChSystemDem::SetRestitution_SPH(double v) { m_sys->cor[0] = v; }
+void ChSystemDem::SetRestitution_WALL(double v) { m_sys->cor[1] = v; }
+void ChSystemDem::SetMaxSafeVelocity_SU(float max_vel) { m_sys->max_safe_vel = max_vel; }
+void ChSystemDem::SetPsiFactors(unsigned int psi_T, unsigned int psi_L, float psi_R) {
+    m_sys->psi_T = psi_T; m_sys->psi_L = psi_L; m_sys->psi_R = psi_R;  // no simulation-unit system: recorded only
+}
+void ChSystemDem::SetPsiT(unsigned int psi_T) { m_sys->psi_T = psi_T; }
+void ChSystemDem::SetPsiL(unsigned int psi_L) { m_sys->psi_L = psi_L; }
+void ChSystemDem::SetPsiR(float psi_R) { m_sys->psi_R = psi_R; }
+void ChSystemDem::SetRecordingContactInfo(bool record) { m_sys->record_contacts = record; }
+void ChSystemDem::SetSimTime(float time) { m_sys->elapsed = time; }
+void ChSystemDem::SetVerbosity(CHDEM_VERBOSITY level) { m_sys->verbosity = level; }
+void ChSystemDem::SetParticleDensity(float density) { m_sys->density = density; }
+void ChSystemDem::SetParticleRadius(float rad) { m_sys->radius = rad; }
+
+// ---- boundary conditions ----------------------------------------------------------------------------------------------
+size_t ChSystemDem::CreateBCPlane(const ChVector3f& pos, const ChVector3f& normal, bool track_forces) {
+    if (m_sys->initialized)
+        fail("boundary conditions must be created before Initialize");
+    BCInfo bc;
+    bc.kind = BCKind::PLANE;
+    ChVector3d n = ChVector3d(normal).GetNormalized();
+    for (int k = 0; k < 3; k++) { bc.pos[k] = pos[k]; bc.normal[k] = n[k]; }
+    bc.track_forces = track_forces;
+    m_sys->bcs.push_back(bc);
+    return m_sys->bcs.size() - 1;
+}
+size_t ChSystemDem::CreateBCCylinderZ(const ChVector3f& center, float radius, bool outward_normal, bool track_forces) {
+    if (m_sys->initialized)
+        fail("boundary conditions must be created before Initialize");
+    BCInfo bc;
+    bc.kind = BCKind::ZCYL;
+    for (int k = 0; k < 3; k++) bc.pos[k] = center[k];
+    bc.radius = radius;
+    bc.spheres_inside = !outward_normal;  // normal pointing outward = obstacle, inward = container
+    bc.track_forces = track_forces;
+    m_sys->bcs.push_back(bc);
+    return m_sys->bcs.size() - 1;
+}
+size_t ChSystemDem::CreateBCSphere(const ChVector3f&, float, bool, bool, float) {
+    fail("CreateBCSphere: not supported yet (SURVEY 8f item 4; never called in-tree outside chrono_dem)");
+}
+size_t ChSystemDem::CreateBCConeZ(const ChVector3f&, float, float, float, bool, bool) {
+    fail("CreateBCConeZ: not supported yet (SURVEY 8f item 4; never called in-tree outside chrono_dem)");
+}
+size_t ChSystemDem::CreateCustomizedPlate(const ChVector3f&, const ChVector3f&, float) {
+    fail("CreateCustomizedPlate: not supported (the reference has no force case for PLATE either, SURVEY Q5)");
+}
+bool ChSystemDem::DisableBCbyID(size_t id) {
+    if (id >= m_sys->bcs.size()) return false;
+    m_sys->bcs[id].enabled = false;
+    if (m_sys->initialized && m_sys->bcs[id].wall >= 0)
+        m_sys->check(dem_b200_enable_wall(m_sys->h, m_sys->bcs[id].wall, 0), "DisableBCbyID");
+    return true;
+}
+bool ChSystemDem::EnableBCbyID(size_t id) {
+    if (id >= m_sys->bcs.size()) return false;
+    m_sys->bcs[id].enabled = true;
+    if (m_sys->initialized && m_sys->bcs[id].wall >= 0)
+        m_sys->check(dem_b200_enable_wall(m_sys->h, m_sys->bcs[id].wall, 1), "EnableBCbyID");
+    return true;
+}
+bool ChSystemDem::SetBCOffsetFunction(size_t id, const GranPositionFunction& f) {
+    if (id >= m_sys->bcs.size()) return false;
+    m_sys->bcs[id].offset = f;
+    m_sys->bcs[id].has_offset = true;
+    m_sys->any_offset = true;
+    return true;
+}
+void ChSystemDem::setBDWallsMotionFunction(const GranPositionFunction& pos_fn) {
+    for (size_t id = 0; id < NUM_RESERVED_BC_IDS; id++)
+        SetBCOffsetFunction(id, pos_fn);
+}
+
+// ---- run --------------------------------------------------------------------------------------------------------------
+void ChSystemDem::Initialize() {
+    ChSystemDem_impl& S = *m_sys;
+    if (S.initialized)
+        fail("Initialize called twice");
+    const size_t n = S.pos.size() / 3;
+    if (n == 0)
+        fail("Initialize without particles");
+    if (S.rad.size() != n)
+        S.rad.assign(n, S.radius);
+    if (S.fixed.size() != n)
+        S.fixed.resize(n, 0);
+    dem_b200_config cfg = S.make_config();
+    int rc = dem_b200_create(&cfg, &S.h);
+    if (rc < 0)
+        fail(std::string("no usable CUDA device: ") + dem_b200_last_error(nullptr));
+    // six reserved big-domain planes, normals pointing inwards (ChSystemDem_impl.cpp:102-132)
+    const double c[3] = {S.O[0], S.O[1], S.O[2]};
+    for (int a = 0; a < 3; a++)
+        for (int side = 0; side < 2; side++) {
+            BCInfo& bc = S.bcs[2 * a + side];
+            bc.kind = BCKind::PLANE;
+            for (int k = 0; k < 3; k++) { bc.pos[k] = 0; bc.normal[k] = 0; }
+            bc.pos[a] = c[a] + (side == 0 ? -0.5 : 0.5) * S.box[a];
+            bc.normal[a] = side == 0 ? 1.0 : -1.0;
+        }
+    bool track = false;
+    for (auto& bc : S.bcs) {
+        if (bc.kind == BCKind::PLANE)
+            bc.wall = dem_b200_add_plane_wall(S.h, bc.pos, bc.normal);
+        else
+            bc.wall = dem_b200_add_zcylinder_wall(S.h, bc.pos, bc.radius, bc.spheres_inside ? 1 : 0);
+        S.check(bc.wall, "CreateBC");
+        if (!bc.enabled)
+            S.check(dem_b200_enable_wall(S.h, bc.wall, 0), "DisableBCbyID");
+        track |= bc.track_forces;
+    }
+    if (track)
+        S.check(dem_b200_track_wall_forces(S.h, 1), "track_forces");
+    for (int k = 0; k < 3; k++) {
+        dem_b200_contact_class cc = S.make_class(k);
+        S.check(dem_b200_set_contact_class(S.h, k, &cc), "set_contact_class");
+    }
+    S.check(dem_b200_set_spheres(S.h, n, S.pos.data(), S.vel.data(), S.omg.data(), S.rad.data(), S.fixed.data()),
+            "SetParticles");
+    {
+        // engine shape ids: wall w is shape w (walls are added in BC-id order), sphere i is shape nW + i
+        const uint32_t nW = (uint32_t)S.bcs.size();
+        for (auto& r : S.hist) {
+            if (r.is_bc && r.partner >= nW)
+                fail("contact history refers to a boundary condition that was not created before Initialize");
+            S.check(dem_b200_add_history(S.h, nW + r.sphere, r.is_bc ? r.partner : nW + r.partner, r.d, 0.0, 0.0),
+                    "ReadContactHistory");
+        }
+    }
+    S.check(dem_b200_initialize(S.h), "Initialize");
+    S.initialized = true;
+    if (S.verbosity != CHDEM_VERBOSITY::QUIET)
+        printf("ChSystemDem (B200 engine): %zu spheres, %zu boundary conditions, h = %g\n", n, S.bcs.size(), (double)S.step);
+}
+
+double ChSystemDem::AdvanceSimulation(float duration) {
+    ChSystemDem_impl& S = *m_sys;
+    if (!S.initialized)
+        fail("AdvanceSimulation before Initialize");
+    const auto t0 = std::chrono::steady_clock::now();
+    const int nsteps = (int)std::lround((double)duration / S.step);  // ChDemSMC.cu:623-624
+    if (!S.any_offset) {
+        S.check(dem_b200_step(S.h, nsteps), "AdvanceSimulation");
+    } else {
+        // moving boundaries: position at the start of each step, velocity = midpoint difference quotient
+        // (ChSystemDem_impl.cpp:863-948)
+        for (int i = 0; i < nsteps; i++) {
+            const float t = (float)(S.elapsed + (double)i * S.step);
+            for (auto& bc : S.bcs) {
+                if (!bc.has_offset || (S.BD_fixed && (&bc - &S.bcs[0]) < (long)NUM_RESERVED_BC_IDS))
+                    continue;
+                const double3 o0 = bc.offset(t), o1 = bc.offset(t + S.step);
+                double p[3] = {bc.pos[0] + o0.x, bc.pos[1] + o0.y, bc.pos[2] + o0.z};
+                double v[3] = {(o1.x - o0.x) / S.step, (o1.y - o0.y) / S.step, (o1.z - o0.z) / S.step};
+                S.check(dem_b200_set_wall_state(S.h, bc.wall, p, v), "SetBCOffsetFunction");
+            }
+            S.check(dem_b200_step(S.h, 1), "AdvanceSimulation");
+        }
+    }
+    S.elapsed += (double)nsteps * S.step;
+    if (S.verbosity == CHDEM_VERBOSITY::METRICS) {
+        S.check(dem_b200_sync(S.h), "AdvanceSimulation");
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        m_RTF = (float)(wall / std::max(1e-30, (double)nsteps * S.step));
+    }
+    return (double)nsteps * S.step;
+}
+
+// ---- state access -----------------------------------------------------------------------------------------------------
+void ChSystemDem::SetParticlePosition(int i, const ChVector3d p) {
+    ChSystemDem_impl& S = *m_sys;
+    if (!S.initialized) {
+        for (int k = 0; k < 3; k++) S.pos[3 * (size_t)i + k] = p[k];
+        return;
+    }
+    const size_t n = S.n();
+    std::vector<double> all(3 * n);
+    S.check(dem_b200_get_state(S.h, all.data(), nullptr, nullptr), "SetParticlePosition");
+    for (int k = 0; k < 3; k++) all[3 * (size_t)i + k] = p[k];
+    S.check(dem_b200_set_state(S.h, all.data(), nullptr, nullptr), "SetParticlePosition");
+}
+void ChSystemDem::SetParticleVelocity(int i, const ChVector3d v) {
+    ChSystemDem_impl& S = *m_sys;
+    if (!S.initialized) {
+        for (int k = 0; k < 3; k++) S.vel[3 * (size_t)i + k] = v[k];
+        return;
+    }
+    const size_t n = S.n();
+    std::vector<double> all(3 * n);
+    S.check(dem_b200_get_state(S.h, nullptr, all.data(), nullptr), "SetParticleVelocity");
+    for (int k = 0; k < 3; k++) all[3 * (size_t)i + k] = v[k];
+    S.check(dem_b200_set_state(S.h, nullptr, all.data(), nullptr), "SetParticleVelocity");
+}
+
+float ChSystemDem::GetSimTime() const { return (float)m_sys->elapsed; }
+size_t ChSystemDem::GetNumParticles() const { return m_sys->n(); }
+float ChSystemDem::GetParticleRadius() const { return m_sys->radius; }
+bool ChSystemDem::IsFixed(int i) const { return m_sys->fixed.at((size_t)i) != 0; }
+unsigned int ChSystemDem::GetNumSDs() const { return 0; }  // no subdomain partition in this engine
+size_t ChSystemDem::EstimateMemUsage() const { return m_sys->n() * 1900; }
+
+static double reduce(const ChSystemDem_impl& S, int which, double arg, const char* what) {
+    if (!S.initialized)
+        fail(std::string(what) + " before Initialize");
+    double out = 0;
+    S.check(dem_b200_reduce(S.h, which, arg, &out), what);
+    return out;
+}
+double ChSystemDem::GetMaxParticleZ() const { return reduce(*m_sys, DEMB200_RED_MAX_Z, 0, "GetMaxParticleZ"); }
+double ChSystemDem::GetMinParticleZ() const { return reduce(*m_sys, DEMB200_RED_MIN_Z, 0, "GetMinParticleZ"); }
+unsigned int ChSystemDem::GetNumParticleAboveZ(float z) const {
+    return (unsigned int)reduce(*m_sys, DEMB200_RED_COUNT_ABOVE_Z, z, "GetNumParticleAboveZ");
+}
+unsigned int ChSystemDem::GetNumParticleAboveX(float x) const {
+    return (unsigned int)reduce(*m_sys, DEMB200_RED_COUNT_ABOVE_X, x, "GetNumParticleAboveX");
+}
+float ChSystemDem::GetParticlesKineticEnergy() const {
+    // the reference sums m v^2 / 2 only (ChSystemDem_impl.cpp:1250-1264); the engine adds the rotational part
+    return (float)reduce(*m_sys, DEMB200_RED_KE, 0, "GetParticlesKineticEnergy");
+}
+unsigned int ChSystemDem::GetNumContacts() const {
+    if (m_sys->friction != CHDEM_FRICTION_MODE::MULTI_STEP)
+        return 0;
+    return (unsigned int)(reduce(*m_sys, DEMB200_RED_NUM_CONTACTS, 0, "GetNumContacts") / 2);
+}
+
+static ChVector3f get3(const ChSystemDem_impl& S, int i, int what) {
+    double p[3], v[3], w[3];
+    if (!S.initialized) {
+        const std::vector<double>& a = what == 0 ? S.pos : what == 1 ? S.vel : S.omg;
+        return ChVector3f((float)a[3 * (size_t)i], (float)a[3 * (size_t)i + 1], (float)a[3 * (size_t)i + 2]);
+    }
+    S.check(dem_b200_get_sphere(S.h, (size_t)i, p, v, w), "GetParticle*");
+    const double* a = what == 0 ? p : what == 1 ? v : w;
+    return ChVector3f((float)a[0], (float)a[1], (float)a[2]);
+}
+ChVector3f ChSystemDem::GetParticlePosition(int i) const { return get3(*m_sys, i, 0); }
+ChVector3f ChSystemDem::GetParticleVelocity(int i) const { return get3(*m_sys, i, 1); }
+ChVector3f ChSystemDem::GetParticleAngVelocity(int i) const {
+    if (m_sys->friction == CHDEM_FRICTION_MODE::FRICTIONLESS)
+        return ChVector3f(0);
+    return get3(*m_sys, i, 2);
+}
+ChVector3f ChSystemDem::GetBCPlanePosition(size_t id) const {
+    const BCInfo& bc = m_sys->bcs.at(id);
+    double3 o = bc.has_offset ? bc.offset((float)m_sys->elapsed) : make_double3(0, 0, 0);
+    return ChVector3f((float)(bc.pos[0] + o.x), (float)(bc.pos[1] + o.y), (float)(bc.pos[2] + o.z));
+}
+bool ChSystemDem::GetBCReactionForces(size_t id, ChVector3f& force) const {
+    if (id >= m_sys->bcs.size() || !m_sys->bcs[id].track_forces || !m_sys->initialized)
+        return false;
+    double f[3];
+    m_sys->check(dem_b200_wall_force(m_sys->h, m_sys->bcs[id].wall, f), "GetBCReactionForces");
+    force = ChVector3f((float)f[0], (float)f[1], (float)f[2]);
+    return true;
+}
+
+// ---- output -----------------------------------------------------------------------------------------------------------
+namespace {
+struct Snapshot {
+    std::vector<double> pos, vel, omg;
+};
+Snapshot snapshot(const ChSystemDem_impl& S) {
+    Snapshot s;
+    const size_t n = S.n();
+    if (!S.initialized) {
+        s.pos = S.pos; s.vel = S.vel; s.omg = S.omg;
+        return s;
+    }
+    s.pos.resize(3 * n); s.vel.resize(3 * n); s.omg.resize(3 * n);
+    S.check(dem_b200_get_state(S.h, s.pos.data(), s.vel.data(), s.omg.data()), "WriteParticleFile");
+    return s;
+}
+}  // namespace
+
+// CSV layout of the reference: ChSystemDem_impl.cpp:259-333 (header, then one row per sphere, default ostream floats)
+void ChSystemDem::WriteCsvParticles(std::ofstream& ptFile) const {
+    const ChSystemDem_impl& S = *m_sys;
+    const Snapshot s = snapshot(S);
+    const unsigned f = S.out_flags;
+    const bool fr = S.friction != CHDEM_FRICTION_MODE::FRICTIONLESS;
+    std::ostringstream o;
+    o << "x,y,z";
+    if (f & VEL_COMPONENTS) o << ",vx,vy,vz";
+    if (f & ABSV) o << ",absv";
+    if (f & FIXITY) o << ",fixed";
+    if (fr && (f & ANG_VEL_COMPONENTS)) o << ",wx,wy,wz";
+    o << "\n";
+    for (size_t i = 0; i < S.n(); i++) {
+        const float x = (float)s.pos[3 * i], y = (float)s.pos[3 * i + 1], z = (float)s.pos[3 * i + 2];
+        o << x << "," << y << "," << z;
+        const float vx = (float)s.vel[3 * i], vy = (float)s.vel[3 * i + 1], vz = (float)s.vel[3 * i + 2];
+        if (f & VEL_COMPONENTS) o << "," << vx << "," << vy << "," << vz;
+        if (f & ABSV) o << "," << (float)std::sqrt((double)vx * vx + (double)vy * vy + (double)vz * vz);
+        if (f & FIXITY) o << "," << (int)S.fixed[i];
+        if (fr && (f & ANG_VEL_COMPONENTS))
+            o << "," << (float)s.omg[3 * i] << "," << (float)s.omg[3 * i + 1] << "," << (float)s.omg[3 * i + 2];
+        o << "\n";
+    }
+    ptFile << o.str();
+}
+
+// headerless packed fp32 records: ChSystemDem_impl.cpp:212-257
+void ChSystemDem::WriteRawParticles(std::ofstream& ptFile) const {
+    const ChSystemDem_impl& S = *m_sys;
+    const Snapshot s = snapshot(S);
+    const unsigned f = S.out_flags;
+    const bool fr = S.friction != CHDEM_FRICTION_MODE::FRICTIONLESS;
+    std::vector<float> rec;
+    for (size_t i = 0; i < S.n(); i++) {
+        rec.clear();
+        for (int k = 0; k < 3; k++) rec.push_back((float)s.pos[3 * i + k]);
+        const float vx = (float)s.vel[3 * i], vy = (float)s.vel[3 * i + 1], vz = (float)s.vel[3 * i + 2];
+        if (f & VEL_COMPONENTS) { rec.push_back(vx); rec.push_back(vy); rec.push_back(vz); }
+        if (f & ABSV) rec.push_back((float)std::sqrt((double)vx * vx + (double)vy * vy + (double)vz * vz));
+        if (fr && (f & ANG_VEL_COMPONENTS))
+            for (int k = 0; k < 3; k++) rec.push_back((float)s.omg[3 * i + k]);
+        ptFile.write((const char*)rec.data(), (std::streamsize)(rec.size() * sizeof(float)));
+    }
+}
+
+void ChSystemDem::WriteParticleFile(const std::string& outfilename) const {
+    switch (m_sys->out_mode) {
+        case CHDEM_OUTPUT_MODE::NONE:
+            return;
+        case CHDEM_OUTPUT_MODE::BINARY: {
+            std::ofstream f(outfilename, std::ios::out | std::ios::binary);
+            WriteRawParticles(f);
+            return;
+        }
+        case CHDEM_OUTPUT_MODE::HDF5:
+            fail("HDF5 output is not available in this build (the reference needs USE_HDF5 too, ChSystemDem_impl.cpp:336)");
+        default: {
+            std::ofstream f(outfilename, std::ios::out);
+            WriteCsvParticles(f);
+        }
+    }
+}
+
+// ---- checkpoint (text grammar of the reference: ChSystemDem.cpp:1322-1412, 1450-1500; reader :704-857, 900-1169) ----
+void ChSystemDem::WriteCheckpointParams(std::ofstream& cp) const {
+    const ChSystemDem_impl& S = *m_sys;
+    std::ostringstream p;
+    p << "nSpheres: " << GetNumParticles() << "\n";
+    p << "density: " << S.density << "\n";
+    p << "radius: " << S.radius << "\n";
+    p << "boxSize: " << S.box[0] << " " << S.box[1] << " " << S.box[2] << "\n";
+    p << "BDFixed: " << (int)S.BD_fixed << "\n";
+    p << "BDCenter: " << S.O[0] << " " << S.O[1] << " " << S.O[2] << "\n";
+    p << "verbosity: " << (unsigned)S.verbosity << "\n";
+    p << "useMinLengthUnit: " << (int)S.use_min_length << "\n";
+    p << "recordContactInfo: " << (int)S.record_contacts << "\n";
+    p << "particleFileMode: " << (unsigned)S.out_mode << "\n";
+    p << "particleFileFlags: " << S.out_flags << "\n";
+    p << "fixedStepSize: " << S.step << "\n";
+    p << "cohesionOverG: " << (float)S.cohesion_over_g << "\n";
+    p << "adhesionOverG_s2w: " << (float)S.adhesion_over_g[1] << "\n";
+    p << "G: " << S.grav[0] << " " << S.grav[1] << " " << S.grav[2] << "\n";
+    p << "elapsedTime: " << GetSimTime() << "\n";
+    p << "K_n_s2s: " << S.Kn[0] << "\n" << "K_n_s2w: " << S.Kn[1] << "\n";
+    p << "K_t_s2s: " << S.Kt[0] << "\n" << "K_t_s2w: " << S.Kt[1] << "\n";
+    p << "G_n_s2s: " << S.Gn[0] << "\n" << "G_n_s2w: " << S.Gn[1] << "\n";
+    p << "G_t_s2s: " << S.Gt[0] << "\n" << "G_t_s2w: " << S.Gt[1] << "\n";
+    p << "RollingCoeff_s2s: " << S.mu_roll[0] << "\n" << "RollingCoeff_s2w: " << S.mu_roll[1] << "\n";
+    p << "SpinningCoeff_s2s: " << S.mu_spin[0] << "\n" << "SpinningCoeff_s2w: " << S.mu_spin[1] << "\n";
+    p << "StaticFrictionCoeff_s2s: " << S.mu[0] << "\n" << "StaticFrictionCoeff_s2w: " << S.mu[1] << "\n";
+    p << "PsiT: " << S.psi_T << "\n" << "PsiL: " << S.psi_L << "\n" << "PsiR: " << S.psi_R << "\n";
+    p << "frictionMode: " << (unsigned)S.friction << "\n";
+    p << "rollingMode: " << (unsigned)S.rolling << "\n";
+    p << "timeIntegrator: " << (unsigned)S.integrator << "\n";
+    p << "maxSafeVelSU: " << S.max_safe_vel << "\n";
+    cp << p.str();
+}
+
+// "partners 12 history 12", then per sphere 12 partner labels and 12 x 3 history floats.  Labels: sphere index, or
+// nSpheres + BC_id + 1 for a boundary (ChDemBoundaryConditions.cuh:102), NULL_CHDEM_ID for an empty slot.  Each sphere
+// lists every contact it takes part in (as the reference does); the displacement is written from that sphere's point of
+// view (sign flipped for the higher-id partner, see the reader).
+void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
+    const ChSystemDem_impl& S = *m_sys;
+    const size_t n = S.n();
+    const unsigned K = MAX_SPHERES_TOUCHED_BY_SPHERE;
+    std::vector<std::vector<std::pair<uint32_t, std::array<float, 3>>>> rows(n);
+    if (S.initialized && S.friction == CHDEM_FRICTION_MODE::MULTI_STEP) {
+        size_t m = 0;
+        S.check(dem_b200_get_history(S.h, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &m), "WriteHstHistory");
+        std::vector<uint32_t> owner(m), other(m);
+        std::vector<double> d(3 * m);
+        if (m)
+            S.check(dem_b200_get_history(S.h, owner.data(), other.data(), d.data(), nullptr, nullptr, m, &m), "WriteHstHistory");
+        const uint32_t nW = (uint32_t)dem_b200_num_walls(S.h);
+        for (size_t c = 0; c < m; c++) {
+            const uint32_t so = owner[c] - nW;  // owner = higher shape id = body 2 of the canonical orientation
+            std::array<float, 3> hv = {(float)-d[3 * c], (float)-d[3 * c + 1], (float)-d[3 * c + 2]};
+            if (other[c] < nW) {  // wall: label by BC id
+                size_t bc = 0;
+                for (; bc < S.bcs.size(); bc++)
+                    if (S.bcs[bc].wall == (int)other[c]) break;
+                rows[so].push_back({(uint32_t)(n + bc + 1), hv});
+            } else {
+                const uint32_t sp = other[c] - nW;
+                rows[so].push_back({sp, hv});
+                rows[sp].push_back({so, {-hv[0], -hv[1], -hv[2]}});
+            }
+        }
+    }
+    std::ostringstream o;
+    o << "partners " << K << " history " << K << "\n";
+    for (size_t i = 0; i < n; i++) {
+        for (unsigned k = 0; k < K; k++)
+            o << (k < rows[i].size() ? rows[i][k].first : (uint32_t)NULL_CHDEM_ID) << " ";
+        for (unsigned k = 0; k < K; k++) {
+            if (k < rows[i].size())
+                o << rows[i][k].second[0] << " " << rows[i][k].second[1] << " " << rows[i][k].second[2] << " ";
+            else
+                o << "0 0 0 ";
+        }
+        o << "\n";
+    }
+    hf << o.str();
+}
+
+void ChSystemDem::WriteContactHistoryFile(const std::string& outfilename) const {
+    std::ofstream f(outfilename, std::ios::out);
+    WriteHstHistory(f);
+}
+
+void ChSystemDem::WriteCheckpointFile(const std::string& outfilename) {
+    std::ofstream cp(outfilename, std::ios::out);
+    cp << "ChSystemDem\n";
+    WriteCheckpointParams(cp);
+    cp << "ParamsEnd\n\n";
+    cp << "CsvParticles\n";
+    const unsigned int flags = m_sys->out_flags;
+    const CHDEM_FRICTION_MODE fm = m_sys->friction;
+    m_sys->out_flags = VEL_COMPONENTS | FIXITY | ANG_VEL_COMPONENTS;
+    WriteCsvParticles(cp);
+    m_sys->out_flags = flags;
+    cp << "\n";
+    if (fm != CHDEM_FRICTION_MODE::FRICTIONLESS) {
+        cp << "HstHistory\n";
+        WriteHstHistory(cp);
+        cp << "\n";
+    }
+}
+
+bool ChSystemDem::SetParamsFromIdentifier(const std::string& id, std::istringstream& iss, bool /*overwrite*/) {
+    ChSystemDem_impl& S = *m_sys;
+    unsigned u;
+    if (id == "density") iss >> S.density;
+    else if (id == "radius") iss >> S.radius;
+    else if (id == "boxSize") iss >> S.box[0] >> S.box[1] >> S.box[2];
+    else if (id == "BDFixed") { iss >> u; S.BD_fixed = u != 0; }
+    else if (id == "BDCenter") iss >> S.O[0] >> S.O[1] >> S.O[2];
+    else if (id == "verbosity") { iss >> u; S.verbosity = (CHDEM_VERBOSITY)u; }
+    else if (id == "useMinLengthUnit") { iss >> u; S.use_min_length = u != 0; }
+    else if (id == "recordContactInfo") { iss >> u; S.record_contacts = u != 0; }
+    else if (id == "particleFileMode") { iss >> u; S.out_mode = (CHDEM_OUTPUT_MODE)u; }
+    else if (id == "particleFileFlags") iss >> S.out_flags;
+    else if (id == "fixedStepSize") iss >> S.step;
+    else if (id == "cohesionOverG") iss >> S.cohesion_over_g;
+    else if (id == "adhesionOverG_s2w") iss >> S.adhesion_over_g[1];
+    else if (id == "G") iss >> S.grav[0] >> S.grav[1] >> S.grav[2];
+    else if (id == "elapsedTime") iss >> S.elapsed;
+    else if (id == "K_n_s2s") iss >> S.Kn[0];
+    else if (id == "K_n_s2w") iss >> S.Kn[1];
+    else if (id == "K_t_s2s") iss >> S.Kt[0];
+    else if (id == "K_t_s2w") iss >> S.Kt[1];
+    else if (id == "G_n_s2s") iss >> S.Gn[0];
+    else if (id == "G_n_s2w") iss >> S.Gn[1];
+    else if (id == "G_t_s2s") iss >> S.Gt[0];
+    else if (id == "G_t_s2w") iss >> S.Gt[1];
+    else if (id == "RollingCoeff_s2s") iss >> S.mu_roll[0];
+    else if (id == "RollingCoeff_s2w") iss >> S.mu_roll[1];
+    else if (id == "SpinningCoeff_s2s") iss >> S.mu_spin[0];
+    else if (id == "SpinningCoeff_s2w") iss >> S.mu_spin[1];
+    else if (id == "StaticFrictionCoeff_s2s") iss >> S.mu[0];
+    else if (id == "StaticFrictionCoeff_s2w") iss >> S.mu[1];
+    else if (id == "PsiT") iss >> S.psi_T;
+    else if (id == "PsiL") iss >> S.psi_L;
+    else if (id == "PsiR") iss >> S.psi_R;
+    else if (id == "frictionMode") { iss >> u; S.friction = (CHDEM_FRICTION_MODE)u; }
+    else if (id == "rollingMode") { iss >> u; S.rolling = (CHDEM_ROLLING_MODE)u; }
+    else if (id == "timeIntegrator") { iss >> u; S.integrator = (CHDEM_TIME_INTEGRATOR)u; }
+    else if (id == "maxSafeVelSU") iss >> S.max_safe_vel;
+    else if (id == "nSpheres") { /* consumed by ReadDatParams */ }
+    else return false;
+    return true;
+}
+
+unsigned int ChSystemDem::ReadDatParams(std::ifstream& ifile, bool overwrite) {
+    std::string line;
+    unsigned int nSpheres = 0;
+    while (std::getline(ifile, line)) {
+        if (line.find("ParamsEnd") != std::string::npos)
+            break;
+        const size_t colon = line.find(':');
+        if (colon == std::string::npos)
+            continue;
+        const std::string id = line.substr(0, colon);
+        std::istringstream iss(line.substr(colon + 1));
+        if (id == "nSpheres") {
+            std::istringstream t(line.substr(colon + 1));
+            t >> nSpheres;
+        }
+        if (!SetParamsFromIdentifier(id, iss, overwrite) && m_sys->verbosity != CHDEM_VERBOSITY::QUIET)
+            printf("ChSystemDem: unknown checkpoint parameter \"%s\" skipped\n", id.c_str());
+    }
+    return nSpheres;
+}
+
+void ChSystemDem::ReadCsvParticles(std::ifstream& ifile, unsigned int totRow) {
+    ChSystemDem_impl& S = *m_sys;
+    std::string line;
+    if (!std::getline(ifile, line))
+        fail("particle file: missing header");
+    std::vector<std::string> cols;
+    {
+        std::istringstream h(line);
+        std::string c;
+        while (std::getline(h, c, ',')) {
+            while (!c.empty() && (c.back() == '\r' || c.back() == ' ')) c.pop_back();
+            cols.push_back(c);
+        }
+    }
+    auto col = [&](const char* name) {
+        for (size_t i = 0; i < cols.size(); i++)
+            if (cols[i] == name) return (int)i;
+        return -1;
+    };
+    const int ix = col("x"), iy = col("y"), iz = col("z"), ivx = col("vx"), ivy = col("vy"), ivz = col("vz"),
+              ifx = col("fixed"), iwx = col("wx"), iwy = col("wy"), iwz = col("wz");
+    if (ix < 0 || iy < 0 || iz < 0)
+        fail("particle file: x,y,z columns are required");
+    S.pos.clear(); S.vel.clear(); S.omg.clear(); S.fixed.clear();
+    unsigned int rows = 0;
+    while (rows < totRow && std::getline(ifile, line)) {
+        if (line.empty() || line == "\r")
+            break;
+        std::vector<double> v;
+        std::istringstream r(line);
+        std::string c;
+        while (std::getline(r, c, ','))
+            v.push_back(std::stod(c));
+        auto get = [&](int i) { return (i >= 0 && i < (int)v.size()) ? v[i] : 0.0; };
+        S.pos.push_back(get(ix)); S.pos.push_back(get(iy)); S.pos.push_back(get(iz));
+        S.vel.push_back(get(ivx)); S.vel.push_back(get(ivy)); S.vel.push_back(get(ivz));
+        S.omg.push_back(get(iwx)); S.omg.push_back(get(iwy)); S.omg.push_back(get(iwz));
+        S.fixed.push_back(get(ifx) != 0 ? 1 : 0);
+        rows++;
+    }
+    S.rad.assign(rows, S.radius);
+}
+
+void ChSystemDem::ReadHstHistory(std::ifstream& ifile, unsigned int totItem) {
+    ChSystemDem_impl& S = *m_sys;
+    std::string line, w1, w2;
+    if (!std::getline(ifile, line))
+        fail("history: missing header");
+    unsigned np = 0, nh = 0;
+    {
+        std::istringstream h(line);
+        h >> w1 >> np >> w2 >> nh;
+        if (w1 != "partners" || w2 != "history" || np == 0 || np != nh)
+            fail("history: header must read \"partners N history N\"");
+    }
+    const size_t n = S.n();
+    S.hist.clear();
+    for (size_t i = 0; i < n && i < totItem; i++) {
+        if (!std::getline(ifile, line))
+            break;
+        std::istringstream r(line);
+        std::vector<uint32_t> partner(np);
+        for (auto& p : partner) r >> p;
+        for (unsigned k = 0; k < np; k++) {
+            double d[3];
+            r >> d[0] >> d[1] >> d[2];
+            const uint32_t p = partner[k];
+            if (p == (uint32_t)NULL_CHDEM_ID)
+                continue;
+            ChSystemDem_impl::HistRow row;
+            row.sphere = (uint32_t)i;
+            if (p > n) {  // boundary label nSpheres + BC_id + 1 (ChDemBoundaryConditions.cuh:102)
+                row.is_bc = true;
+                row.partner = p - (uint32_t)n - 1;
+            } else {
+                if (p > i)
+                    continue;  // the higher-id partner's copy is the one we keep (both are present in the file)
+                row.is_bc = false;
+                row.partner = p;
+            }
+            // canonical orientation: body 1 = wall / lower id; the file holds the view of sphere i = body 2
+            for (int c = 0; c < 3; c++) row.d[c] = -d[c];
+            S.hist.push_back(row);
+        }
+    }
+}
+
+void ChSystemDem::ReadParticleFile(const std::string& infilename) {
+    std::ifstream f(infilename);
+    if (!f)
+        fail("cannot open " + infilename);
+    ReadCsvParticles(f);
+    m_sys->defragment = false;
+}
+void ChSystemDem::ReadContactHistoryFile(const std::string& infilename) {
+    std::ifstream f(infilename);
+    if (!f)
+        fail("cannot open " + infilename);
+    ReadHstHistory(f);
+}
+
+void ChSystemDem::ReadCheckpointFile(const std::string& infilename, bool overwrite) {
+    if (m_sys->initialized)
+        fail("ReadCheckpointFile after Initialize");
+    std::ifstream f(infilename);
+    if (!f)
+        fail("cannot open checkpoint " + infilename);
+    std::string line;
+    if (!std::getline(f, line))
+        fail("empty checkpoint");
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+    // "ChSystemGpu" is the header the module wrote before it was renamed (data/testing/dem/pyramid_checkpoint.dat:1)
+    if (line != "ChSystemDem" && line != "ChSystemGpu" && line != "ChSystemDemMesh" && line != "ChSystemGpuMesh")
+        fail("not a Chrono::Dem checkpoint: " + line);
+    const unsigned int n = ReadDatParams(f, overwrite);
+    while (std::getline(f, line)) {
+        if (line.find("CsvParticles") != std::string::npos)
+            ReadCsvParticles(f, n);
+        else if (line.find("HstHistory") != std::string::npos)
+            ReadHstHistory(f, n);
+    }
+    if (m_sys->n() != n)
+        fail("checkpoint: nSpheres does not match the particle block");
+    m_sys->defragment = false;  // ids stay stable (ChSystemDem.cpp:785-786); ours always are
+}
+
+}  // namespace dem
+}  // namespace chrono

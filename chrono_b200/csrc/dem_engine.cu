@@ -30,6 +30,9 @@ struct dem_b200_system {
     dem_b200_config cfg{};
     Params P{};
     Buffers B{};
+    WallSet W{};                       // host copy of the walls (device copy: B.walls)
+    bool cls_override[3] = {false, false, false};
+    dem_b200_contact_class cls[3]{};   // explicit contact-class coefficients (dem_b200_set_contact_class)
     // scene staged on the host until initialize()
     std::vector<double> h_pos, h_vel, h_om, h_rad;
     std::vector<uint8_t> h_fixed;
@@ -41,6 +44,7 @@ struct dem_b200_system {
     bool recording = false;
     size_t max_pairs = 0;
     bool use_hrel = false;
+    bool track_wall_forces = false;
     double time = 0.0;
     std::string err;
     // scratch (device, by user index) and pinned host staging
@@ -138,10 +142,22 @@ void refresh_params(dem_b200_system* s) {
     P.comp[0] = make_comp(c.material[DEMB200_MAT_SPHERE], c.material[DEMB200_MAT_SPHERE]);
     P.comp[1] = make_comp(c.material[DEMB200_MAT_WALL], c.material[DEMB200_MAT_SPHERE]);
     P.comp[2] = make_comp(c.material[DEMB200_MAT_MESH], c.material[DEMB200_MAT_SPHERE]);
+    for (int k = 0; k < 3; k++)
+        if (s->cls_override[k]) {
+            const dem_b200_contact_class& o = s->cls[k];
+            Comp& cm = P.comp[k];
+            cm.E_eff = o.E_eff; cm.G_eff = o.G_eff; cm.mu = o.mu; cm.mu_roll = o.mu_roll; cm.mu_spin = o.mu_spin;
+            cm.cr = o.cr; cm.adh = o.adhesion; cm.kn = o.kn; cm.kt = o.kt; cm.gn = o.gn; cm.gt = o.gt;
+            const double eps = 2.220446049250313e-16, kPI = 3.141592653589793238462643383279;
+            double loge = (cm.cr < eps) ? std::log(eps) : std::log(cm.cr);
+            cm.hertz_damp = -2 * std::sqrt(5.0 / 6) * (loge / std::sqrt(loge * loge + kPI * kPI));
+            cm.gt_ratio = (cm.E_eff > 0) ? std::sqrt(4.0 * cm.G_eff / cm.E_eff) : 0.0;
+        }
     // union of the box-wall AABBs
-    P.has_wall_bb = 0;
+    WallSet& WS = s->W;
+    WS.has_bb = 0;
     for (int w = 0; w < P.nW; w++) {
-        Wall& W = P.walls[w];
+        Wall& W = WS.w[w];
         if (W.type != WALL_BOX)
             continue;
         double ext[3];
@@ -149,16 +165,17 @@ void refresh_params(dem_b200_system* s) {
         for (int k = 0; k < 3; k++) {
             W.amin[k] = W.pos[k] - ext[k];
             W.amax[k] = W.pos[k] + ext[k];
-            if (!P.has_wall_bb) {
-                P.wall_bb_min[k] = W.amin[k];
-                P.wall_bb_max[k] = W.amax[k];
+            if (!WS.has_bb) {
+                WS.bb_min[k] = W.amin[k];
+                WS.bb_max[k] = W.amax[k];
             } else {
-                P.wall_bb_min[k] = std::min(P.wall_bb_min[k], W.amin[k]);
-                P.wall_bb_max[k] = std::max(P.wall_bb_max[k], W.amax[k]);
+                WS.bb_min[k] = std::min(WS.bb_min[k], W.amin[k]);
+                WS.bb_max[k] = std::max(WS.bb_max[k], W.amax[k]);
             }
         }
-        P.has_wall_bb = 1;
+        WS.has_bb = 1;
     }
+    P.track_wall_forces = s->track_wall_forces ? 1 : 0;
     P.shape_base = (unsigned)P.nW;
     // Verlet skin: negative -> default 0.25 * largest radius (set at initialize, when radii are known)
     if (c.verlet_skin >= 0)
@@ -297,8 +314,8 @@ int read_ctrl(dem_b200_system* s, Ctrl* out) {
 int recompute_bbox(dem_b200_system* s) {
     unsigned long long init[6];
     for (int k = 0; k < 3; k++) {
-        init[k] = s->P.has_wall_bb ? enc_ord_h(s->P.wall_bb_min[k]) : enc_ord_h(INFINITY);
-        init[3 + k] = s->P.has_wall_bb ? enc_ord_h(s->P.wall_bb_max[k]) : enc_ord_h(-INFINITY);
+        init[k] = s->W.has_bb ? enc_ord_h(s->W.bb_min[k]) : enc_ord_h(INFINITY);
+        init[3 + k] = s->W.has_bb ? enc_ord_h(s->W.bb_max[k]) : enc_ord_h(-INFINITY);
     }
     CU(cudaMemcpyAsync(s->B.ctrl->bbox, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));  // init[] is on the stack
@@ -461,9 +478,10 @@ static int add_wall(dem_b200_system* s, int type, const double pos[3], const dou
         s->err = "too many walls";
         return DEMB200_EINVAL;
     }
-    Wall& W = s->P.walls[s->P.nW];
+    Wall& W = s->W.w[s->P.nW];
     memset(&W, 0, sizeof(W));
     W.type = type;
+    W.enabled = 1;
     for (int k = 0; k < 3; k++) {
         W.pos[k] = pos[k];
         W.hdims[k] = hd[k];
@@ -489,22 +507,84 @@ int dem_b200_add_plane_wall(dem_b200_system* s, const double pos[3], const doubl
     double n[3] = {normal[0] / l, normal[1] / l, normal[2] / l};
     return add_wall(s, WALL_PLANE, pos, nullptr, n);
 }
-int dem_b200_set_wall_velocity(dem_b200_system* s, int w, const double pos[3], const double vel[3]) {
+int dem_b200_add_zcylinder_wall(dem_b200_system* s, const double center[3], double radius, int spheres_inside) {
+    if (!(radius > 0))
+        return DEMB200_EINVAL;
+    double hd[3] = {radius, spheres_inside ? 1.0 : -1.0, 0.0};
+    return add_wall(s, WALL_ZCYL, center, nullptr, hd);
+}
+
+static int upload_walls(dem_b200_system* s) {
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemcpyAsync(s->B.walls, &s->W, sizeof(WallSet), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));  // s->W may change again right after this call
+    return 0;
+}
+
+int dem_b200_set_wall_state(dem_b200_system* s, int w, const double pos[3], const double vel[3]) {
     if (!s || w < 0 || w >= s->P.nW)
         return DEMB200_EINVAL;
+    double moved = 0;
     for (int k = 0; k < 3; k++) {
-        if (pos) s->P.walls[w].pos[k] = pos[k];
-        if (vel) s->P.walls[w].vel[k] = vel[k];
+        if (pos) {
+            moved += (pos[k] - s->W.w[w].pos[k]) * (pos[k] - s->W.w[w].pos[k]);
+            s->W.w[w].pos[k] = pos[k];
+        }
+        if (vel) s->W.w[w].vel[k] = vel[k];
     }
     refresh_params(s);
-    drop_graph(s);
-    if (s->initialized) {
-        // the per-sphere wall candidate masks were computed for the old wall position
-        CU(cudaSetDevice(s->cfg.device));
-        const unsigned one = 1;
-        CU(cudaMemcpyAsync(&s->B.ctrl->need_rebuild, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+    if (!s->initialized)
+        return 0;
+    // walls live in device memory: the captured graph stays valid.  A moving wall uses up Verlet skin like a moving
+    // sphere (the per-sphere wall-candidate masks were computed with a skin/2 reach).
+    int rc = upload_walls(s);
+    if (rc)
+        return rc;
+    if (moved > 0) {
+        k_wall_moved<<<1, 1, 0, s->stream>>>(s->B, std::sqrt(moved));
+        CU(cudaGetLastError());
     }
+    return 0;
+}
+int dem_b200_set_wall_velocity(dem_b200_system* s, int w, const double pos[3], const double vel[3]) {
+    return dem_b200_set_wall_state(s, w, pos, vel);
+}
+int dem_b200_enable_wall(dem_b200_system* s, int w, int enabled) {
+    if (!s || w < 0 || w >= s->P.nW)
+        return DEMB200_EINVAL;
+    s->W.w[w].enabled = enabled ? 1 : 0;
+    return s->initialized ? upload_walls(s) : 0;
+}
+int dem_b200_track_wall_forces(dem_b200_system* s, int enable) {
+    if (!s)
+        return DEMB200_EINVAL;
+    s->track_wall_forces = enable != 0;
+    refresh_params(s);
+    drop_graph(s);
+    return 0;
+}
+int dem_b200_wall_force(dem_b200_system* s, int w, double force[3]) {
+    if (!s || !s->initialized || w < 0 || w >= s->P.nW || !force)
+        return DEMB200_EINVAL;
+    if (!s->track_wall_forces) {
+        s->err = "wall_force: call dem_b200_track_wall_forces(s, 1) first";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemcpyAsync(s->h_pin, s->B.ctrl->wall_force[w], 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < 3; k++)
+        force[k] = s->h_pin[k];
+    return 0;
+}
+int dem_b200_set_contact_class(dem_b200_system* s, int cls, const dem_b200_contact_class* c) {
+    if (!s || cls < 0 || cls > 2)
+        return DEMB200_EINVAL;
+    s->cls_override[cls] = (c != nullptr);
+    if (c)
+        s->cls[cls] = *c;
+    refresh_params(s);
+    drop_graph(s);
     return 0;
 }
 int dem_b200_num_walls(const dem_b200_system* s) { return s ? s->P.nW : 0; }
@@ -541,8 +621,8 @@ int dem_b200_initialize(dem_b200_system* s) {
     {
         double mn[3], mx[3];
         for (int k = 0; k < 3; k++) {
-            mn[k] = P.has_wall_bb ? P.wall_bb_min[k] : INFINITY;
-            mx[k] = P.has_wall_bb ? P.wall_bb_max[k] : -INFINITY;
+            mn[k] = s->W.has_bb ? s->W.bb_min[k] : INFINITY;
+            mx[k] = s->W.has_bb ? s->W.bb_max[k] : -INFINITY;
         }
         for (size_t i = 0; i < n; i++)
             for (int k = 0; k < 3; k++) {
@@ -564,6 +644,7 @@ int dem_b200_initialize(dem_b200_system* s) {
     int rc = 0;
     const size_t HS = (size_t)P.Kn + (size_t)P.nW;  // history slots per sphere: one per candidate + one per wall
     rc |= dev_alloc(s, &B.ctrl, 1);
+    rc |= dev_alloc(s, &B.walls, 1);
     for (int b = 0; b < 2; b++) {
         rc |= dev_alloc(s, &B.pos[b], Np);
         rc |= dev_alloc(s, &B.vel[b], Np);
@@ -682,6 +763,7 @@ int dem_b200_initialize(dem_b200_system* s) {
         c.need_rebuild = 1;
         c.init_stage = rows.empty() ? 0u : 1u;
         CU(cudaMemcpy(B.ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(B.walls, &s->W, sizeof(WallSet), cudaMemcpyHostToDevice));
     }
     s->h_pos.clear(); s->h_pos.shrink_to_fit();
     s->h_vel.clear(); s->h_vel.shrink_to_fit();

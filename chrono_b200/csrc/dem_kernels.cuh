@@ -110,6 +110,8 @@ __device__ __forceinline__ double pack_key(unsigned key, unsigned steps) { retur
 __device__ __forceinline__ unsigned rec_key(double w) { return (unsigned)__double2loint(w); }
 __device__ __forceinline__ unsigned rec_steps(double w) { return (unsigned)__double2hiint(w); }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Fast reciprocal / reciprocal square root for normal, positive, well-scaled arguments: hardware seed
 // (MUFU.RCP64H / MUFU.RSQ64H, ~2^-23) + one cubically convergent correction, error <= ~1 ulp, no special-case branch.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -176,6 +178,7 @@ __global__ void k_step_begin(Params P, Buffers B) {
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
     Ctrl& C = *B.ctrl;
+    const WallSet& WS = *B.walls;
     // ---- Verlet bookkeeping: every sphere moved at most `travel` since the lists were built ----
     const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
     C.max_dx2 = 0ull;
@@ -189,9 +192,9 @@ __global__ void k_step_begin(Params P, Buffers B) {
     for (int k = 0; k < 3; k++) {
         mn[k] = dec_ord(C.bbox[k]);
         mx[k] = dec_ord(C.bbox[3 + k]);
-        if (P.has_wall_bb) {
-            mn[k] = fmin(mn[k], P.wall_bb_min[k]);
-            mx[k] = fmax(mx[k], P.wall_bb_max[k]);
+        if (WS.has_bb) {
+            mn[k] = fmin(mn[k], WS.bb_min[k]);
+            mx[k] = fmax(mx[k], WS.bb_max[k]);
         }
     }
     // ---- Multicore grid: ChBroadphase::DetermineBoundingBox + ComputeTopLevelResolution (ChBroadphase.cpp:143-208)
@@ -212,8 +215,8 @@ __global__ void k_step_begin(Params P, Buffers B) {
     }
     for (int w = 0; w < P.nW; w++)
         for (int k = 0; k < 3; k++) {
-            G.wmin[w][k] = __dsub_rn(P.walls[w].amin[k], G.origin[k]);
-            G.wmax[w][k] = __dsub_rn(P.walls[w].amax[k], G.origin[k]);
+            G.wmin[w][k] = __dsub_rn(WS.w[w].amin[k], G.origin[k]);
+            G.wmax[w][k] = __dsub_rn(WS.w[w].amax[k], G.origin[k]);
         }
     if (err)
         atomicOr(&C.err, err);
@@ -265,9 +268,17 @@ __global__ void k_step_begin(Params P, Buffers B) {
     C.pair_count = 0ull;
     // restart the running sphere bounding box for the positions this step will produce
     for (int k = 0; k < 3; k++) {
-        C.bbox[k] = P.has_wall_bb ? enc_ord(P.wall_bb_min[k]) : enc_ord(CUDART_INF);
-        C.bbox[3 + k] = P.has_wall_bb ? enc_ord(P.wall_bb_max[k]) : enc_ord(-CUDART_INF);
+        C.bbox[k] = WS.has_bb ? enc_ord(WS.bb_min[k]) : enc_ord(CUDART_INF);
+        C.bbox[3 + k] = WS.has_bb ? enc_ord(WS.bb_max[k]) : enc_ord(-CUDART_INF);
     }
+    for (int w = 0; w < P.nW; w++)
+        C.wall_force[w][0] = C.wall_force[w][1] = C.wall_force[w][2] = 0.0;
+}
+
+// A wall was moved by the host (dem_b200_set_wall_state): its displacement uses up Verlet skin like a sphere's.
+__global__ void k_wall_moved(Buffers B, double dist) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        B.ctrl->travel += dist;
 }
 
 // HashMin of the sphere AABB lower corner, HashMax of the upper corner (ChCollisionUtils.h:44-60), computed on the
@@ -612,13 +623,16 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     {
         const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
         for (int w = 0; w < P.nW; w++) {
-            const Wall& W = P.walls[w];
+            const Wall& W = B.walls->w[w];
             bool near;
             if (W.type == WALL_BOX) {
                 near = me.x - reach <= W.amax[0] && W.amin[0] <= me.x + reach && me.y - reach <= W.amax[1] &&
                        W.amin[1] <= me.y + reach && me.z - reach <= W.amax[2] && W.amin[2] <= me.z + reach;
-            } else {
+            } else if (W.type == WALL_PLANE) {
                 near = (me.x - W.pos[0]) * W.hdims[0] + (me.y - W.pos[1]) * W.hdims[1] + (me.z - W.pos[2]) * W.hdims[2] < reach;
+            } else {
+                const double dxy = sqrt((me.x - W.pos[0]) * (me.x - W.pos[0]) + (me.y - W.pos[1]) * (me.y - W.pos[1]));
+                near = (W.hdims[1] > 0) ? (dxy + reach > W.hdims[0]) : (dxy - reach < W.hdims[0]);
             }
             if (near)
                 wc |= 1u << w;
@@ -1016,13 +1030,36 @@ __device__ __forceinline__ bool plane_sphere_dev(const Wall& W, V3 pos2, double 
     return true;
 }
 
+// Z-axis cylinder (Chrono::Dem CreateBCCylinderZ, ChSystemDem.h:228; force form of addBCForces_Zcyl,
+// ChDemBoundaryConditions.cuh): hdims = (radius, side): side +1 = spheres inside (normal towards the axis),
+// side -1 = spheres outside.  Face contact, eff. radius r.
+__device__ __forceinline__ bool zcyl_sphere_dev(const Wall& W, V3 pos2, double r2, Geom& g) {
+    const double dx = pos2.x - W.pos[0], dy = pos2.y - W.pos[1];
+    const double d = sqrt(dx * dx + dy * dy);
+    const double Rc = W.hdims[0];
+    const bool inside = W.hdims[1] > 0;
+    const double gap = inside ? (Rc - d) : (d - Rc);  // distance from the sphere centre to the wall surface
+    if (gap >= r2 || !(d > 1e-12 * Rc))
+        return false;
+    const double s = inside ? -1.0 : 1.0;
+    g.n = mk(s * dx / d, s * dy / d, 0.0);  // from the wall towards the sphere
+    g.depth = gap - r2;
+    g.pt1 = pos2 - gap * g.n;
+    g.pt2 = pos2 - r2 * g.n;
+    g.erad = r2;
+    return true;
+}
+
 // --------------------------------------------------------------------------------------------
 // fused narrowphase + force + integrate.  One thread per sphere in storage (cell) order.
 // --------------------------------------------------------------------------------------------
 constexpr int kForceThreads = 128;
+#ifndef DEMB200_FORCE_MINBLOCKS
+#define DEMB200_FORCE_MINBLOCKS 4
+#endif
 
 template <bool HIST, bool ROLL, bool FAST, bool REC>
-__global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
                                                                       const __grid_constant__ Buffers B) {
     __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
     __shared__ unsigned char cslot[kMaxSlots * kForceThreads];  // its index in the candidate list (= history slot)
@@ -1044,6 +1081,16 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
         me = pos_in[s];
         mv = load_vel(vel_in, s);
         // ---- phase 1: exact sphere_sphere test (ChNarrowphasePRIMS.cpp:50-59, separation = 0) on the candidates
+        if (HIST) {
+            // the live history records of this sphere are a pure stream (read once, by this thread): start them now
+            unsigned long long m = mv.amask;
+            const double4* hp = B.hist + s;
+            while (m) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                prefetch_l1(hp + (size_t)k * P.Np);
+            }
+        }
         const unsigned ncw = B.ncnt[s];
         const unsigned nc = ncw & 0xFFu;
         wcand = ncw >> 8;
@@ -1077,6 +1124,7 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
                     clist[cnt * kForceThreads + tid] = jj[u];
                     cslot[cnt * kForceThreads + tid] = (unsigned char)(k0 + u);
                 }
+                prefetch_l1(vel_in + jj[u]);  // the partner's velocity record is needed in phase 2
                 cnt++;
             }
         }
@@ -1106,10 +1154,14 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
         while (wcand) {
             const int w = __ffs(wcand) - 1;
             wcand &= wcand - 1;
-            const Wall& W = P.walls[w];
+            const Wall& W = B.walls->w[w];
+            if (!W.enabled)
+                continue;
             Geom g;
             bool hit;
-            if (W.type == WALL_BOX) {
+            if (W.type == WALL_ZCYL) {
+                hit = zcyl_sphere_dev(W, mpos, me.w, g);
+            } else if (W.type == WALL_BOX) {
                 // broadphase AABB overlap on origin-offset boxes (ChCollisionUtils.h:83-87)
                 if (!(amin[0] <= G.wmax[w][0] && G.wmin[w][0] <= amax[0] && amin[1] <= G.wmax[w][1] &&
                       G.wmin[w][1] <= amax[1] && amin[2] <= G.wmax[w][2] && G.wmin[w][2] <= amax[2]))
@@ -1147,6 +1199,11 @@ __global__ void __launch_bounds__(kForceThreads, 4) k_force_integrate(const __gr
             contact_force<HIST, ROLL>(P, P.comp[1], b1, b2, g, h, F, T1, T2);
             Fsum = Fsum + F;
             Tsum = Tsum + T2;
+            if (P.track_wall_forces) {
+                atomicAdd(&C.wall_force[w][0], -F.x);
+                atomicAdd(&C.wall_force[w][1], -F.y);
+                atomicAdd(&C.wall_force[w][2], -F.z);
+            }
             if (HIST) {
                 hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, steps);
                 if (rcol)

@@ -36,7 +36,7 @@ enum : unsigned {
     ERR_PAIR_CAPACITY = 32u
 };
 
-enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1 };
+enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1, WALL_ZCYL = 2 };
 
 // Composite material of a contact class, widened from the float values the reference computes
 // (src/chrono/physics/ChContactMaterialSMC.cpp:107-130).
@@ -49,11 +49,19 @@ struct Comp {
 
 struct Wall {
     int type;
-    double pos[3];     // box centre / plane point (world)
+    int enabled;       // DisableBCbyID / EnableBCbyID
+    double pos[3];     // box centre / plane point / a point on the cylinder axis (world)
     double rot[4];     // box orientation (w,x,y,z)
-    double hdims[3];   // box half dimensions / plane unit normal
+    double hdims[3];   // box half dimensions / plane unit normal / (cylinder radius, +1 spheres inside | -1 outside, -)
     double vel[3];     // velocity of the wall body (moving boundaries)
-    double amin[3], amax[3];  // world AABB (ChCollisionSystemMulticore.cpp:395-406)
+    double amin[3], amax[3];  // world AABB (ChCollisionSystemMulticore.cpp:395-406); boxes only
+};
+
+// All walls live in one device block so that they can move (SetBCOffsetFunction) without touching the CUDA graph.
+struct WallSet {
+    Wall w[kMaxWalls];
+    double bb_min[3], bb_max[3];  // union of the box-wall AABBs (planes / cylinders are unbounded: excluded)
+    int has_bb;
 };
 
 struct Params {
@@ -67,14 +75,12 @@ struct Params {
     double g[3];
     double mass_coef, wall_mass;
     Comp comp[3];
-    Wall walls[kMaxWalls];
     int bins[3];          // Multicore broadphase resolution (parity output only; the search grid is our own)
     unsigned shape_base;  // shape id of sphere sid is shape_base + sid
     double rmax;          // largest sphere radius
     double skin;          // Verlet skin: candidates are spheres closer than r_i + r_j + skin at rebuild time
     unsigned cell_cap;    // capacity of the search-cell arrays
-    double wall_bb_min[3], wall_bb_max[3];  // union of wall AABBs (infinite planes excluded)
-    int has_wall_bb;
+    int track_wall_forces;  // accumulate the reaction force on every wall (GetBCReactionForces)
 };
 
 // 64-byte velocity record.  meta = flags (bits 0-7: 1 = fixed) | live wall-contact mask (bits 8-23);
@@ -112,10 +118,12 @@ struct Ctrl {
     unsigned s_ncell;
     GridDev mc;
     unsigned long long n_contacts, pair_count;
+    double wall_force[kMaxWalls][3];  // force exerted by the spheres on wall w during the last step
 };
 
 struct Buffers {
     Ctrl* ctrl;
+    WallSet* walls;
     // state, ping-pong
     double4* pos[2];
     VelRec* vel[2];

@@ -96,7 +96,29 @@ int dem_b200_add_box_wall(dem_b200_system* s, const double pos[3], const double 
 /* Infinite plane wall (Chrono::Dem CreateBCPlane, src/chrono_dem/physics/ChSystemDem.h:228): point + unit normal
  * pointing into the domain.  Contact iff distance < r; eff. radius = r. */
 int dem_b200_add_plane_wall(dem_b200_system* s, const double pos[3], const double normal[3]);
-int dem_b200_set_wall_velocity(dem_b200_system* s, int wall, const double pos[3], const double vel[3]);
+/* Z-axis cylinder (Chrono::Dem CreateBCCylinderZ, src/chrono_dem/physics/ChSystemDem.h:235): spheres_inside != 0 ->
+ * container wall (normal towards the axis), else an obstacle. */
+int dem_b200_add_zcylinder_wall(dem_b200_system* s, const double center[3], double radius, int spheres_inside);
+/* Move a wall (SetBCOffsetFunction, src/chrono_dem/physics/ChSystemDem_impl.cpp:863-948): new reference point and
+ * velocity (either may be NULL).  Legal between steps; does not invalidate the step graph. */
+int dem_b200_set_wall_state(dem_b200_system* s, int wall, const double pos[3], const double vel[3]);
+int dem_b200_set_wall_velocity(dem_b200_system* s, int wall, const double pos[3], const double vel[3]); /* alias */
+int dem_b200_enable_wall(dem_b200_system* s, int wall, int enabled); /* DisableBCbyID / EnableBCbyID */
+/* Reaction force on a wall during the last step (GetBCReactionForces, ChSystemDem_impl.cpp:1003-1029). */
+int dem_b200_track_wall_forces(dem_b200_system* s, int enable);
+int dem_b200_wall_force(dem_b200_system* s, int wall, double force[3]);
+
+/* Explicit coefficients of a contact class (DEMB200_MAT_SPHERE = sphere-sphere, _WALL = sphere-wall, _MESH =
+ * sphere-mesh), overriding the composite of the two ChContactMaterialSMC materials.  This is how the per-class setters
+ * of Chrono::Dem map (SetKn_SPH2WALL, SetStaticFrictionCoeff_SPH2MESH, ... src/chrono_dem/physics/ChSystemDem.h:107-160).
+ * c == NULL removes the override. */
+typedef struct dem_b200_contact_class {
+    double E_eff, G_eff;          /* used when use_mat_props */
+    double mu, mu_roll, mu_spin, cr;
+    double adhesion;              /* constant adhesion force */
+    double kn, kt, gn, gt;        /* used when !use_mat_props (Multicore convention) */
+} dem_b200_contact_class;
+int dem_b200_set_contact_class(dem_b200_system* s, int cls, const dem_b200_contact_class* c);
 
 /* ---- run -- ChSystemDem::Initialize / AdvanceSimulation --------------------------------------------------- */
 int dem_b200_initialize(dem_b200_system* s);

@@ -1,0 +1,166 @@
+// =============================================================================
+// chrono::dem::ChSystemDem -- source-compatible mirror of the reference class
+// (src/chrono_dem/physics/ChSystemDem.h:40-393) on top of the B200 engine's C ABI (include/chrono_b200_dem.h).
+// Same method names, argument meaning and order contract (setters -> Initialize -> loop { AdvanceSimulation; getters }).
+// Differences: fp64 user units instead of the int32 simulation-unit lattice; the force law
+// follows Chrono::Multicore's arithmetic (the Dem user coefficients are mapped); particle
+// indices seen through getters/files are always the USER order (the reference re-orders on Initialize,
+// src/chrono_dem/gpu/ChDemSMC.cu:185-194, 434-436); errors throw std::runtime_error instead of exit(1).
+// =============================================================================
+#ifndef CHRONO_B200_CHSYSTEMDEM_H
+#define CHRONO_B200_CHSYSTEMDEM_H
+
+#include <climits>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "chrono/core/ChMatrix33.h"
+#include "chrono/core/ChQuaternion.h"
+#include "chrono/core/ChVector3.h"
+#include "chrono_dem/ChApiDem.h"
+#include "chrono_dem/ChDemDefines.h"
+
+namespace chrono {
+namespace dem {
+
+class ChSystemDem_impl;  // holds the engine handle (dem_b200_system*) and the staged parameters
+
+/// Interface to a Chrono::Dem system.
+class CH_DEM_API ChSystemDem {
+  public:
+    /// Construct system with given sphere radius, density, big domain dimensions and center (ChSystemDem.h:43).
+    ChSystemDem(float sphere_rad, float density, const ChVector3f& boxDims, ChVector3f O = ChVector3f(0));
+    /// Construct system with a checkpoint file (ChSystemDem.h:46).
+    ChSystemDem(const std::string& checkpoint);
+    virtual ~ChSystemDem();
+
+    void SetGravitationalAcceleration(const ChVector3f& g);
+    void SetParticles(const std::vector<ChVector3f>& points,
+                      const std::vector<ChVector3f>& vels = std::vector<ChVector3f>(),
+                      const std::vector<ChVector3f>& ang_vels = std::vector<ChVector3f>());
+    /// Additive API (hard part 5): per-particle radii for polydisperse packings.  Must match SetParticles.
+    void SetParticleRadii(const std::vector<float>& radii);
+    void ReadParticleFile(const std::string& infilename);
+    void ReadContactHistoryFile(const std::string& infilename);
+    void ReadCheckpointFile(const std::string& infilename, bool overwrite = false);
+
+    void SetBDFixed(bool fixed);
+    void SetBDCenter(const ChVector3f& O);
+    void SetParticleFixed(const std::vector<bool>& fixed);
+    void SetParticleOutputMode(CHDEM_OUTPUT_MODE mode);
+    void SetParticleOutputFlags(unsigned int flags);
+    void SetFixedStepSize(float size_UU);
+    float GetFixedStepSize() const;
+    void SetDefragmentOnInitialize(bool defragment);
+    void EnableMinLength(bool useMinLen);
+    void DisableMinLength() { EnableMinLength(false); }
+    void SetTimeIntegrator(CHDEM_TIME_INTEGRATOR new_integrator);
+    void SetFrictionMode(CHDEM_FRICTION_MODE new_mode);
+    void SetRollingMode(CHDEM_ROLLING_MODE new_mode);
+
+    void SetStaticFrictionCoeff_SPH2SPH(float mu);
+    void SetStaticFrictionCoeff_SPH2WALL(float mu);
+    void SetRollingCoeff_SPH2SPH(float mu);
+    void SetRollingCoeff_SPH2WALL(float mu);
+    void SetSpinningCoeff_SPH2SPH(float mu);
+    void SetSpinningCoeff_SPH2WALL(float mu);
+    void SetKn_SPH2SPH(double someValue);
+    void SetKn_SPH2WALL(double someValue);
+    void SetGn_SPH2SPH(double someValue);
+    void SetGn_SPH2WALL(double someValue);
+    void SetKt_SPH2SPH(double someValue);
+    void SetGt_SPH2SPH(double someValue);
+    void SetKt_SPH2WALL(double someValue);
+    void SetGt_SPH2WALL(double someValue);
+    void SetCohesionRatio(float someValue);
+    void SetAdhesionRatio_SPH2WALL(float someValue);
+    void UseMaterialBasedModel(bool val);
+    void SetYoungModulus_SPH(double someValue);
+    void SetYoungModulus_WALL(double someValue);
+    void SetPoissonRatio_SPH(double someValue);
+    void SetPoissonRatio_WALL(double someValue);
+    void SetRestitution_SPH(double someValue);
+    void SetRestitution_WALL(double someValue);
+    void SetMaxSafeVelocity_SU(float max_vel);
+    void SetPsiFactors(unsigned int psi_T, unsigned int psi_L, float psi_R = 1.f);
+    void SetPsiT(unsigned int psi_T);
+    void SetPsiL(unsigned int psi_L);
+    void SetPsiR(float psi_R = 1.f);
+    void SetRecordingContactInfo(bool record);
+    void SetSimTime(float time);
+    void SetVerbosity(CHDEM_VERBOSITY level);
+
+    size_t CreateBCSphere(const ChVector3f& center, float radius, bool outward_normal, bool track_forces, float mass);
+    size_t CreateBCConeZ(const ChVector3f& tip, float slope, float hmax, float hmin, bool outward_normal, bool track_forces);
+    size_t CreateBCPlane(const ChVector3f& pos, const ChVector3f& normal, bool track_forces);
+    size_t CreateCustomizedPlate(const ChVector3f& pos_center, const ChVector3f& normal, float hdim_y);
+    size_t CreateBCCylinderZ(const ChVector3f& center, float radius, bool outward_normal, bool track_forces);
+    bool DisableBCbyID(size_t BC_id);
+    bool EnableBCbyID(size_t BC_id);
+    bool SetBCOffsetFunction(size_t BC_id, const GranPositionFunction& offset_function);
+    void setBDWallsMotionFunction(const GranPositionFunction& pos_fn);
+
+    void SetParticlePosition(int nSphere, const ChVector3d pos);
+    void SetParticleDensity(float density);
+    void SetParticleRadius(float rad);
+    void SetParticleVelocity(int nSphere, const ChVector3d velo);
+
+    float GetSimTime() const;
+    size_t GetNumParticles() const;
+    double GetMaxParticleZ() const;
+    double GetMinParticleZ() const;
+    unsigned int GetNumParticleAboveZ(float ZValue) const;
+    unsigned int GetNumParticleAboveX(float XValue) const;
+    float GetParticleRadius() const;
+    ChVector3f GetParticlePosition(int nSphere) const;
+    ChVector3f GetParticleVelocity(int nSphere) const;
+    ChVector3f GetParticleAngVelocity(int nSphere) const;
+    float GetParticlesKineticEnergy() const;
+    ChVector3f GetBCPlanePosition(size_t plane_id) const;
+    bool IsFixed(int nSphere) const;
+    bool GetBCReactionForces(size_t BC_id, ChVector3f& force) const;
+    unsigned int GetNumContacts() const;
+    unsigned int GetNumSDs() const;
+
+    virtual void Initialize();
+    /// Advance simulation by duration in user units, return actual duration elapsed (round(duration/h) steps,
+    /// src/chrono_dem/gpu/ChDemSMC.cu:623-624).
+    virtual double AdvanceSimulation(float duration);
+
+    void WriteCheckpointFile(const std::string& outfilename);
+    void WriteParticleFile(const std::string& outfilename) const;
+    void WriteContactHistoryFile(const std::string& outfilename) const;
+    size_t EstimateMemUsage() const;
+    float GetRTF() const { return m_RTF; }
+
+    /// Engine handle (dem_b200_system*) for callers that want the C ABI directly (bulk state access, statistics).
+    void* GetEngineHandle() const;
+
+  protected:
+    ChSystemDem() : m_sys(nullptr), m_RTF(0) {}
+    ChSystemDem_impl* m_sys;  ///< underlying system implementation
+
+    void ReadCsvParticles(std::ifstream& ifile, unsigned int totRow = UINT_MAX);
+    void ReadHstHistory(std::ifstream& ifile, unsigned int totItem = UINT_MAX);
+    virtual bool SetParamsFromIdentifier(const std::string& identifier, std::istringstream& iss1, bool overwrite);
+    unsigned int ReadDatParams(std::ifstream& ifile, bool overwrite);
+    void WriteCheckpointParams(std::ofstream& cpFile) const;
+    void WriteCsvParticles(std::ofstream& ptFile) const;
+    void WriteRawParticles(std::ofstream& ptFile) const;
+    void WriteHstHistory(std::ofstream& histFile) const;
+
+    float m_RTF;  // real-time factor
+};
+
+}  // namespace dem
+
+// The module was called Chrono::Gpu before the rename; the checkpoint fixture and the CHANGELOG still use that name
+// (data/testing/dem/pyramid_checkpoint.dat:1, CHANGELOG.md:3584-3704).
+namespace gpu {
+using ChSystemGpu = ::chrono::dem::ChSystemDem;
+}
+}  // namespace chrono
+#endif
