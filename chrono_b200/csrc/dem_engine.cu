@@ -45,6 +45,18 @@ struct dem_b200_system {
     size_t max_pairs = 0;
     bool use_hrel = false;
     bool track_wall_forces = false;
+    // slab decomposition (one process per GPU)
+    bool mgpu = false;
+    bool own_stream = true;
+    size_t mg_cap = 0;                 // capacity (local spheres incl. ghosts)
+    double mg_rmax = 0;                // global largest radius
+    std::vector<uint32_t> h_ids;       // global stable ids of the spheres given to set_spheres
+    unsigned mg_n_own = 0, mg_n_local = 0;
+    unsigned mg_ns[2] = {0, 0};        // owned spheres sent as ghosts to the left / right neighbour
+    unsigned mg_ng[2] = {0, 0};        // ghosts received from the left / right neighbour
+    int mg_phase = 0;                  // 0 idle, 1 extracted, 2 ghosts selected
+    bool mg_remap_pending = false;
+    unsigned* d_count = nullptr;
     double time = 0.0;
     std::string err;
     // scratch (device, by user index) and pinned host staging
@@ -176,6 +188,7 @@ void refresh_params(dem_b200_system* s) {
         WS.has_bb = 1;
     }
     P.track_wall_forces = s->track_wall_forces ? 1 : 0;
+    P.external_rebuild = s->mgpu ? 1 : 0;
     P.shape_base = (unsigned)P.nW;
     // Verlet skin: negative -> default 0.25 * largest radius (set at initialize, when radii are known)
     if (c.verlet_skin >= 0)
@@ -339,7 +352,7 @@ int run_steps(dem_b200_system* s, int nsteps) {
         return DEMB200_EINVAL;
     }
     int done = 0;
-    if (!s->recording && nsteps >= 2) {
+    if (!s->recording && !s->mgpu && nsteps >= 2) {
         if (!s->graph1) {
             int rc = build_graph(s);
             if (rc)
@@ -355,6 +368,16 @@ int run_steps(dem_b200_system* s, int nsteps) {
         int rc = enqueue_step(s, nullptr);
         if (rc)
             return rc;
+        if (s->mg_remap_pending) {
+            // that step sorted the freshly assembled slab: turn pre-sort indices into storage slots for the halo lists
+            const unsigned N = s->P.N;
+            const unsigned m = std::max(std::max(s->mg_ns[0], s->mg_ns[1]), std::max(s->mg_ng[0], s->mg_ng[1]));
+            k_mgpu_invert_perm<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B);
+            if (m)
+                k_mgpu_remap<<<(m + 255) / 256, 256, 0, s->stream>>>(s->B, s->mg_n_own, s->mg_ns[0], s->mg_ns[1], s->mg_ng[0], s->mg_ng[1]);
+            CU(cudaGetLastError());
+            s->mg_remap_pending = false;
+        }
     }
     return 0;
 }
@@ -408,7 +431,7 @@ void dem_b200_destroy(dem_b200_system* s) {
         cudaFree(p);
     if (s->h_pin)
         cudaFreeHost(s->h_pin);
-    if (s->stream)
+    if (s->stream && s->own_stream)
         cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -457,6 +480,7 @@ int dem_b200_set_spheres(dem_b200_system* s, size_t n, const double* pos3, const
     s->h_rad.assign(radius, radius + n);
     if (vel3) s->h_vel.assign(vel3, vel3 + 3 * n); else s->h_vel.assign(3 * n, 0.0);
     if (omega3) s->h_om.assign(omega3, omega3 + 3 * n); else s->h_om.assign(3 * n, 0.0);
+    s->h_ids.clear();
     s->any_fixed = false;
     s->h_fixed.assign(n, 0);
     if (fixed)
@@ -605,8 +629,18 @@ int dem_b200_initialize(dem_b200_system* s) {
     Params& P = s->P;
     Buffers& B = s->B;
     P.N = (unsigned)n;
-    P.Np = (unsigned)((n + 31) / 32 * 32);
+    if (s->mgpu && s->mg_cap < n) {
+        s->err = "mgpu: capacity smaller than the number of spheres";
+        return DEMB200_EINVAL;
+    }
+    P.Np = (unsigned)(((s->mgpu ? s->mg_cap : n) + 31) / 32 * 32);
     P.rmax = *std::max_element(s->h_rad.begin(), s->h_rad.end());
+    if (s->mgpu && s->mg_rmax > P.rmax)
+        P.rmax = s->mg_rmax;
+    if (!s->h_ids.empty() && s->h_ids.size() != n) {
+        s->err = "set_sphere_ids: size differs from set_spheres";
+        return DEMB200_EINVAL;
+    }
     refresh_params(s);
     if (P.bins[0] < 1 || P.bins[1] < 1 || P.bins[2] < 1) {
         s->err = "bad bins_per_axis";
@@ -633,7 +667,7 @@ int dem_b200_initialize(dem_b200_system* s) {
         double cells = 1.0;
         for (int k = 0; k < 3; k++)
             cells *= std::max(1.0, std::floor((mx[k] - mn[k]) / e) + 1.0);
-        cells = std::min(std::max(2.0 * cells, 4096.0), std::max(4096.0, 16.0 * (double)n));
+        cells = std::min(std::max(2.0 * cells, 4096.0), std::max(4096.0, 16.0 * (double)(s->mgpu ? s->mg_cap : n)));
         P.cell_cap = (unsigned)cells;
     }
     s->ntiles = (P.cell_cap + kScanTile - 1) / kScanTile;
@@ -664,10 +698,29 @@ int dem_b200_initialize(dem_b200_system* s) {
     rc |= dev_alloc(s, &B.cell_count, (size_t)P.cell_cap + 8); rc |= dev_alloc(s, &B.cell_start, (size_t)P.cell_cap + 8);
     rc |= dev_alloc(s, &B.block_sums, (size_t)s->ntiles + 8);
     rc |= dev_alloc(s, &B.nl, (size_t)P.Kn * Np); rc |= dev_alloc(s, &B.ncnt, Np);
-    rc |= dev_alloc(s, &s->d_pos3, 3 * n); rc |= dev_alloc(s, &s->d_vel3, 3 * n); rc |= dev_alloc(s, &s->d_om3, 3 * n);
+    rc |= dev_alloc(s, &s->d_pos3, 3 * Np); rc |= dev_alloc(s, &s->d_vel3, 3 * Np); rc |= dev_alloc(s, &s->d_om3, 3 * Np);
     rc |= dev_alloc(s, &s->d_red, 4);
+    if (s->mgpu) {
+        rc |= dev_alloc(s, &B.slab, 1);
+        rc |= dev_alloc(s, &B.inv_perm, Np);
+        rc |= dev_alloc(s, &s->d_count, 4);
+        for (int d = 0; d < 2; d++) {
+            rc |= dev_alloc(s, &B.send_pre[d], Np); rc |= dev_alloc(s, &B.send_slot[d], Np); rc |= dev_alloc(s, &B.ghost_slot[d], Np);
+        }
+        if (hist) {
+            rc |= dev_alloc(s, &B.stage_init, K * Np);
+            rc |= dev_alloc(s, &B.stage_cnt_init, Np);
+            if (s->use_hrel)
+                rc |= dev_alloc(s, &B.stage_rel_init, K * Np);
+        }
+    }
     if (rc)
         return DEMB200_ECUDA;
+    if (s->mgpu) {
+        CU(cudaMemset(B.slab, 0, sizeof(SlabDev)));
+        if (B.stage_cnt_init)
+            CU(cudaMemset(B.stage_cnt_init, 0, Np * sizeof(uint32_t)));
+    }
 
     // history supplied before initialize (checkpoint restart): every sphere taking part in a contact gets a record
     // (keyed by the partner's shape id); the first rebuild moves them into the candidate slots
@@ -696,10 +749,12 @@ int dem_b200_initialize(dem_b200_system* s) {
                 s->err = "add_history: too many rows for one sphere";
                 return DEMB200_EHISTORY;
             }
-        rc |= dev_alloc(s, &B.stage_init, K * Np);
-        rc |= dev_alloc(s, &B.stage_cnt_init, Np);
-        if (s->use_hrel)
-            rc |= dev_alloc(s, &B.stage_rel_init, K * Np);
+        if (!B.stage_init) {
+            rc |= dev_alloc(s, &B.stage_init, K * Np);
+            rc |= dev_alloc(s, &B.stage_cnt_init, Np);
+            if (s->use_hrel)
+                rc |= dev_alloc(s, &B.stage_rel_init, K * Np);
+        }
         if (rc)
             return DEMB200_ECUDA;
     }
@@ -715,7 +770,7 @@ int dem_b200_initialize(dem_b200_system* s) {
                 hv[i].v[k] = s->h_vel[3 * i + k];
                 hv[i].w[k] = s->h_om[3 * i + k];
             }
-            hv[i].sid = (uint32_t)i;
+            hv[i].sid = s->h_ids.empty() ? (uint32_t)i : s->h_ids[i];
             hv[i].meta = s->h_fixed[i] ? 1u : 0u;
             hv[i].amask = 0ull;
         }
@@ -769,6 +824,7 @@ int dem_b200_initialize(dem_b200_system* s) {
     s->h_vel.clear(); s->h_vel.shrink_to_fit();
     s->h_om.clear(); s->h_om.shrink_to_fit();
     s->initialized = true;
+    s->mg_n_own = s->mg_n_local = (unsigned)n;
     rc = recompute_bbox(s);
     if (rc)
         return rc;
@@ -1109,6 +1165,235 @@ int dem_b200_add_history(dem_b200_system* s, uint32_t owner_shape, uint32_t othe
     dem_b200_system::HRow r{owner_shape, other_shape, {disp[0], disp[1], disp[2]}, duration, relvel_init};
     s->h_hist.push_back(r);
     return 0;
+}
+
+// =============================================================================================
+// slab decomposition (one process per GPU): the engine side of the neighbour exchange.  The caller (chrono_b200/slab.py)
+// owns the communication buffers and the transport (torch.distributed: NCCL on GPUs, gloo in the CPU tests).
+// =============================================================================================
+int dem_b200_set_stream(dem_b200_system* s, void* cuda_stream) {
+    if (!s || s->initialized)
+        return DEMB200_EINVAL;
+    if (s->stream && s->own_stream)
+        cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return 0;
+}
+
+int dem_b200_set_sphere_ids(dem_b200_system* s, const uint32_t* ids) {
+    if (!s || !ids || s->initialized || s->h_rad.empty())
+        return DEMB200_EINVAL;
+    s->h_ids.assign(ids, ids + s->h_rad.size());
+    return 0;
+}
+
+int dem_b200_mgpu_enable(dem_b200_system* s, size_t capacity, double rmax_global) {
+    if (!s || s->initialized || capacity == 0 || capacity >= 0xFFFF0000ull)
+        return DEMB200_EINVAL;
+    s->mgpu = true;
+    s->mg_cap = capacity;
+    s->mg_rmax = rmax_global;
+    refresh_params(s);
+    return 0;
+}
+
+int dem_b200_mgpu_sizes(dem_b200_system* s, size_t* halo_bytes, size_t* ghost_bytes, size_t* migrant_bytes, double* cut) {
+    if (!s || !s->mgpu)
+        return DEMB200_EINVAL;
+    if (halo_bytes) *halo_bytes = kHaloDoubles * sizeof(double);
+    if (ghost_bytes) *ghost_bytes = kGhostDoubles * sizeof(double);
+    if (migrant_bytes) *migrant_bytes = (size_t)migrant_doubles(s->P.K) * sizeof(double);
+    if (cut) *cut = 2.0 * s->P.rmax + s->P.skin;
+    return 0;
+}
+
+static int read_slab(dem_b200_system* s, SlabDev* out) {
+    CU(cudaMemcpyAsync(s->h_pin, s->B.slab, sizeof(SlabDev), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(out, s->h_pin, sizeof(SlabDev));
+    return 0;
+}
+
+int dem_b200_mgpu_extract(dem_b200_system* s, double lo, double hi, void* out_left_dev, void* out_right_dev,
+                          size_t cap_records, size_t* n_keep, size_t* n_left, size_t* n_right) {
+    if (!s || !s->initialized || !s->mgpu || s->mg_phase != 0)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemsetAsync(s->B.slab, 0, sizeof(SlabDev), s->stream));
+    const unsigned N = s->P.N;
+    k_mgpu_extract<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, lo, hi, (double*)out_left_dev, (double*)out_right_dev,
+                                                            (unsigned)cap_records);
+    CU(cudaGetLastError());
+    SlabDev sd;
+    int rc = read_slab(s, &sd);
+    if (rc)
+        return rc;
+    if (sd.n_out[0] > cap_records || sd.n_out[1] > cap_records) {
+        s->err = "mgpu_extract: migration buffer too small";
+        return DEMB200_ECAPACITY;
+    }
+    s->mg_n_own = sd.n_keep;
+    s->mg_ng[0] = s->mg_ng[1] = s->mg_ns[0] = s->mg_ns[1] = 0;
+    s->mg_phase = 1;
+    if (n_keep) *n_keep = sd.n_keep;
+    if (n_left) *n_left = sd.n_out[0];
+    if (n_right) *n_right = sd.n_out[1];
+    return check_device_error(s);
+}
+
+int dem_b200_mgpu_append(dem_b200_system* s, const void* in_dev, size_t n, int ghost, int dir) {
+    if (!s || !s->initialized || !s->mgpu || (n && !in_dev) || dir < 0 || dir > 1)
+        return DEMB200_EINVAL;
+    if ((!ghost && s->mg_phase != 1) || (ghost && s->mg_phase != 2)) {
+        s->err = "mgpu_append: migrants go between extract and select_ghosts, ghosts between select_ghosts and finish";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    unsigned base;
+    if (!ghost) {
+        base = s->mg_n_own;
+    } else {
+        if (dir == 0 && s->mg_ng[1] != 0) {
+            s->err = "mgpu_append: append the ghosts of the left neighbour before those of the right one";
+            return DEMB200_EINVAL;
+        }
+        base = s->mg_n_own + s->mg_ng[0] + s->mg_ng[1];
+    }
+    if ((size_t)base + n > s->mg_cap) {
+        s->err = "mgpu_append: local capacity exceeded";
+        return DEMB200_ECAPACITY;
+    }
+    if (n) {
+        k_mgpu_append<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->P, s->B, (const double*)in_dev, (unsigned)n, base, ghost);
+        CU(cudaGetLastError());
+    }
+    if (!ghost)
+        s->mg_n_own += (unsigned)n;
+    else
+        s->mg_ng[dir] += (unsigned)n;
+    return 0;
+}
+
+int dem_b200_mgpu_select_ghosts(dem_b200_system* s, double lo, double hi, double cut, void* out_left_dev, void* out_right_dev,
+                                size_t cap_records, size_t* n_left, size_t* n_right) {
+    if (!s || !s->initialized || !s->mgpu || s->mg_phase != 1)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    if (!(cut >= 0))
+        cut = 2.0 * s->P.rmax + s->P.skin;
+    const unsigned n = s->mg_n_own;
+    if (n) {
+        k_mgpu_select_ghosts<<<(n + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, n, lo, hi, cut, (double*)out_left_dev,
+                                                                      (double*)out_right_dev, (unsigned)cap_records);
+        CU(cudaGetLastError());
+    }
+    SlabDev sd;
+    int rc = read_slab(s, &sd);
+    if (rc)
+        return rc;
+    if (sd.n_gsend[0] > cap_records || sd.n_gsend[1] > cap_records) {
+        s->err = "mgpu_select_ghosts: ghost buffer too small";
+        return DEMB200_ECAPACITY;
+    }
+    s->mg_ns[0] = sd.n_gsend[0];
+    s->mg_ns[1] = sd.n_gsend[1];
+    s->mg_phase = 2;
+    if (n_left) *n_left = sd.n_gsend[0];
+    if (n_right) *n_right = sd.n_gsend[1];
+    return check_device_error(s);
+}
+
+int dem_b200_mgpu_finish_rebuild(dem_b200_system* s) {
+    if (!s || !s->initialized || !s->mgpu || s->mg_phase != 2)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    k_mgpu_finish<<<1, 32, 0, s->stream>>>(s->B);
+    CU(cudaGetLastError());
+    s->mg_n_local = s->mg_n_own + s->mg_ng[0] + s->mg_ng[1];
+    if (s->mg_n_local == 0) {
+        s->err = "mgpu: a slab without spheres is not supported";
+        return DEMB200_EINVAL;
+    }
+    s->P.N = s->mg_n_local;
+    s->mg_phase = 0;
+    s->mg_remap_pending = true;
+    s->export_valid = false;
+    return recompute_bbox(s);
+}
+
+int dem_b200_mgpu_counts(dem_b200_system* s, size_t* n_own, size_t* n_ghost_left, size_t* n_ghost_right, size_t* n_send_left,
+                         size_t* n_send_right) {
+    if (!s || !s->mgpu)
+        return DEMB200_EINVAL;
+    if (n_own) *n_own = s->mg_n_own;
+    if (n_ghost_left) *n_ghost_left = s->mg_ng[0];
+    if (n_ghost_right) *n_ghost_right = s->mg_ng[1];
+    if (n_send_left) *n_send_left = s->mg_ns[0];
+    if (n_send_right) *n_send_right = s->mg_ns[1];
+    return 0;
+}
+
+int dem_b200_mgpu_pack(dem_b200_system* s, int dir, void* out_dev) {
+    if (!s || !s->initialized || !s->mgpu || dir < 0 || dir > 1 || s->mg_remap_pending)
+        return DEMB200_EINVAL;
+    const unsigned n = s->mg_ns[dir];
+    if (n) {
+        k_mgpu_pack<<<(n + 255) / 256, 256, 0, s->stream>>>(s->B, dir, n, (double*)out_dev);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+int dem_b200_mgpu_unpack(dem_b200_system* s, int dir, const void* in_dev) {
+    if (!s || !s->initialized || !s->mgpu || dir < 0 || dir > 1 || s->mg_remap_pending)
+        return DEMB200_EINVAL;
+    const unsigned n = s->mg_ng[dir];
+    if (n) {
+        k_mgpu_unpack<<<(n + 255) / 256, 256, 0, s->stream>>>(s->B, dir, n, (const double*)in_dev);
+        CU(cudaGetLastError());
+        s->export_valid = false;
+    }
+    return 0;
+}
+
+int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev) {
+    if (!s || !s->initialized || !s->mgpu || !flag_dev)
+        return DEMB200_EINVAL;
+    k_mgpu_want<<<1, 32, 0, s->stream>>>(s->P, s->B, flag_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
+                          size_t* n) {
+    if (!s || !s->initialized || !sid || !n)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    if (!s->d_count) {
+        int rc = dev_alloc(s, &s->d_count, 4);
+        if (rc)
+            return rc;
+    }
+    const unsigned N = s->P.N;
+    unsigned* d_sid = reinterpret_cast<unsigned*>(s->B.rank);  // scratch of the rebuild, free between steps
+    CU(cudaMemsetAsync(s->d_count, 0, sizeof(unsigned), s->stream));
+    k_export_owned<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, s->d_count, (unsigned)std::min<size_t>(capacity, N), d_sid,
+                                                            s->d_pos3, s->d_vel3, s->d_om3);
+    CU(cudaGetLastError());
+    s->export_valid = false;
+    CU(cudaMemcpyAsync(s->h_pin, s->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    unsigned c;
+    memcpy(&c, s->h_pin, sizeof(unsigned));
+    *n = c;
+    if (c > capacity)
+        return DEMB200_ECAPACITY;
+    CU(cudaMemcpyAsync(sid, d_sid, c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    if (pos3) CU(cudaMemcpyAsync(pos3, s->d_pos3, 3 * (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (vel3) CU(cudaMemcpyAsync(vel3, s->d_vel3, 3 * (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (omega3) CU(cudaMemcpyAsync(omega3, s->d_om3, 3 * (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return check_device_error(s);
 }
 
 }  // extern "C"

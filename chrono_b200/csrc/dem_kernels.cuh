@@ -183,7 +183,7 @@ __global__ void k_step_begin(Params P, Buffers B) {
     const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
     C.max_dx2 = 0ull;
     C.travel += dx;
-    const bool rebuild = (C.need_rebuild != 0) || !(C.travel < 0.499 * P.skin);
+    const bool rebuild = (C.need_rebuild != 0) || (!P.external_rebuild && !(C.travel < 0.499 * P.skin));
     if (C.nrebuilds >= 1)
         C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
 
@@ -563,6 +563,10 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         return;
     const double4* __restrict__ pos = B.pos[C.f_src];
     const VelRec* vel = B.vel[C.f_src];
+    if (vel[s].meta & FLAG_GHOST) {  // ghosts take part in other spheres' lists only
+        B.ncnt[s] = 0u;
+        return;
+    }
     const double4 me = pos[s];
     const int cx = cell_coord(me.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
     const int cy = cell_coord(me.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
@@ -1135,6 +1139,9 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
     }
     const unsigned sid = mv.sid;
     const unsigned flags = mv.meta & 0xFFu;
+    const bool ghost = (flags & FLAG_GHOST) != 0;
+    if (ghost)
+        cnt = 0;  // a ghost is somebody else's sphere: no forces here, its state arrives with the next halo message
     const unsigned wmask_old = (mv.meta >> 8) & 0xFFFFu;
     const unsigned long long amask_old = mv.amask;
     unsigned wmask_new = 0u;
@@ -1146,7 +1153,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
     double* const rcol = (HIST && B.hrel) ? B.hrel + s : nullptr;
     const V3 mpos = mk(me.x, me.y, me.z);
 
-    if (valid) {
+    if (valid && !ghost) {
         // ---- walls first: body 1 = wall body (lower id), body 2 = this sphere
         double amin[3], amax[3];
         if (wcand)
@@ -1348,7 +1355,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
         }
 
         // ---- time integration ----
-        const bool fixed = (flags & 1u) != 0;
+        const bool fixed = (flags & (FLAG_FIXED | FLAG_GHOST)) != 0;
         const double hdt = P.dt;
         const double inv_m = 1.0 / my_mass;
         const double inv_I = 1.0 / (0.4 * my_mass * me.w * me.w);
@@ -1395,8 +1402,10 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
             atomicOr(&C.err, ERR_NAN);
         B.pos[dst][s] = make_double4(x.x, x.y, x.z, me.w);
         store_vel(B.vel[dst], s, vn, wn, sid, flags | (wmask_new << 8), amask_new);
-        nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
-        nmxx = x.x + me.w; nmxy = x.y + me.w; nmxz = x.z + me.w;
+        if (!ghost) {
+            nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
+            nmxx = x.x + me.w; nmxy = x.y + me.w; nmxz = x.z + me.w;
+        }
         const V3 dxv = x - mpos;
         dx2 = dot(dxv, dxv);
     }
@@ -1410,6 +1419,295 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
         if (e > C.max_dx2)
             atomicMax(&C.max_dx2, e);
     }
+}
+
+// --------------------------------------------------------------------------------------------
+// slab decomposition (one process per GPU).  All kernels below run only at a neighbour-list rebuild, except
+// k_mgpu_pack / k_mgpu_unpack (the per-step halo) and k_mgpu_want.
+// Record layouts (doubles): halo = pos xyz, v xyz, w xyz (9); ghost = pos4, VelRec (12);
+// migrant = pos4, VelRec, acc[6], n_hist, K x (disp xyz, key|steps, relvel0)  (19 + 5 K).
+// --------------------------------------------------------------------------------------------
+constexpr int kHaloDoubles = 9;
+constexpr int kGhostDoubles = 12;
+__host__ __device__ inline int migrant_doubles(int K) { return 19 + 5 * K; }
+
+// warp-aggregated slot allocation: one atomic per warp and counter
+__device__ __forceinline__ unsigned warp_alloc(unsigned* counter, bool take) {
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (m && lane == (unsigned)(__ffs(m) - 1))
+        base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, m ? (__ffs(m) - 1) : 0);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+// live history of old slot `src` -> compact keyed records (same walk as k_gather_sorted)
+template <class Emit>
+__device__ __forceinline__ unsigned walk_history(const Params& P, const Buffers& B, const VelRec* vel_old, unsigned src,
+                                                 unsigned meta, unsigned long long amask, Emit emit) {
+    unsigned cnt = 0;
+    unsigned wmask = (meta >> 8) & 0xFFFFu;
+    while (wmask) {
+        const int w = __ffs(wmask) - 1;
+        wmask &= wmask - 1;
+        const size_t si = (size_t)(P.Kn + w) * P.Np + src;
+        if (cnt < (unsigned)P.K) {
+            double4 r = B.hist[si];
+            r.w = pack_key((unsigned)w, (unsigned)r.w);
+            emit(cnt, r, B.hrel ? B.hrel[si] : 0.0);
+        }
+        cnt++;
+    }
+    while (amask) {
+        const int k = __ffsll((long long)amask) - 1;
+        amask &= amask - 1;
+        const size_t si = (size_t)k * P.Np + src;
+        if (cnt < (unsigned)P.K) {
+            const unsigned jo = B.nl[si];
+            double4 r = B.hist[si];
+            r.w = pack_key(P.shape_base + vel_old[jo].sid, (unsigned)r.w);
+            emit(cnt, r, B.hrel ? B.hrel[si] : 0.0);
+        }
+        cnt++;
+    }
+    return cnt;
+}
+
+// Step 1 of a slab rebuild: drop the ghosts, keep the spheres still inside [lo, hi) (compacted into the OTHER
+// ping-pong buffer together with their staged history), write the ones that left into the migration messages.
+__global__ void __launch_bounds__(256) k_mgpu_extract(Params P, Buffers B, double lo, double hi, double* out_left,
+                                                      double* out_right, unsigned cap_out) {
+    Ctrl& C = *B.ctrl;
+    SlabDev& S = *B.slab;
+    const unsigned a = C.cur, b = a ^ 1u;
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = s < P.N;
+    double4 p = make_double4(0, 0, 0, 1);
+    VelVal r;
+    r.meta = 0; r.sid = 0; r.amask = 0; r.v = mk(0, 0, 0); r.w = mk(0, 0, 0);
+    if (valid) {
+        p = B.pos[a][s];
+        r = load_vel(B.vel[a], s);
+        if (r.meta & FLAG_GHOST)
+            valid = false;
+    }
+    const int dest = !valid ? -1 : (p.x < lo ? 0 : (p.x >= hi ? 1 : 2));
+    const unsigned ik = warp_alloc(&S.n_keep, dest == 2);
+    const unsigned il = warp_alloc(&S.n_out[0], dest == 0);
+    const unsigned ir = warp_alloc(&S.n_out[1], dest == 1);
+    if (dest < 0)
+        return;
+    const unsigned flags = r.meta & 0xFFu;
+    if (dest == 2) {
+        B.pos[b][ik] = p;
+        store_vel(B.vel[b], ik, r.v, r.w, r.sid, flags, 0ull);
+        if (B.acc[0]) {
+            const double2* as = reinterpret_cast<const double2*>(B.acc[a] + 6 * (size_t)s);
+            double2* ad = reinterpret_cast<double2*>(B.acc[b] + 6 * (size_t)ik);
+            ad[0] = as[0]; ad[1] = as[1]; ad[2] = as[2];
+        }
+        unsigned cnt = 0;
+        if (B.hist) {
+            cnt = walk_history(P, B, B.vel[a], s, r.meta, r.amask, [&](unsigned c, double4 h, double rel) {
+                B.stage_init[(size_t)c * P.Np + ik] = h;
+                if (B.stage_rel_init)
+                    B.stage_rel_init[(size_t)c * P.Np + ik] = rel;
+            });
+            if (cnt > (unsigned)P.K) {
+                atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
+                cnt = P.K;
+            }
+            B.stage_cnt_init[ik] = cnt;
+        }
+    } else {
+        const unsigned io = dest == 0 ? il : ir;
+        if (io >= cap_out) {
+            atomicOr(&C.err, ERR_PAIR_CAPACITY);
+            return;
+        }
+        double* o = (dest == 0 ? out_left : out_right) + (size_t)io * migrant_doubles(P.K);
+        o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.w;
+        o[4] = r.v.x; o[5] = r.v.y; o[6] = r.v.z; o[7] = r.w.x; o[8] = r.w.y; o[9] = r.w.z;
+        o[10] = __hiloint2double((int)flags, (int)r.sid);
+        o[11] = 0.0;
+        for (int k = 0; k < 6; k++)
+            o[12 + k] = B.acc[0] ? B.acc[a][6 * (size_t)s + k] : 0.0;
+        unsigned cnt = 0;
+        if (B.hist) {
+            cnt = walk_history(P, B, B.vel[a], s, r.meta, r.amask, [&](unsigned c, double4 h, double rel) {
+                double* q = o + 19 + 5 * c;
+                q[0] = h.x; q[1] = h.y; q[2] = h.z; q[3] = h.w; q[4] = rel;
+            });
+            if (cnt > (unsigned)P.K)
+                cnt = P.K;
+        }
+        o[18] = (double)cnt;
+    }
+}
+
+// Append received records behind the kept spheres (same pre-sort arrays).  ghost != 0: light records, flagged.
+__global__ void __launch_bounds__(256) k_mgpu_append(Params P, Buffers B, const double* in, unsigned n, unsigned base,
+                                                     int ghost) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned b = C.cur ^ 1u;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const unsigned at = base + i;
+    const double* o = in + (size_t)i * (ghost ? kGhostDoubles : migrant_doubles(P.K));
+    B.pos[b][at] = make_double4(o[0], o[1], o[2], o[3]);
+    const unsigned sid = (unsigned)__double2loint(o[10]);
+    unsigned flags = ((unsigned)__double2hiint(o[10])) & 0xFFu;
+    flags = ghost ? (flags | FLAG_GHOST) : (flags & ~FLAG_GHOST);
+    store_vel(B.vel[b], at, mk(o[4], o[5], o[6]), mk(o[7], o[8], o[9]), sid, flags, 0ull);
+    if (ghost) {
+        if (B.acc[0])
+            for (int k = 0; k < 6; k++)
+                B.acc[b][6 * (size_t)at + k] = 0.0;
+        if (B.hist)
+            B.stage_cnt_init[at] = 0;
+        return;
+    }
+    if (B.acc[0])
+        for (int k = 0; k < 6; k++)
+            B.acc[b][6 * (size_t)at + k] = o[12 + k];
+    if (B.hist) {
+        const unsigned cnt = (unsigned)o[18];
+        for (unsigned c = 0; c < cnt && c < (unsigned)P.K; c++) {
+            const double* q = o + 19 + 5 * c;
+            B.stage_init[(size_t)c * P.Np + at] = make_double4(q[0], q[1], q[2], q[3]);
+            if (B.stage_rel_init)
+                B.stage_rel_init[(size_t)c * P.Np + at] = q[4];
+        }
+        B.stage_cnt_init[at] = cnt;
+    }
+}
+
+// Owned spheres (pre-sort indices [0, n_own)) within `cut` of a slab face: their copies go to that neighbour.
+__global__ void __launch_bounds__(256) k_mgpu_select_ghosts(Params P, Buffers B, unsigned n_own, double lo, double hi,
+                                                            double cut, double* out_left, double* out_right,
+                                                            unsigned cap_out) {
+    Ctrl& C = *B.ctrl;
+    SlabDev& S = *B.slab;
+    const unsigned b = C.cur ^ 1u;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n_own;
+    double4 p = make_double4(0, 0, 0, 1);
+    if (valid)
+        p = B.pos[b][i];
+    const bool tl = valid && (p.x < lo + cut), tr = valid && (p.x >= hi - cut);
+    const unsigned il = warp_alloc(&S.n_gsend[0], tl);
+    const unsigned ir = warp_alloc(&S.n_gsend[1], tr);
+    if (!tl && !tr)
+        return;
+    const VelVal r = load_vel(B.vel[b], i);
+    for (int d = 0; d < 2; d++) {
+        if (!(d == 0 ? tl : tr))
+            continue;
+        const unsigned io = d == 0 ? il : ir;
+        if (io >= cap_out) {
+            atomicOr(&C.err, ERR_PAIR_CAPACITY);
+            continue;
+        }
+        B.send_pre[d][io] = i;
+        double* o = (d == 0 ? out_left : out_right) + (size_t)io * kGhostDoubles;
+        o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.w;
+        o[4] = r.v.x; o[5] = r.v.y; o[6] = r.v.z; o[7] = r.w.x; o[8] = r.w.y; o[9] = r.w.z;
+        o[10] = __hiloint2double((int)(r.meta & 0xFFu), (int)r.sid);
+        o[11] = 0.0;
+    }
+}
+
+// Last step of a slab rebuild: the assembled pre-sort arrays become the live buffer; the next step sorts them and
+// rebuilds the candidate lists, taking the history from the staging columns.
+__global__ void k_mgpu_finish(Buffers B) {
+    if (threadIdx.x || blockIdx.x)
+        return;
+    Ctrl& C = *B.ctrl;
+    C.cur ^= 1u;
+    C.need_rebuild = 1u;
+    C.init_stage = 1u;
+    C.nrebuilds = 0ull;  // k_step_begin clears init_stage once nrebuilds >= 1: restart that latch
+    C.travel = 0.0;
+    C.max_dx2 = 0ull;
+    SlabDev& S = *B.slab;
+    S.n_keep = S.n_out[0] = S.n_out[1] = S.n_gsend[0] = S.n_gsend[1] = 0u;
+    S.want_rebuild = 0u;
+}
+
+// After the sorting step: pre-sort indices -> storage slots for the per-step halo lists.
+__global__ void __launch_bounds__(256) k_mgpu_invert_perm(Params P, Buffers B) {
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.N)
+        B.inv_perm[B.perm[s]] = s;
+}
+__global__ void __launch_bounds__(256) k_mgpu_remap(Buffers B, unsigned n_own, unsigned ns0, unsigned ns1, unsigned ng0,
+                                                    unsigned ng1) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ns0) B.send_slot[0][i] = B.inv_perm[B.send_pre[0][i]];
+    if (i < ns1) B.send_slot[1][i] = B.inv_perm[B.send_pre[1][i]];
+    if (i < ng0) B.ghost_slot[0][i] = B.inv_perm[n_own + i];
+    if (i < ng1) B.ghost_slot[1][i] = B.inv_perm[n_own + ng0 + i];
+}
+
+// per-step halo: current state of the ghost-senders -> message; message -> ghost slots of the live buffer
+__global__ void __launch_bounds__(256) k_mgpu_pack(Buffers B, int dir, unsigned n, double* out) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const unsigned s = B.send_slot[dir][i];
+    const double4 p = B.pos[C.cur][s];
+    const VelVal r = load_vel(B.vel[C.cur], s);
+    double* o = out + (size_t)i * kHaloDoubles;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z;
+    o[3] = r.v.x; o[4] = r.v.y; o[5] = r.v.z; o[6] = r.w.x; o[7] = r.w.y; o[8] = r.w.z;
+}
+__global__ void __launch_bounds__(256) k_mgpu_unpack(Buffers B, int dir, unsigned n, const double* in) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const unsigned s = B.ghost_slot[dir][i];
+    const double* o = in + (size_t)i * kHaloDoubles;
+    double4 p = B.pos[C.cur][s];
+    p.x = o[0]; p.y = o[1]; p.z = o[2];
+    B.pos[C.cur][s] = p;
+    double2* q = reinterpret_cast<double2*>(B.vel[C.cur] + s);
+    q[0] = make_double2(o[3], o[4]);
+    q[1] = make_double2(o[5], o[6]);
+    q[2] = make_double2(o[7], o[8]);
+}
+// Would the next step have to rebuild?  (travel so far + the displacement of the step that just ran)
+__global__ void k_mgpu_want(Params P, Buffers B, int* flag_out) {
+    if (threadIdx.x || blockIdx.x)
+        return;
+    const Ctrl& C = *B.ctrl;
+    const double t = C.travel + sqrt(__longlong_as_double((long long)C.max_dx2));
+    *flag_out = (C.need_rebuild != 0 || !(t < 0.499 * P.skin)) ? 1 : 0;
+}
+// compact export of the owned spheres (any order): sid, pos, vel, omega
+__global__ void __launch_bounds__(256) k_export_owned(Params P, Buffers B, unsigned* count, unsigned cap, unsigned* sid,
+                                                      double* pos3, double* vel3, double* om3) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool own = false;
+    double4 p = make_double4(0, 0, 0, 0);
+    VelVal r;
+    r.meta = 0; r.sid = 0; r.amask = 0; r.v = mk(0, 0, 0); r.w = mk(0, 0, 0);
+    if (i < P.N) {
+        p = B.pos[C.cur][i];
+        r = load_vel(B.vel[C.cur], i);
+        own = !(r.meta & FLAG_GHOST);
+    }
+    const unsigned at = warp_alloc(count, own);
+    if (!own || at >= cap)
+        return;
+    sid[at] = r.sid;
+    if (pos3) { pos3[3 * (size_t)at] = p.x; pos3[3 * (size_t)at + 1] = p.y; pos3[3 * (size_t)at + 2] = p.z; }
+    if (vel3) { vel3[3 * (size_t)at] = r.v.x; vel3[3 * (size_t)at + 1] = r.v.y; vel3[3 * (size_t)at + 2] = r.v.z; }
+    if (om3) { om3[3 * (size_t)at] = r.w.x; om3[3 * (size_t)at + 1] = r.w.y; om3[3 * (size_t)at + 2] = r.w.z; }
 }
 
 // --------------------------------------------------------------------------------------------

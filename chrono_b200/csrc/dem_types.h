@@ -81,9 +81,13 @@ struct Params {
     double skin;          // Verlet skin: candidates are spheres closer than r_i + r_j + skin at rebuild time
     unsigned cell_cap;    // capacity of the search-cell arrays
     int track_wall_forces;  // accumulate the reaction force on every wall (GetBCReactionForces)
+    int external_rebuild;   // slab mode: rebuilds happen only when the host asks (all ranks at the same step)
 };
 
-// 64-byte velocity record.  meta = flags (bits 0-7: 1 = fixed) | live wall-contact mask (bits 8-23);
+constexpr unsigned FLAG_FIXED = 1u;
+constexpr unsigned FLAG_GHOST = 2u;  // copy of a sphere owned by a neighbouring slab (multi-GPU): never integrated here
+
+// 64-byte velocity record.  meta = flags (bits 0-7: 1 = fixed, 2 = ghost) | live wall-contact mask (bits 8-23);
 // amask bit k = the contact with candidate k of the sphere's Verlet list carried force last step (history live).
 struct __align__(16) VelRec {
     double v[3];
@@ -121,9 +125,22 @@ struct Ctrl {
     double wall_force[kMaxWalls][3];  // force exerted by the spheres on wall w during the last step
 };
 
+// Slab decomposition (one process per GPU): counters and index lists of the neighbour exchange.
+struct SlabDev {
+    unsigned n_keep;        // owned spheres that stay (extract)
+    unsigned n_out[2];      // spheres leaving to the left / right neighbour
+    unsigned n_gsend[2];    // owned spheres whose copies the left / right neighbour needs as ghosts
+    unsigned want_rebuild;  // this rank's Verlet skin is (about to be) used up
+};
+
 struct Buffers {
     Ctrl* ctrl;
     WallSet* walls;
+    SlabDev* slab;
+    uint32_t* send_pre[2];   // pre-sort index of every ghost-sender, in message order
+    uint32_t* send_slot[2];  // its storage slot after the sort (per-step pack list)
+    uint32_t* ghost_slot[2]; // storage slot of the i-th ghost received from the left / right neighbour
+    uint32_t* inv_perm;      // scratch: pre-sort index -> storage slot
     // state, ping-pong
     double4* pos[2];
     VelRec* vel[2];

@@ -1,0 +1,231 @@
+"""Slab domain decomposition of the DEM step: one process per GPU, torch.distributed for the plumbing.
+
+No reference counterpart exists (Chrono::Dem is single-GPU; the MPI module Chrono::Distributed was removed,
+CHANGELOG.md:496-501); the design follows SURVEY.md 8(e):
+
+* 1-D slabs along x with boundaries fixed at start-up (equal sphere counts);
+* every rank keeps its owned spheres plus ghosts = copies of the neighbours' spheres within 2 r_max + skin of the face;
+* between neighbour-list rebuilds the ghost SET is frozen: the per-step halo is a fixed-index pack -> send/recv -> unpack
+  of (pos, v, omega), 72 bytes per ghost, no sizes exchanged;
+* spheres change owner only at a rebuild and take their contact history with them; no force or history exchange, because
+  both partners of a contact keep (bit-identical) copies of it;
+* all ranks rebuild at the same step: a 4-byte MAX all-reduce of "my Verlet skin is used up" per step.
+
+`SlabDriver` is the protocol; it talks to a backend object (the CUDA engine through its C ABI: `EngineBackend`; the CPU
+tests plug an oracle-based backend in, tests/test_slab_gloo.py) and to torch.distributed (NCCL on GPUs, gloo on CPU).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(x_all, world):
+    """Slab faces with equal sphere counts: world+1 values, first -inf, last +inf.  x_all: every sphere's x."""
+    xs = np.sort(np.asarray(x_all, dtype=np.float64))
+    cuts = [-np.inf]
+    for r in range(1, world):
+        k = (len(xs) * r) // world
+        cuts.append(0.5 * (xs[k - 1] + xs[k]) if 0 < k < len(xs) else xs[min(k, len(xs) - 1)])
+    cuts.append(np.inf)
+    return np.array(cuts)
+
+
+class SlabDriver:
+    def __init__(self, backend, rank, world, lo, hi, group=None):
+        self.b, self.rank, self.world, self.lo, self.hi, self.group = backend, rank, world, float(lo), float(hi), group
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
+        self.stats = dict(steps=0, rebuilds=0, halo_bytes=0, migrated=0, ghost_bytes=0)
+        self.fresh = False  # the ghosts were just exchanged by a rebuild: no halo needed before the next step
+
+    # ---- transport -------------------------------------------------------------------------------------------------
+    def _exchange(self, to_left, to_right, width):
+        """Send variable-length record arrays to both neighbours, receive theirs.  Returns (from_left, from_right)."""
+        dev = self.b.device
+        counts_out = torch.tensor([0 if to_left is None else to_left.shape[0], 0 if to_right is None else to_right.shape[0]],
+                                  dtype=torch.int64, device=dev)
+        cl, cr = torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
+        ops = []
+        if self.left is not None:
+            ops += [dist.P2POp(dist.isend, counts_out[0:1], self.left, self.group), dist.P2POp(dist.irecv, cl, self.left, self.group)]
+        if self.right is not None:
+            ops += [dist.P2POp(dist.isend, counts_out[1:2], self.right, self.group), dist.P2POp(dist.irecv, cr, self.right, self.group)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        nl, nr = int(cl.item()), int(cr.item())
+        from_left = torch.empty((nl, width), dtype=torch.float64, device=dev)
+        from_right = torch.empty((nr, width), dtype=torch.float64, device=dev)
+        ops = []
+        if self.left is not None:
+            if to_left is not None and to_left.shape[0]:
+                ops.append(dist.P2POp(dist.isend, to_left.contiguous(), self.left, self.group))
+            if nl:
+                ops.append(dist.P2POp(dist.irecv, from_left, self.left, self.group))
+        if self.right is not None:
+            if to_right is not None and to_right.shape[0]:
+                ops.append(dist.P2POp(dist.isend, to_right.contiguous(), self.right, self.group))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, from_right, self.right, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return from_left, from_right
+
+    # ---- rebuild: migration, new ghost set ---------------------------------------------------------------------------
+    def rebuild(self):
+        b = self.b
+        n_keep, out_l, out_r = b.extract(self.lo, self.hi)
+        if self.left is None and out_l.shape[0] or self.right is None and out_r.shape[0]:
+            raise RuntimeError("a sphere left the outermost slab (bounds must be infinite there)")
+        in_l, in_r = self._exchange(out_l, out_r, b.migrant_doubles)
+        b.append(in_l, ghost=False, direction=0)
+        b.append(in_r, ghost=False, direction=1)
+        self.stats["migrated"] += int(out_l.shape[0] + out_r.shape[0])
+        g_l, g_r = b.select_ghosts(self.lo, self.hi)
+        if self.left is None:
+            g_l = g_l[:0]
+        if self.right is None:
+            g_r = g_r[:0]
+        gin_l, gin_r = self._exchange(g_l, g_r, b.ghost_doubles)
+        self.stats["ghost_bytes"] += int((gin_l.numel() + gin_r.numel()) * 8)
+        b.append(gin_l, ghost=True, direction=0)
+        b.append(gin_r, ghost=True, direction=1)
+        b.finish_rebuild()
+        self.n_recv = (int(gin_l.shape[0]), int(gin_r.shape[0]))
+        self.n_send = (int(g_l.shape[0]), int(g_r.shape[0]))
+        self.stats["rebuilds"] += 1
+        self.fresh = True
+
+    # ---- per-step halo -------------------------------------------------------------------------------------------------
+    def halo(self):
+        b = self.b
+        send = [b.pack(0) if self.left is not None else None, b.pack(1) if self.right is not None else None]
+        recv = [b.halo_buffer(0, self.n_recv[0]), b.halo_buffer(1, self.n_recv[1])]
+        ops = []
+        for d, peer in ((0, self.left), (1, self.right)):
+            if peer is None:
+                continue
+            if self.n_send[d]:
+                ops.append(dist.P2POp(dist.isend, send[d], peer, self.group))
+            if self.n_recv[d]:
+                ops.append(dist.P2POp(dist.irecv, recv[d], peer, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for d in (0, 1):
+            if self.n_recv[d]:
+                b.unpack(d, recv[d])
+        self.stats["halo_bytes"] += int((self.n_recv[0] + self.n_recv[1]) * b.halo_doubles * 8)
+
+    def step(self, nsteps=1):
+        for _ in range(nsteps):
+            if not self.fresh:
+                self.halo()
+            self.fresh = False
+            self.b.step()
+            flag = self.b.want_rebuild()  # 1-element int32 tensor on the backend's device
+            if self.world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            self.stats["steps"] += 1
+            if int(flag.item()):
+                self.rebuild()
+
+
+class EngineBackend:
+    """The CUDA engine (libchrono_b200_dem.so) as a slab backend.  Communication buffers are torch tensors whose device
+    pointers are handed to the C ABI; the engine runs on torch's current stream so that NCCL and the kernels are ordered."""
+
+    def __init__(self, system, capacity, max_records=None):
+        from . import dem
+        self.g = system
+        self.L = system.L
+        self.h = system.h
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        hb, gb, mb, cut = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_double(0)
+        system._ck(self.L.dem_b200_mgpu_sizes(self.h, C.byref(hb), C.byref(gb), C.byref(mb), C.byref(cut)))
+        self.halo_doubles, self.ghost_doubles, self.migrant_doubles = hb.value // 8, gb.value // 8, mb.value // 8
+        self.cut = cut.value
+        self.capacity = capacity
+        self.max_records = max_records or max(1024, capacity // 4)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.mig = [torch.empty((max(1024, self.max_records // 16), self.migrant_doubles), **f64) for _ in range(2)]
+        self.gho = [torch.empty((self.max_records, self.ghost_doubles), **f64) for _ in range(2)]
+        self.hsend = [torch.empty((self.max_records, self.halo_doubles), **f64) for _ in range(2)]
+        self.hrecv = [torch.empty((self.max_records, self.halo_doubles), **f64) for _ in range(2)]
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.n_send = [0, 0]
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr())
+
+    def extract(self, lo, hi):
+        nk, nl, nr = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self.g._ck(self.L.dem_b200_mgpu_extract(self.h, C.c_double(lo), C.c_double(hi), self._p(self.mig[0]), self._p(self.mig[1]),
+                                                C.c_size_t(self.mig[0].shape[0]), C.byref(nk), C.byref(nl), C.byref(nr)))
+        return nk.value, self.mig[0][:nl.value], self.mig[1][:nr.value]
+
+    def append(self, buf, ghost, direction):
+        n = int(buf.shape[0])
+        self.g._ck(self.L.dem_b200_mgpu_append(self.h, self._p(buf) if n else None, C.c_size_t(n), int(ghost), int(direction)))
+
+    def select_ghosts(self, lo, hi):
+        nl, nr = C.c_size_t(0), C.c_size_t(0)
+        self.g._ck(self.L.dem_b200_mgpu_select_ghosts(self.h, C.c_double(lo), C.c_double(hi), C.c_double(-1.0), self._p(self.gho[0]),
+                                                      self._p(self.gho[1]), C.c_size_t(self.max_records), C.byref(nl), C.byref(nr)))
+        self.n_send = [nl.value, nr.value]
+        return self.gho[0][:nl.value], self.gho[1][:nr.value]
+
+    def finish_rebuild(self):
+        self.g._ck(self.L.dem_b200_mgpu_finish_rebuild(self.h))
+
+    def pack(self, d):
+        self.g._ck(self.L.dem_b200_mgpu_pack(self.h, d, self._p(self.hsend[d])))
+        return self.hsend[d][:self.n_send[d]]
+
+    def halo_buffer(self, d, n):
+        return self.hrecv[d][:n]
+
+    def unpack(self, d, buf):
+        self.g._ck(self.L.dem_b200_mgpu_unpack(self.h, d, self._p(buf)))
+
+    def step(self):
+        self.g._ck(self.L.dem_b200_step(self.h, 1))
+
+    def want_rebuild(self):
+        self.g._ck(self.L.dem_b200_mgpu_want_rebuild(self.h, C.c_void_p(self.flag.data_ptr())))
+        return self.flag
+
+    def export_owned(self):
+        cap = self.capacity
+        sid = np.empty(cap, dtype=np.uint32)
+        pos, vel, om = np.empty((cap, 3)), np.empty((cap, 3)), np.empty((cap, 3))
+        n = C.c_size_t(0)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self.g._ck(self.L.dem_b200_export_owned(self.h, sid.ctypes.data_as(C.POINTER(C.c_uint32)), dp(pos), dp(vel), dp(om),
+                                                C.c_size_t(cap), C.byref(n)))
+        k = n.value
+        return sid[:k], pos[:k], vel[:k], om[:k]
+
+
+def make_engine_slab(cfg, scene_walls, pos, radius, ids, vel=None, omega=None, capacity=None, rmax_global=None, add_walls=None):
+    """Create a slab-mode engine for the given owned spheres (global ids `ids`) on the current CUDA device/stream."""
+    from . import dem
+    g = dem.DemSystem(cfg)
+    L = g.L
+    g._ck(L.dem_b200_set_stream(g.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    for p, h in scene_walls:
+        g.add_box_wall(p, h)
+    if add_walls:
+        add_walls(g)
+    n = len(ids)
+    capacity = capacity or int(1.5 * n + 4096)
+    g.set_spheres(pos, radius, vel=vel, omega=omega)
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    g._ck(L.dem_b200_set_sphere_ids(g.h, ids.ctypes.data_as(C.POINTER(C.c_uint32))))
+    g._ck(L.dem_b200_mgpu_enable(g.h, C.c_size_t(capacity), C.c_double(rmax_global if rmax_global is not None else float(np.max(radius)))))
+    g.initialize()
+    return g, EngineBackend(g, capacity)

@@ -169,6 +169,34 @@ int dem_b200_num_walls(const dem_b200_system* s);
 int dem_b200_get_stats(dem_b200_system* s, unsigned long long* nsteps, unsigned long long* nrebuilds,
                        unsigned long long* contacts_last_step);
 
+/* ---- slab decomposition: one process per GPU (no reference counterpart: Chrono::Dem is single-GPU and the
+ * MPI module Chrono::Distributed was removed, CHANGELOG.md:496-501) --------------------------------------------------
+ * The engine keeps owned spheres and ghosts (copies of the neighbour slabs' spheres within 2 r_max + skin of the
+ * face) in one array; ghosts are never integrated.  Between neighbour-list rebuilds the halo is a fixed-index
+ * pack -> send/recv -> unpack of (pos, v, omega); spheres change owner only at a rebuild, together with their contact
+ * history.  No force or history exchange: both partners of a contact keep their own copy.  The caller owns the device
+ * buffers and the transport (chrono_b200/slab.py: torch.distributed, NCCL).  Call order of a rebuild:
+ *   extract -> [exchange migrants] -> append(ghost=0) x2 -> select_ghosts -> [exchange ghosts] -> append(ghost=1, dir 0)
+ *   -> append(ghost=1, dir 1) -> finish_rebuild -> step ... ; per step: pack x2 -> [exchange] -> unpack x2 -> step. */
+int dem_b200_set_stream(dem_b200_system* s, void* cuda_stream);              /* before initialize: run on the caller's stream */
+int dem_b200_set_sphere_ids(dem_b200_system* s, const uint32_t* ids);       /* global stable ids of the spheres of set_spheres */
+int dem_b200_mgpu_enable(dem_b200_system* s, size_t capacity, double rmax_global); /* before initialize */
+int dem_b200_mgpu_sizes(dem_b200_system* s, size_t* halo_bytes, size_t* ghost_bytes, size_t* migrant_bytes, double* cut);
+int dem_b200_mgpu_extract(dem_b200_system* s, double lo, double hi, void* out_left_dev, void* out_right_dev,
+                          size_t cap_records, size_t* n_keep, size_t* n_left, size_t* n_right);
+int dem_b200_mgpu_append(dem_b200_system* s, const void* in_dev, size_t n, int ghost, int dir);
+int dem_b200_mgpu_select_ghosts(dem_b200_system* s, double lo, double hi, double cut, void* out_left_dev, void* out_right_dev,
+                                size_t cap_records, size_t* n_left, size_t* n_right);
+int dem_b200_mgpu_finish_rebuild(dem_b200_system* s);
+int dem_b200_mgpu_counts(dem_b200_system* s, size_t* n_own, size_t* n_ghost_left, size_t* n_ghost_right, size_t* n_send_left,
+                         size_t* n_send_right);
+int dem_b200_mgpu_pack(dem_b200_system* s, int dir, void* out_dev);
+int dem_b200_mgpu_unpack(dem_b200_system* s, int dir, const void* in_dev);
+int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev); /* writes 1/0 to DEVICE memory (for an all-reduce) */
+/* owned spheres (ghosts excluded) in arbitrary order: global id, pos, vel, omega to HOST buffers */
+int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
+                          size_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,11 +37,11 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None
 
 
 def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
-             integrator=None, history_slots=16, **model):
+             integrator=None, history_slots=16, device=0, **model):
     from chrono_b200 import dem
     mat = mat or settling_material()
     kw = dict(model)
-    cfg = dem.config(dt=dt, bins=scene["bins"], gravity=gravity, mat_sphere=dem.material(**mat),
+    cfg = dem.config(device=device, dt=dt, bins=scene["bins"], gravity=gravity, mat_sphere=dem.material(**mat),
                      mat_wall=dem.material(**(wall_mat or mat)), mass_coef=MASS_COEF, wall_mass=wall_mass,
                      integrator=dem.CENTERED_DIFFERENCE if integrator is None else integrator,
                      history_slots=history_slots, **kw)

@@ -225,3 +225,17 @@ def test_history_overflow_is_reported():
     with pytest.raises(dem.DemError) as e:
         g.step(1)
     assert e.value.code == -4
+
+
+def test_slab_decomposition_two_gpus_bit_identical():
+    """2-rank slab run (NCCL halo exchange, migration with history) == single-GPU run, bit for bit (tests/mgpu_check.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(here, "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
