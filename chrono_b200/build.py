@@ -8,7 +8,8 @@ LIB_PATH = os.environ.get("DEMB200_LIB") or os.path.join(HERE, "libchrono_b200_d
 SOURCES = [os.path.join(HERE, "csrc", "dem_engine.cu"), os.path.join(HERE, "csrc", "ChSystemDem.cpp")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("dem_kernels.cuh", "dem_types.h")] + [
     os.path.join(ROOT, "include", "chrono_b200_dem.h"), os.path.join(ROOT, "include", "chrono_dem", "physics", "ChSystemDem.h"),
-    os.path.join(ROOT, "include", "chrono_dem", "ChDemDefines.h")]
+    os.path.join(ROOT, "include", "chrono_dem", "ChDemDefines.h"),
+    os.path.join(ROOT, "include", "chrono", "geometry", "ChTriangleMeshConnected.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-I", os.path.join(ROOT, "include"), "-Xcompiler", "-fPIC", "-shared"]
 

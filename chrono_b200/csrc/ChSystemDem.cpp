@@ -76,6 +76,21 @@ class ChSystemDem_impl {
     std::vector<HistRow> hist;  // staged contact history (checkpoint): sphere index, partner sphere index or BC id
     std::vector<BCInfo> bcs;
     bool any_offset = false;
+    // triangle meshes staged by ChSystemDemMesh (uploaded at Initialize, before the spheres: their triangles take the
+    // shape ids between the walls and the spheres)
+    struct MeshStage {
+        std::vector<double> verts9;  // 9 doubles per triangle, mesh frame
+        double mass = 1.0;
+        bool has_motion = false;
+        double pos[3] = {0, 0, 0}, rot[4] = {1, 0, 0, 0}, lin[3] = {0, 0, 0}, ang[3] = {0, 0, 0};
+    };
+    std::vector<MeshStage> meshes;
+    bool mesh_collision = true;
+    uint32_t num_triangles() const {
+        size_t t = 0;
+        for (auto& m : meshes) t += m.verts9.size() / 9;
+        return (uint32_t)t;
+    }
 
     size_t n() const { return rad.empty() ? pos.size() / 3 : rad.size(); }
 
@@ -360,15 +375,31 @@ void ChSystemDem::Initialize() {
         dem_b200_contact_class cc = S.make_class(k);
         S.check(dem_b200_set_contact_class(S.h, k, &cc), "set_contact_class");
     }
+    for (size_t m = 0; m < S.meshes.size(); m++) {
+        auto& M = S.meshes[m];
+        const int id = dem_b200_add_mesh(S.h, M.verts9.size() / 9, M.verts9.data(), M.mass);
+        S.check(id, "AddMesh");
+        if (M.has_motion)
+            S.check(dem_b200_set_mesh_motion(S.h, id, M.pos, M.rot, M.lin, M.ang), "ApplyMeshMotion");
+    }
+    if (!S.meshes.empty() && !S.mesh_collision)
+        S.check(dem_b200_enable_mesh_collision(S.h, 0), "EnableMeshCollision");
     S.check(dem_b200_set_spheres(S.h, n, S.pos.data(), S.vel.data(), S.omg.data(), S.rad.data(), S.fixed.data()),
             "SetParticles");
     {
-        // engine shape ids: wall w is shape w (walls are added in BC-id order), sphere i is shape nW + i
+        // engine shape ids: wall w is shape w (walls are added in BC-id order), then the mesh triangles, then sphere i
+        // is shape nW + nT + i
         const uint32_t nW = (uint32_t)S.bcs.size();
+        const uint32_t base = nW + S.num_triangles();
         for (auto& r : S.hist) {
-            if (r.is_bc && r.partner >= nW)
+            if (r.is_bc && r.partner >= nW) {
+                // label nSpheres + 1 + nBCs + 1 + family: a mesh-family record (ChDemSMCtrimesh.cu:728) cannot be
+                // attached to one facet; the contact restarts with an empty history
+                if (!S.meshes.empty() && r.partner > nW)
+                    continue;
                 fail("contact history refers to a boundary condition that was not created before Initialize");
-            S.check(dem_b200_add_history(S.h, nW + r.sphere, r.is_bc ? r.partner : nW + r.partner, r.d, 0.0, 0.0),
+            }
+            S.check(dem_b200_add_history(S.h, base + r.sphere, r.is_bc ? r.partner : base + r.partner, r.d, 0.0, 0.0),
                     "ReadContactHistory");
         }
     }
@@ -634,16 +665,28 @@ void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
         if (m)
             S.check(dem_b200_get_history(S.h, owner.data(), other.data(), d.data(), nullptr, nullptr, m, &m), "WriteHstHistory");
         const uint32_t nW = (uint32_t)dem_b200_num_walls(S.h);
+        const uint32_t base = nW + (uint32_t)dem_b200_num_triangles(S.h);
         for (size_t c = 0; c < m; c++) {
-            const uint32_t so = owner[c] - nW;  // owner = higher shape id = body 2 of the canonical orientation
+            const uint32_t so = owner[c] - base;  // owner = higher shape id = body 2 of the canonical orientation
             std::array<float, 3> hv = {(float)-d[3 * c], (float)-d[3 * c + 1], (float)-d[3 * c + 2]};
             if (other[c] < nW) {  // wall: label by BC id
                 size_t bc = 0;
                 for (; bc < S.bcs.size(); bc++)
                     if (S.bcs[bc].wall == (int)other[c]) break;
                 rows[so].push_back({(uint32_t)(n + bc + 1), hv});
+            } else if (other[c] < base) {
+                // mesh facet: the reference keeps one record per (sphere, mesh family), labelled
+                // nSpheres + 1 + nBCs + 1 + family (ChDemSMCtrimesh.cu:728); write the first facet's record of a family
+                uint32_t tri = other[c] - nW, fam = 0;
+                for (; fam < S.meshes.size() && tri >= S.meshes[fam].verts9.size() / 9; fam++)
+                    tri -= (uint32_t)(S.meshes[fam].verts9.size() / 9);
+                const uint32_t label = (uint32_t)(n + 1 + S.bcs.size() + 1 + fam);
+                bool seen = false;
+                for (auto& r : rows[so]) seen |= (r.first == label);
+                if (!seen)
+                    rows[so].push_back({label, hv});
             } else {
-                const uint32_t sp = other[c] - nW;
+                const uint32_t sp = other[c] - base;
                 rows[so].push_back({sp, hv});
                 rows[sp].push_back({so, {-hv[0], -hv[1], -hv[2]}});
             }
@@ -878,6 +921,284 @@ void ChSystemDem::ReadCheckpointFile(const std::string& infilename, bool overwri
     if (m_sys->n() != n)
         fail("checkpoint: nSpheres does not match the particle block");
     m_sys->defragment = false;  // ids stay stable (ChSystemDem.cpp:785-786); ours always are
+}
+
+// =====================================================================================================================
+// ChSystemDemMesh (reference: src/chrono_dem/physics/ChSystemDem.cpp:470-655, 1274-1301, 1510-1766)
+// =====================================================================================================================
+ChSystemDemMesh::ChSystemDemMesh(float sphere_rad, float density, const ChVector3f& boxDims, ChVector3f O)
+    : ChSystemDem(sphere_rad, density, boxDims, O) {}
+
+ChSystemDemMesh::ChSystemDemMesh(const std::string& checkpoint) : ChSystemDem() {
+    m_sys = new ChSystemDem_impl();
+    m_sys->bcs.resize(NUM_RESERVED_BC_IDS);
+    ReadCheckpointFile(checkpoint, true);
+}
+
+ChSystemDemMesh::~ChSystemDemMesh() {}
+
+unsigned int ChSystemDemMesh::AddMesh(std::shared_ptr<ChTriangleMeshConnected> mesh, float mass) {
+    if (m_sys->initialized)
+        fail("AddMesh must be called before Initialize");
+    if (!mesh)
+        fail("AddMesh: null mesh");
+    const unsigned int id = (unsigned int)m_meshes.size();
+    m_meshes.push_back(mesh);
+    m_mesh_masses.push_back(mass);
+    return id;
+}
+
+unsigned int ChSystemDemMesh::AddMesh(const std::string& filename, const ChVector3f& translation,
+                                      const ChMatrix33<float>& rotscale, float mass) {
+    auto mesh = std::make_shared<ChTriangleMeshConnected>();
+    if (!mesh->LoadWavefrontMesh(filename, true, false))
+        fail("mesh " + filename + " failed to load");
+    if (mesh->GetNumTriangles() == 0)
+        printf("WARNING: Mesh %s has no triangles!\n", filename.c_str());
+    ChMatrix33<double> rs;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            rs(i, j) = rotscale(i, j);
+    mesh->Transform(ChVector3d(translation), rs);
+    return AddMesh(mesh, mass);
+}
+
+std::vector<unsigned int> ChSystemDemMesh::AddMeshes(const std::vector<std::string>& objfilenames,
+                                                     const std::vector<ChVector3f>& translations,
+                                                     const std::vector<ChMatrix33<float>>& rotscales,
+                                                     const std::vector<float>& masses) {
+    const size_t size = objfilenames.size();
+    if (size != rotscales.size() || size != translations.size() || size != masses.size())
+        fail("mesh loading vectors must all have the same size");
+    std::vector<unsigned int> ids(size);
+    for (size_t i = 0; i < size; i++)
+        ids[i] = AddMesh(objfilenames[i], translations[i], rotscales[i], masses[i]);
+    return ids;
+}
+
+// Flatten the cached meshes into the staging soup (reference SetMeshes, ChSystemDem.cpp:543-625).
+void ChSystemDemMesh::SetMeshes() {
+    ChSystemDem_impl& S = *m_sys;
+    std::vector<ChSystemDem_impl::MeshStage> staged(m_meshes.size());
+    for (size_t m = 0; m < m_meshes.size(); m++) {
+        auto& M = staged[m];
+        if (m < S.meshes.size()) {  // keep a motion applied before Initialize
+            M = S.meshes[m];
+            M.verts9.clear();
+        }
+        M.mass = m_mesh_masses[m] > 0 ? (double)m_mesh_masses[m] : 1e30;
+        const unsigned nt = m_meshes[m]->GetNumTriangles();
+        M.verts9.reserve((size_t)nt * (m_two_sided ? 18 : 9));
+        for (unsigned i = 0; i < nt; i++) {
+            const ChTriangle t = m_meshes[m]->GetTriangle(i);
+            const ChVector3d* v[3] = {&t.p1, &t.p2, &t.p3};
+            for (int k = 0; k < 3; k++)
+                for (unsigned c = 0; c < 3; c++)
+                    M.verts9.push_back((*v[k])[c]);
+            if (m_two_sided) {
+                const ChVector3d* w[3] = {&t.p1, &t.p3, &t.p2};
+                for (int k = 0; k < 3; k++)
+                    for (unsigned c = 0; c < 3; c++)
+                        M.verts9.push_back((*w[k])[c]);
+            }
+        }
+        if (mesh_verbosity == CHDEM_MESH_VERBOSITY::INFO)
+            printf("mesh %zu: %u facets (%s)\n", m, nt, m_two_sided ? "two-sided" : "one-sided");
+    }
+    S.meshes.swap(staged);
+}
+
+void ChSystemDemMesh::EnableMeshCollision(bool val) {
+    m_sys->mesh_collision = val;
+    if (m_sys->initialized)
+        m_sys->check(dem_b200_enable_mesh_collision(m_sys->h, val ? 1 : 0), "EnableMeshCollision");
+}
+
+void ChSystemDemMesh::ApplyMeshMotion(unsigned int mesh_id, const ChVector3d& pos, const ChQuaternion<>& rot,
+                                      const ChVector3d& lin_vel, const ChVector3d& ang_vel) {
+    ChSystemDem_impl& S = *m_sys;
+    if (mesh_id >= m_meshes.size())
+        fail("ApplyMeshMotion: bad mesh id");
+    const double p[3] = {pos.x(), pos.y(), pos.z()};
+    const double q[4] = {rot.e0(), rot.e1(), rot.e2(), rot.e3()};
+    const double v[3] = {lin_vel.x(), lin_vel.y(), lin_vel.z()};
+    const double w[3] = {ang_vel.x(), ang_vel.y(), ang_vel.z()};
+    if (!S.initialized) {
+        if (S.meshes.size() < m_meshes.size())
+            S.meshes.resize(m_meshes.size());
+        auto& M = S.meshes[mesh_id];
+        M.has_motion = true;
+        for (int k = 0; k < 3; k++) { M.pos[k] = p[k]; M.lin[k] = v[k]; M.ang[k] = w[k]; }
+        for (int k = 0; k < 4; k++) M.rot[k] = q[k];
+        return;
+    }
+    auto& M = S.meshes[mesh_id];
+    for (int k = 0; k < 3; k++) M.pos[k] = p[k];
+    for (int k = 0; k < 4; k++) M.rot[k] = q[k];
+    S.check(dem_b200_set_mesh_motion(S.h, (int)mesh_id, p, q, v, w), "ApplyMeshMotion");
+}
+
+unsigned int ChSystemDemMesh::GetNumMeshes() const { return (unsigned int)m_meshes.size(); }
+
+void ChSystemDemMesh::SetStaticFrictionCoeff_SPH2MESH(float mu) { m_sys->mu[2] = mu; }
+void ChSystemDemMesh::SetRollingCoeff_SPH2MESH(float mu) { m_sys->mu_roll[2] = mu; }
+void ChSystemDemMesh::SetSpinningCoeff_SPH2MESH(float mu) { m_sys->mu_spin[2] = mu; }
+void ChSystemDemMesh::SetKn_SPH2MESH(double v) { m_sys->Kn[2] = v; }
+void ChSystemDemMesh::SetGn_SPH2MESH(double v) { m_sys->Gn[2] = v; }
+void ChSystemDemMesh::SetKt_SPH2MESH(double v) { m_sys->Kt[2] = v; }
+void ChSystemDemMesh::SetGt_SPH2MESH(double v) { m_sys->Gt[2] = v; }
+void ChSystemDemMesh::UseMaterialBasedModel(bool val) { m_sys->use_mat_based = val; }
+void ChSystemDemMesh::SetYoungModulus_MESH(double v) { m_sys->young[2] = v; }
+void ChSystemDemMesh::SetPoissonRatio_MESH(double v) { m_sys->poisson[2] = v; }
+void ChSystemDemMesh::SetRestitution_MESH(double v) { m_sys->cor[2] = v; }
+void ChSystemDemMesh::SetAdhesionRatio_SPH2MESH(float v) { m_sys->adhesion_over_g[2] = v; }
+
+void ChSystemDemMesh::Initialize() {
+    if (!m_meshes.empty())
+        SetMeshes();
+    ChSystemDem::Initialize();  // the base uploads the staged meshes ahead of the spheres
+}
+
+// The reference can add the triangles to a system whose spheres are already initialised; here the facets own shape ids
+// below the spheres', so they must be known at Initialize.
+void ChSystemDemMesh::InitializeMeshes() {
+    if (m_sys->initialized) {
+        if (m_sys->num_triangles() == 0 && !m_meshes.empty())
+            fail("InitializeMeshes after Initialize is not supported: add the meshes before Initialize");
+        return;
+    }
+    if (!m_meshes.empty())
+        SetMeshes();
+}
+
+double ChSystemDemMesh::AdvanceSimulation(float duration) { return ChSystemDem::AdvanceSimulation(duration); }
+
+void ChSystemDemMesh::CollectMeshContactForces(int mesh, ChVector3d& force, ChVector3d& torque) {
+    double f[3], t[3];
+    m_sys->check(dem_b200_mesh_wrench(m_sys->h, mesh, f, t), "CollectMeshContactForces");
+    force = ChVector3d(f[0], f[1], f[2]);
+    torque = ChVector3d(t[0], t[1], t[2]);
+}
+
+void ChSystemDemMesh::CollectMeshContactForces(std::vector<ChVector3d>& forces, std::vector<ChVector3d>& torques) {
+    forces.resize(m_meshes.size());
+    torques.resize(m_meshes.size());
+    for (size_t i = 0; i < m_meshes.size(); i++)
+        CollectMeshContactForces((int)i, forces[i], torques[i]);
+}
+
+void ChSystemDemMesh::WriteCheckpointMeshParams(std::ofstream& cp) const {
+    const ChSystemDem_impl& S = *m_sys;
+    std::ostringstream p;
+    p << "adhesionOverG_s2m: " << (float)S.adhesion_over_g[2] << "\n";
+    p << "K_n_s2m: " << S.Kn[2] << "\n" << "K_t_s2m: " << S.Kt[2] << "\n";
+    p << "G_n_s2m: " << S.Gn[2] << "\n" << "G_t_s2m: " << S.Gt[2] << "\n";
+    p << "RollingCoeff_s2m: " << S.mu_roll[2] << "\n" << "SpinningCoeff_s2m: " << S.mu_spin[2] << "\n";
+    p << "StaticFrictionCoeff_s2m: " << S.mu[2] << "\n";
+    p << "MeshCollisionEnabled: " << (S.mesh_collision ? 1 : 0) << "\n";
+    cp << p.str();
+}
+
+void ChSystemDemMesh::WriteCheckpointFile(const std::string& outfilename) {
+    std::ofstream cp(outfilename, std::ios::out);
+    cp << "ChSystemDemMesh\n";
+    WriteCheckpointParams(cp);
+    WriteCheckpointMeshParams(cp);
+    cp << "ParamsEnd\n\n";
+    cp << "CsvParticles\n";
+    const unsigned int flags = m_sys->out_flags;
+    m_sys->out_flags = VEL_COMPONENTS | FIXITY | ANG_VEL_COMPONENTS;
+    WriteCsvParticles(cp);
+    m_sys->out_flags = flags;
+    cp << "\n";
+    if (m_sys->friction != CHDEM_FRICTION_MODE::FRICTIONLESS) {
+        cp << "HstHistory\n";
+        WriteHstHistory(cp);
+        cp << "\n";
+    }
+}
+
+void ChSystemDemMesh::ReadCheckpointFile(const std::string& infilename, bool overwrite) {
+    ChSystemDem::ReadCheckpointFile(infilename, overwrite);  // SetParamsFromIdentifier is virtual: mesh keys are ours
+}
+
+bool ChSystemDemMesh::SetParamsFromIdentifier(const std::string& id, std::istringstream& iss, bool overwrite) {
+    ChSystemDem_impl& S = *m_sys;
+    unsigned u;
+    if (id == "adhesionOverG_s2m") iss >> S.adhesion_over_g[2];
+    else if (id == "K_n_s2m") iss >> S.Kn[2];
+    else if (id == "K_t_s2m") iss >> S.Kt[2];
+    else if (id == "G_n_s2m") iss >> S.Gn[2];
+    else if (id == "G_t_s2m") iss >> S.Gt[2];
+    else if (id == "RollingCoeff_s2m") iss >> S.mu_roll[2];
+    else if (id == "SpinningCoeff_s2m") iss >> S.mu_spin[2];
+    else if (id == "StaticFrictionCoeff_s2m") iss >> S.mu[2];
+    else if (id == "MeshCollisionEnabled") { iss >> u; S.mesh_collision = u != 0; }
+    else return ChSystemDem::SetParamsFromIdentifier(id, iss, overwrite);
+    return true;
+}
+
+// ASCII VTK unstructured grid of mesh i at its current frame (reference: ChSystemDem.cpp:1564-1613).
+static void write_vtk(std::ostream& o, const std::vector<const ChTriangleMeshConnected*>& ms,
+                      const std::vector<const ChSystemDem_impl::MeshStage*>& frames) {
+    size_t nv = 0, nf = 0;
+    for (auto* m : ms) { nv += m->GetCoordsVertices().size(); nf += m->GetIndicesVertices().size(); }
+    o << "# vtk DataFile Version 2.0\nVTK from simulation\nASCII\n\n\nDATASET UNSTRUCTURED_GRID\n";
+    o << "POINTS " << nv << " float" << std::endl;
+    for (size_t k = 0; k < ms.size(); k++) {
+        const auto* F = frames[k];
+        ChQuaternion<double> q(1, 0, 0, 0);
+        double p[3] = {0, 0, 0};
+        if (F) { q = ChQuaternion<double>(F->rot[0], F->rot[1], F->rot[2], F->rot[3]); p[0] = F->pos[0]; p[1] = F->pos[1]; p[2] = F->pos[2]; }
+        ChMatrix33<double> A(q);
+        for (auto& v : ms[k]->GetCoordsVertices()) {
+            const ChVector3d w = A * v;
+            o << (float)(w.x() + p[0]) << " " << (float)(w.y() + p[1]) << " " << (float)(w.z() + p[2]) << std::endl;
+        }
+    }
+    o << "\n\nCELLS " << nf << " " << 4 * nf << std::endl;
+    size_t off = 0;
+    for (auto* m : ms) {
+        for (auto& f : m->GetIndicesVertices())
+            o << "3 " << f.x() + (int)off << " " << f.y() + (int)off << " " << f.z() + (int)off << std::endl;
+        off += m->GetCoordsVertices().size();
+    }
+    o << "\n\nCELL_TYPES " << nf << std::endl;
+    for (size_t j = 0; j < nf; j++)
+        o << "5 " << std::endl;
+}
+
+static std::string vtk_name(const std::string& n) {
+    const std::string tail = n.substr(n.length() - std::min(n.length(), (size_t)4));
+    return (tail == ".vtk" || tail == ".VTK") ? n : n + ".vtk";
+}
+
+void ChSystemDemMesh::WriteMesh(const std::string& outfilename, unsigned int i) const {
+    if (m_sys->out_mode == CHDEM_OUTPUT_MODE::NONE)
+        return;
+    if (i >= m_meshes.size()) {
+        printf("WARNING: attempted to write mesh %u, yet only %zu meshes present. No mesh file generated.\n", i, m_meshes.size());
+        return;
+    }
+    std::ofstream f(vtk_name(outfilename), std::ios::out);
+    write_vtk(f, {m_meshes[i].get()}, {i < m_sys->meshes.size() ? &m_sys->meshes[i] : nullptr});
+}
+
+void ChSystemDemMesh::WriteMeshes(const std::string& outfilename) const {
+    if (m_sys->out_mode == CHDEM_OUTPUT_MODE::NONE)
+        return;
+    if (m_meshes.empty()) {
+        printf("WARNING: attempted to write meshes to file yet no mesh found in system cache. No mesh file generated.\n");
+        return;
+    }
+    std::vector<const ChTriangleMeshConnected*> ms;
+    std::vector<const ChSystemDem_impl::MeshStage*> fr;
+    for (size_t i = 0; i < m_meshes.size(); i++) {
+        ms.push_back(m_meshes[i].get());
+        fr.push_back(i < m_sys->meshes.size() ? &m_sys->meshes[i] : nullptr);
+    }
+    std::ofstream f(vtk_name(outfilename), std::ios::out);
+    write_vtk(f, ms, fr);
 }
 
 }  // namespace dem

@@ -31,6 +31,11 @@ struct dem_b200_system {
     Params P{};
     Buffers B{};
     WallSet W{};                       // host copy of the walls (device copy: B.walls)
+    MeshSet M{};                       // host copy of the mesh bodies (device copy: B.meshes)
+    std::vector<double> h_tri;         // triangle soup, body frame, 9 doubles per triangle
+    std::vector<uint32_t> h_tri_mesh;  // owner mesh of each triangle
+    double mesh_radius[kMaxMeshes] = {0};  // largest vertex distance from the body origin (bound of a rotation's travel)
+    MeshSet* h_mesh_pin = nullptr;     // pinned staging of MeshSet::m (mesh motion is applied every step by co-simulation)
     bool cls_override[3] = {false, false, false};
     dem_b200_contact_class cls[3]{};   // explicit contact-class coefficients (dem_b200_set_contact_class)
     // scene staged on the host until initialize()
@@ -189,7 +194,8 @@ void refresh_params(dem_b200_system* s) {
     }
     P.track_wall_forces = s->track_wall_forces ? 1 : 0;
     P.external_rebuild = s->mgpu ? 1 : 0;
-    P.shape_base = (unsigned)P.nW;
+    P.nT = (unsigned)s->h_tri_mesh.size();
+    P.shape_base = (unsigned)P.nW + P.nT;  // Multicore numbering: wall shapes, then mesh triangles, then spheres (Q12)
     // Verlet skin: negative -> default 0.25 * largest radius (set at initialize, when radii are known)
     if (c.verlet_skin >= 0)
         P.skin = c.verlet_skin;
@@ -198,7 +204,7 @@ void refresh_params(dem_b200_system* s) {
 }
 
 bool need_roll(const dem_b200_system* s) {
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < (s->P.nT ? 3 : 2); k++)
         if (s->P.comp[k].mu_roll > 0 || s->P.comp[k].mu_spin > 0)
             return true;
     return false;
@@ -215,7 +221,13 @@ void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks) {
     const bool roll = need_roll(s);
     const bool fast = fast_path(s);
     const int sel = (hist ? 4 : 0) | (roll ? 2 : 0) | (fast ? 1 : 0);
-#define LF(H, R, F) k_force_integrate<H, R, F, REC><<<blocks, kForceThreads, 0, s->stream>>>(P, B)
+#define LF(H, R, F)                                                                                  \
+    do {                                                                                             \
+        if (P.nT)                                                                                    \
+            k_force_integrate<H, R, F, REC, true><<<blocks, kForceThreads, 0, s->stream>>>(P, B);    \
+        else                                                                                         \
+            k_force_integrate<H, R, F, REC, false><<<blocks, kForceThreads, 0, s->stream>>>(P, B);   \
+    } while (0)
     switch (sel) {
         case 0: LF(false, false, false); break;
         case 1: LF(false, false, true); break;
@@ -252,16 +264,24 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
     // the rebuild kernels return immediately unless k_step_begin decided that the Verlet skin is used up
     k_bin_count<<<nb256, 256, 0, st>>>(P, B);
     mark();
-    k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(B);
+    k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(B, 0);
     mark();
-    k_scan_sums<<<1, kScanThreads, 0, st>>>(B);
+    k_scan_sums<<<1, kScanThreads, 0, st>>>(B, 0);
     mark();
-    k_scan_apply<<<s->ntiles, kScanThreads, 0, st>>>(P, B);
+    k_scan_apply<<<s->ntiles, kScanThreads, 0, st>>>(P, B, 0);
     mark();
     k_scatter_perm<<<nb256, 256, 0, st>>>(P, B);
     mark();
     k_gather_sorted<<<nb256, 256, 0, st>>>(P, B);
     mark();
+    if (P.nT) {  // mesh triangles -> search cells (rebuild steps only; timed with k_build_list in the profile)
+        const unsigned tb = (P.nT + 255) / 256;
+        k_tri_count<<<tb, 256, 0, st>>>(P, B);
+        k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(B, 1);
+        k_scan_sums<<<1, kScanThreads, 0, st>>>(B, 1);
+        k_scan_apply<<<s->ntiles, kScanThreads, 0, st>>>(P, B, 1);
+        k_tri_fill<<<tb, 256, 0, st>>>(P, B);
+    }
     k_build_list<<<(N + kListThreads - 1) / kListThreads, kListThreads, 0, st>>>(P, B);
     mark();
     const unsigned fb = (N + kForceThreads - 1) / kForceThreads;
@@ -314,6 +334,7 @@ int check_device_error(dem_b200_system* s) {
     if (e & ERR_HISTORY_OVERFLOW) { s->err = "a sphere has more contacts than history_slots"; return DEMB200_EHISTORY; }
     if (e & ERR_NEIGHBOR_OVERFLOW) { s->err = "a sphere has more neighbour candidates than neighbor_slots"; return DEMB200_ENEIGHBORS; }
     if (e & ERR_PAIR_CAPACITY) { s->err = "pair recording buffer overflow"; return DEMB200_ECAPACITY; }
+    if (e & ERR_MESH_CAPACITY) { s->err = "mesh triangles cover more search cells than reserved (triangles much larger than the spheres: subdivide the mesh)"; return DEMB200_ECAPACITY; }
     s->err = "unknown device error";
     return DEMB200_ECUDA;
 }
@@ -431,6 +452,8 @@ void dem_b200_destroy(dem_b200_system* s) {
         cudaFree(p);
     if (s->h_pin)
         cudaFreeHost(s->h_pin);
+    if (s->h_mesh_pin)
+        cudaFreeHost(s->h_mesh_pin);
     if (s->stream && s->own_stream)
         cudaStreamDestroy(s->stream);
     delete s;
@@ -613,6 +636,121 @@ int dem_b200_set_contact_class(dem_b200_system* s, int cls, const dem_b200_conta
 }
 int dem_b200_num_walls(const dem_b200_system* s) { return s ? s->P.nW : 0; }
 
+// ---- triangle meshes (ChSystemDemMesh::AddMesh / ApplyMeshMotion / CollectMeshContactForces) --------------------
+int dem_b200_add_mesh(dem_b200_system* s, size_t ntri, const double* verts9, double mass) {
+    if (!s || !verts9 || ntri == 0)
+        return DEMB200_EINVAL;
+    if (s->initialized) {
+        s->err = "meshes must be added before initialize";
+        return DEMB200_EINVAL;
+    }
+    if (s->M.n >= kMaxMeshes || s->h_tri_mesh.size() + ntri >= 0x7FFF0000ull) {
+        s->err = "too many meshes / triangles";
+        return DEMB200_EINVAL;
+    }
+    const int m = s->M.n++;
+    MeshBody& B = s->M.m[m];
+    memset(&B, 0, sizeof(B));
+    B.rot[0] = 1.0;
+    B.mass = mass > 0 ? mass : s->cfg.mesh_mass;
+    B.tri_begin = (unsigned)s->h_tri_mesh.size();
+    B.tri_end = B.tri_begin + (unsigned)ntri;
+    s->M.enabled = 1;
+    s->h_tri.insert(s->h_tri.end(), verts9, verts9 + 9 * ntri);
+    s->h_tri_mesh.insert(s->h_tri_mesh.end(), ntri, (uint32_t)m);
+    double r2 = 0;
+    for (size_t i = 0; i < 3 * ntri; i++)
+        r2 = std::max(r2, verts9[3 * i] * verts9[3 * i] + verts9[3 * i + 1] * verts9[3 * i + 1] + verts9[3 * i + 2] * verts9[3 * i + 2]);
+    s->mesh_radius[m] = std::sqrt(r2);
+    refresh_params(s);
+    return m;
+}
+
+int dem_b200_num_meshes(const dem_b200_system* s) { return s ? s->M.n : 0; }
+size_t dem_b200_num_triangles(const dem_b200_system* s) { return s ? s->h_tri_mesh.size() : 0; }
+
+int dem_b200_set_mesh_motion(dem_b200_system* s, int m, const double pos[3], const double rot[4], const double lin_vel[3],
+                             const double ang_vel[3]) {
+    if (!s || m < 0 || m >= s->M.n)
+        return DEMB200_EINVAL;
+    MeshBody& B = s->M.m[m];
+    // how far can a vertex have moved?  |dx| + (rotation angle between the two frames) * (largest vertex radius)
+    double moved = 0;
+    if (pos) {
+        double d2 = 0;
+        for (int k = 0; k < 3; k++) {
+            d2 += (pos[k] - B.pos[k]) * (pos[k] - B.pos[k]);
+            B.pos[k] = pos[k];
+        }
+        moved += std::sqrt(d2);
+    }
+    if (rot) {
+        double l = std::sqrt(rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2] + rot[3] * rot[3]);
+        if (!(l > 0))
+            return DEMB200_EINVAL;
+        double dq = 0;
+        for (int k = 0; k < 4; k++)
+            dq += rot[k] / l * B.rot[k];
+        dq = std::min(1.0, std::fabs(dq));
+        const double ang = 2.0 * std::acos(dq);
+        // acos loses accuracy next to 1: bound the angle from the chord |q - q'| as well
+        double c2 = 0;
+        const double sg = (rot[0] * B.rot[0] + rot[1] * B.rot[1] + rot[2] * B.rot[2] + rot[3] * B.rot[3]) < 0 ? -1.0 : 1.0;
+        for (int k = 0; k < 4; k++)
+            c2 += (sg * rot[k] / l - B.rot[k]) * (sg * rot[k] / l - B.rot[k]);
+        moved += std::max(ang, 2.2 * std::sqrt(c2)) * s->mesh_radius[m];
+        for (int k = 0; k < 4; k++)
+            B.rot[k] = rot[k];  // as given (the oracle / Multicore use the body quaternion unnormalised too)
+    }
+    for (int k = 0; k < 3; k++) {
+        if (lin_vel) B.vel[k] = lin_vel[k];
+        if (ang_vel) B.omg[k] = ang_vel[k];
+    }
+    if (!s->initialized)
+        return 0;
+    CU(cudaSetDevice(s->cfg.device));
+    // asynchronous on the engine's stream (pinned staging is re-used: wait for the previous upload only)
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(s->h_mesh_pin->m, s->M.m, sizeof(s->M.m));
+    CU(cudaMemcpyAsync(s->B.meshes->m, s->h_mesh_pin->m, sizeof(s->M.m), cudaMemcpyHostToDevice, s->stream));
+    if (pos || rot) {
+        const unsigned nt = B.tri_end - B.tri_begin;
+        k_mesh_begin<<<1, 32, 0, s->stream>>>(s->B, m);
+        k_mesh_transform<<<(nt + 255) / 256, 256, 0, s->stream>>>(s->B, m);
+        if (moved > 0)
+            k_wall_moved<<<1, 1, 0, s->stream>>>(s->B, moved);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+int dem_b200_enable_mesh_collision(dem_b200_system* s, int enabled) {
+    if (!s)
+        return DEMB200_EINVAL;
+    s->M.enabled = enabled ? 1 : 0;
+    if (!s->initialized || !s->P.nT)
+        return 0;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemcpyAsync(&s->B.meshes->enabled, &s->M.enabled, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    const unsigned one = 1;  // the candidate lists hold no triangles while collision is off
+    CU(cudaMemcpyAsync(&s->B.ctrl->need_rebuild, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int dem_b200_mesh_wrench(dem_b200_system* s, int m, double force[3], double torque[3]) {
+    if (!s || !s->initialized || m < 0 || m >= s->M.n)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemcpyAsync(s->h_pin, s->B.meshes->wrench[m], 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < 3; k++) {
+        if (force) force[k] = s->h_pin[k];
+        if (torque) torque[k] = s->h_pin[3 + k];
+    }
+    return 0;
+}
+
 int dem_b200_initialize(dem_b200_system* s) {
     if (!s)
         return DEMB200_EINVAL;
@@ -663,6 +801,11 @@ int dem_b200_initialize(dem_b200_system* s) {
                 mn[k] = std::min(mn[k], s->h_pos[3 * i + k] - s->h_rad[i]);
                 mx[k] = std::max(mx[k], s->h_pos[3 * i + k] + s->h_rad[i]);
             }
+        for (int m = 0; m < s->M.n; m++)  // a mesh can be turned about its origin: reserve for its bounding sphere
+            for (int k = 0; k < 3; k++) {
+                mn[k] = std::min(mn[k], s->M.m[m].pos[k] - s->mesh_radius[m]);
+                mx[k] = std::max(mx[k], s->M.m[m].pos[k] + s->mesh_radius[m]);
+            }
         const double e = 2.0 * P.rmax + P.skin;
         double cells = 1.0;
         for (int k = 0; k < 3; k++)
@@ -700,6 +843,32 @@ int dem_b200_initialize(dem_b200_system* s) {
     rc |= dev_alloc(s, &B.nl, (size_t)P.Kn * Np); rc |= dev_alloc(s, &B.ncnt, Np);
     rc |= dev_alloc(s, &s->d_pos3, 3 * Np); rc |= dev_alloc(s, &s->d_vel3, 3 * Np); rc |= dev_alloc(s, &s->d_om3, 3 * Np);
     rc |= dev_alloc(s, &s->d_red, 4);
+    if (P.nT) {
+        // capacity of the (cell, triangle) list: every triangle reaches at most the cells of the cube around its longest
+        // edge inflated by the reach of a sphere
+        const double e = 2.0 * P.rmax + P.skin, reach = P.rmax + 0.5 * P.skin;
+        double tot = 0;
+        for (size_t t = 0; t < P.nT; t++) {
+            const double* v = &s->h_tri[9 * t];
+            double L = 0;
+            for (int a = 0; a < 3; a++) {
+                const int b = (a + 1) % 3;
+                double d2 = 0;
+                for (int k = 0; k < 3; k++)
+                    d2 += (v[3 * a + k] - v[3 * b + k]) * (v[3 * a + k] - v[3 * b + k]);
+                L = std::max(L, std::sqrt(d2));
+            }
+            const double c = std::floor((L + 2 * reach) / e) + 2.0;
+            tot += std::min(c * c * c, 20.0 * c * c);  // the plane cull keeps a slab of ~3-4 cells (+ grid boundary cells)
+        }
+        P.tri_cap = (unsigned)std::min(std::max(2.0 * tot, 1024.0), 1.0e9);
+        rc |= dev_alloc(s, &B.meshes, 1);
+        rc |= dev_alloc(s, &B.tri_loc, 9 * (size_t)P.nT); rc |= dev_alloc(s, &B.tri_w, 9 * (size_t)P.nT);
+        rc |= dev_alloc(s, &B.tri_mesh, (size_t)P.nT);
+        rc |= dev_alloc(s, &B.tcell_count, (size_t)P.cell_cap + 8); rc |= dev_alloc(s, &B.tcell_start, (size_t)P.cell_cap + 8);
+        rc |= dev_alloc(s, &B.tblock_sums, (size_t)s->ntiles + 8);
+        rc |= dev_alloc(s, &B.tcell_tri, (size_t)P.tri_cap);
+    }
     if (s->mgpu) {
         rc |= dev_alloc(s, &B.slab, 1);
         rc |= dev_alloc(s, &B.inv_perm, Np);
@@ -811,6 +980,19 @@ int dem_b200_initialize(dem_b200_system* s) {
     }
     CU(cudaMemset(B.cell_count, 0, ((size_t)P.cell_cap + 8) * sizeof(uint32_t)));
     CU(cudaMemset(B.ncnt, 0, Np * sizeof(uint32_t)));
+    if (P.nT) {
+        CU(cudaMemset(B.tcell_count, 0, ((size_t)P.cell_cap + 8) * sizeof(uint32_t)));
+        CU(cudaMemcpy(B.tri_loc, s->h_tri.data(), 9 * (size_t)P.nT * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(B.tri_mesh, s->h_tri_mesh.data(), (size_t)P.nT * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(B.meshes, &s->M, sizeof(MeshSet), cudaMemcpyHostToDevice));
+        CU(cudaMallocHost((void**)&s->h_mesh_pin, sizeof(MeshSet)));
+        for (int m = 0; m < s->M.n; m++) {
+            const unsigned nt = s->M.m[m].tri_end - s->M.m[m].tri_begin;
+            k_mesh_begin<<<1, 32, 0, s->stream>>>(B, m);
+            k_mesh_transform<<<(nt + 255) / 256, 256, 0, s->stream>>>(B, m);
+        }
+        CU(cudaGetLastError());
+    }
     {
         Ctrl c;
         memset(&c, 0, sizeof(c));
@@ -1145,7 +1327,8 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
         for (size_t k = 0; k < Kn; k++) {
             if (!((vr[i].amask >> k) & 1ull))
                 continue;
-            const uint32_t key = s->P.shape_base + vr[nl[k * Np + i]].sid;
+            const uint32_t jo = nl[k * Np + i];
+            const uint32_t key = (jo & kTriFlag) ? (uint32_t)s->P.nW + (jo & ~kTriFlag) : s->P.shape_base + vr[jo].sid;
             if (key < me)
                 emit(me, key, k * Np + i);
         }

@@ -61,6 +61,11 @@ __device__ __forceinline__ V3 rotate_rn(V3 v, double qw, V3 qv) {
               __dadd_rn(__dadd_rn(v.z, __dmul_rn(qw, t.z)), c2.z)};
 }
 
+__device__ __forceinline__ V3 add_rn(V3 a, V3 b) { return V3{__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y), __dadd_rn(a.z, b.z)}; }
+__device__ __forceinline__ V3 sub_rn(V3 a, V3 b) { return V3{__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)}; }
+__device__ __forceinline__ V3 scale_rn(double s, V3 a) { return V3{__dmul_rn(s, a.x), __dmul_rn(s, a.y), __dmul_rn(s, a.z)}; }
+__device__ __forceinline__ V3 div_rn(V3 a, double s) { return V3{__ddiv_rn(a.x, s), __ddiv_rn(a.y, s), __ddiv_rn(a.z, s)}; }
+
 // order-preserving map double <-> uint64 for atomicMin / atomicMax
 __device__ __forceinline__ unsigned long long enc_ord(double d) {
     unsigned long long u = (unsigned long long)__double_as_longlong(d);
@@ -195,6 +200,17 @@ __global__ void k_step_begin(Params P, Buffers B) {
         if (WS.has_bb) {
             mn[k] = fmin(mn[k], WS.bb_min[k]);
             mx[k] = fmax(mx[k], WS.bb_max[k]);
+        }
+    }
+    if (P.nT) {  // mesh triangles are shapes of the Multicore broadphase too (ChCollisionSystemMulticore.cpp:387-394)
+        MeshSet& MS = *B.meshes;
+        for (int m = 0; m < MS.n; m++) {
+            for (int k = 0; k < 3; k++) {
+                mn[k] = fmin(mn[k], dec_ord(MS.bb[m][k]));
+                mx[k] = fmax(mx[k], dec_ord(MS.bb[m][3 + k]));
+            }
+            for (int k = 0; k < 6; k++)
+                MS.wrench[m][k] = 0.0;
         }
     }
     // ---- Multicore grid: ChBroadphase::DetermineBoundingBox + ComputeTopLevelResolution (ChBroadphase.cpp:143-208)
@@ -386,14 +402,15 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
     return prefix + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(Buffers B) {
+// which = 0: sphere histogram (cell_count -> cell_start); which = 1: (cell, triangle) pair histogram of the meshes
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(Buffers B, int which) {
     const Ctrl& C = *B.ctrl;
     if (!C.rebuild_now)
         return;
     const unsigned n = C.s_ncell;
     if (blockIdx.x * kScanTile >= n)
         return;
-    const uint32_t* __restrict__ in = B.cell_count;
+    const uint32_t* __restrict__ in = which ? B.tcell_count : B.cell_count;
     const unsigned base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     unsigned s = 0;
     if (base + kScanItems <= n) {
@@ -408,15 +425,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(Buffers B) {
     unsigned total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0)
-        B.block_sums[blockIdx.x] = total;
+        (which ? B.tblock_sums : B.block_sums)[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Buffers B) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Buffers B, int which) {
     const Ctrl& C = *B.ctrl;
     if (!C.rebuild_now)
         return;
     const unsigned ntiles = (C.s_ncell + kScanTile - 1) / kScanTile;
-    uint32_t* tile_sums = B.block_sums;
+    uint32_t* tile_sums = which ? B.tblock_sums : B.block_sums;
     __shared__ unsigned carry_s;
     if (threadIdx.x == 0)
         carry_s = 0;
@@ -436,15 +453,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_sums(Buffers B) {
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(Params P, Buffers B) {
-    const Ctrl& C = *B.ctrl;
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(Params P, Buffers B, int which) {
+    Ctrl& C = *B.ctrl;
     if (!C.rebuild_now)
         return;
     const unsigned n = C.s_ncell;
     if (blockIdx.x * kScanTile >= n)
         return;
-    uint32_t* in = B.cell_count;
-    uint32_t* __restrict__ out = B.cell_start;
+    uint32_t* in = which ? B.tcell_count : B.cell_count;
+    uint32_t* __restrict__ out = which ? B.tcell_start : B.cell_start;
     const unsigned base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     unsigned v[kScanItems];
     unsigned s = 0;
@@ -453,17 +470,121 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Params P, Buffers B
         v[k] = (base + k < n) ? in[base + k] : 0;
         s += v[k];
     }
-    unsigned ex = block_exclusive_scan(s, nullptr) + B.block_sums[blockIdx.x];
+    unsigned ex = block_exclusive_scan(s, nullptr) + (which ? B.tblock_sums : B.block_sums)[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
         if (base + k < n) {
             out[base + k] = ex;
-            in[base + k] = 0;  // self-cleaning histogram: ready for the next rebuild, no memset node in the graph
+            // sphere histogram: self-cleaning (ready for the next rebuild, no memset node in the graph); the triangle
+            // histogram is counted back down to zero by k_tri_fill
+            if (!which)
+                in[base + k] = 0;
         }
         ex += v[k];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        out[n] = P.N;
+    if (!which) {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            out[n] = P.N;
+    } else if (base < n && n <= base + kScanItems) {  // the thread that owns the last cell knows the total
+        out[n] = ex;
+        if (ex > P.tri_cap)
+            atomicOr(&C.err, ERR_MESH_CAPACITY);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// triangle meshes.  World-frame soup = body frame + rigid motion (TransformLocalToParent, utility.h:46, rounding
+// pinned); at a rebuild every triangle is registered in the search cells its AABB, inflated by the largest reach of a
+// sphere (r_max + skin/2), overlaps, so that a sphere only has to look at the triangle list of its own cell.
+// --------------------------------------------------------------------------------------------
+__global__ void k_mesh_begin(Buffers B, int m) {
+    if (threadIdx.x || blockIdx.x)
+        return;
+    MeshSet& MS = *B.meshes;
+    for (int k = 0; k < 3; k++) {
+        MS.bb[m][k] = enc_ord(CUDART_INF);
+        MS.bb[m][3 + k] = enc_ord(-CUDART_INF);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mesh_transform(Buffers B, int m) {
+    MeshSet& MS = *B.meshes;
+    const MeshBody& M = MS.m[m];
+    const unsigned t = M.tri_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    double mn[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, mx[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+    if (t < M.tri_end) {
+        const V3 qv = mk(M.rot[1], M.rot[2], M.rot[3]);
+        const V3 bp = mk(M.pos[0], M.pos[1], M.pos[2]);
+        const double* l = B.tri_loc + 9 * (size_t)t;
+        double* w = B.tri_w + 9 * (size_t)t;
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const V3 g = add_rn(bp, rotate_rn(mk(l[3 * v], l[3 * v + 1], l[3 * v + 2]), M.rot[0], qv));
+            w[3 * v] = g.x; w[3 * v + 1] = g.y; w[3 * v + 2] = g.z;
+            mn[0] = fmin(mn[0], g.x); mn[1] = fmin(mn[1], g.y); mn[2] = fmin(mn[2], g.z);
+            mx[0] = fmax(mx[0], g.x); mx[1] = fmax(mx[1], g.y); mx[2] = fmax(mx[2], g.z);
+        }
+    }
+    block_bbox_commit(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], MS.bb[m]);
+}
+
+// cells reached by triangle t: AABB inflated by `reach`, culled by the distance of the cell centre to the triangle's plane
+template <class Visit>
+__device__ __forceinline__ void tri_cells(const Ctrl& C, const double* w, double reach, Visit visit) {
+    const V3 A = mk(w[0], w[1], w[2]), Bv = mk(w[3], w[4], w[5]), Cv = mk(w[6], w[7], w[8]);
+    int lo[3], hi[3];
+    const double mn[3] = {fmin(A.x, fmin(Bv.x, Cv.x)) - reach, fmin(A.y, fmin(Bv.y, Cv.y)) - reach, fmin(A.z, fmin(Bv.z, Cv.z)) - reach};
+    const double mx[3] = {fmax(A.x, fmax(Bv.x, Cv.x)) + reach, fmax(A.y, fmax(Bv.y, Cv.y)) + reach, fmax(A.z, fmax(Bv.z, Cv.z)) + reach};
+    for (int k = 0; k < 3; k++) {
+        lo[k] = cell_coord(mn[k], C.s_org[k], C.s_inv[k], C.s_dim[k]);
+        hi[k] = cell_coord(mx[k], C.s_org[k], C.s_inv[k], C.s_dim[k]);
+    }
+    V3 n = cross(Bv - A, Cv - A);
+    const double nl = len(n);
+    const bool flat = nl > 0;
+    if (flat)
+        n = n / nl;
+    const double cs[3] = {1.0 / C.s_inv[0], 1.0 / C.s_inv[1], 1.0 / C.s_inv[2]};
+    // a point of the cell lies within half the cell diagonal of its centre; boundary cells are unbounded (clamping)
+    const double slack = reach + 0.5 * sqrt(cs[0] * cs[0] + cs[1] * cs[1] + cs[2] * cs[2]) * (1.0 + 1e-9);
+    for (int z = lo[2]; z <= hi[2]; z++)
+        for (int y = lo[1]; y <= hi[1]; y++)
+            for (int x = lo[0]; x <= hi[0]; x++) {
+                const bool edge = x == 0 || y == 0 || z == 0 || x == C.s_dim[0] - 1 || y == C.s_dim[1] - 1 || z == C.s_dim[2] - 1;
+                if (flat && !edge) {
+                    const V3 c = mk(C.s_org[0] + (x + 0.5) * cs[0], C.s_org[1] + (y + 0.5) * cs[1], C.s_org[2] + (z + 0.5) * cs[2]);
+                    if (fabs(dot(c - A, n)) > slack)
+                        continue;
+                }
+                visit((unsigned)((z * C.s_dim[1] + y) * C.s_dim[0] + x));
+            }
+}
+
+__global__ void __launch_bounds__(256) k_tri_count(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nT)
+        return;
+    const double reach = (P.rmax + 0.5 * P.skin) * (1.0 + 1e-9);
+    tri_cells(C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) { atomicAdd(&B.tcell_count[cell], 1u); });
+}
+
+__global__ void __launch_bounds__(256) k_tri_fill(Params P, Buffers B) {
+    const Ctrl& C = *B.ctrl;
+    if (!C.rebuild_now)
+        return;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nT)
+        return;
+    const double reach = (P.rmax + 0.5 * P.skin) * (1.0 + 1e-9);
+    tri_cells(C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) {
+        // counts back down to zero: the histogram is clean again for the next rebuild
+        const unsigned at = B.tcell_start[cell] + atomicSub(&B.tcell_count[cell], 1u) - 1u;
+        if (at < P.tri_cap)
+            B.tcell_tri[at] = t;
+    });
 }
 
 // --------------------------------------------------------------------------------------------
@@ -532,9 +653,9 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
             amask &= amask - 1;
             const size_t si = (size_t)k * P.Np + src;
             if (cnt < (unsigned)P.K) {
-                const unsigned jo = B.nl[si];  // old storage slot of the partner
+                const unsigned jo = B.nl[si];  // old storage slot of the partner, or kTriFlag | triangle
                 double4 r = B.hist[si];
-                r.w = pack_key(P.shape_base + B.vel[a][jo].sid, (unsigned)r.w);
+                r.w = pack_key((jo & kTriFlag) ? (unsigned)P.nW + (jo & ~kTriFlag) : P.shape_base + B.vel[a][jo].sid, (unsigned)r.w);
                 B.stage[(size_t)cnt * P.Np + s] = r;
                 if (B.stage_rel)
                     B.stage_rel[(size_t)cnt * P.Np + s] = B.hrel[si];
@@ -553,6 +674,28 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
 // rebuild, part 3: Verlet candidate list.  One thread per sphere (cell order), 3x3 rows of 3 contiguous cells.
 // --------------------------------------------------------------------------------------------
 constexpr int kListThreads = 128;
+
+// Closest point of triangle ABC to P (Ericson, Real-time collision detection, p.141); plain arithmetic: only used
+// to select candidates, with slack.
+__device__ __forceinline__ void closest_on_triangle(V3 A, V3 Bv, V3 Cv, V3 Pp, V3& res) {
+    const V3 AB = Bv - A, AC = Cv - A, AP = Pp - A;
+    const double d1 = dot(AB, AP), d2 = dot(AC, AP);
+    if (d1 <= 0 && d2 <= 0) { res = A; return; }
+    const V3 BP = Pp - Bv;
+    const double d3 = dot(AB, BP), d4 = dot(AC, BP);
+    if (d3 >= 0 && d4 <= d3) { res = Bv; return; }
+    const double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) { res = A + (d1 / (d1 - d3)) * AB; return; }
+    const V3 CP = Pp - Cv;
+    const double d5 = dot(AB, CP), d6 = dot(AC, CP);
+    if (d6 >= 0 && d5 <= d6) { res = Cv; return; }
+    const double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) { res = A + (d2 / (d2 - d6)) * AC; return; }
+    const double va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { res = Bv + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (Cv - Bv); return; }
+    const double denom = 1.0 / (va + vb + vc);
+    res = A + (vb * denom) * AB + (vc * denom) * AC;
+}
 
 __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B) {
     Ctrl& C = *B.ctrl;
@@ -619,7 +762,40 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         tj[b + 1] = kj;
         ts[b + 1] = ks;
     }
-    for (int k = 0; k < cnt; k++)
+    // mesh triangles within reach (r + skin/2; the mesh's own motion uses up skin like a wall's), ascending triangle
+    // index, behind the sphere candidates.  ts[] keeps the staging key (shape id - shape_base, wrapping for triangles).
+    int tcnt = 0;
+    if (P.nT && B.meshes->enabled) {
+        const unsigned cell = (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
+        const unsigned tb = B.tcell_start[cell], te = min(B.tcell_start[cell + 1], P.tri_cap);
+        const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
+        const V3 c = mk(me.x, me.y, me.z);
+        for (unsigned q = tb; q < te; q++) {
+            const unsigned t = B.tcell_tri[q];
+            const double* w = B.tri_w + 9 * (size_t)t;
+            V3 cp;
+            closest_on_triangle(mk(w[0], w[1], w[2]), mk(w[3], w[4], w[5]), mk(w[6], w[7], w[8]), c, cp);
+            const V3 d = c - cp;
+            if (dot(d, d) > reach * reach)
+                continue;
+            if (cnt + tcnt >= P.Kn) {
+                overflow = true;
+                continue;
+            }
+            int b = cnt + tcnt - 1;
+            while (b >= cnt && (tj[b] & ~kTriFlag) > t) {
+                tj[b + 1] = tj[b];
+                ts[b + 1] = ts[b];
+                b--;
+            }
+            tj[b + 1] = kTriFlag | t;
+            ts[b + 1] = (unsigned)P.nW + t - P.shape_base;
+            tcnt++;
+        }
+        if (overflow)
+            atomicOr(&C.err, ERR_NEIGHBOR_OVERFLOW);
+    }
+    for (int k = 0; k < cnt + tcnt; k++)
         B.nl[(size_t)k * P.Np + s] = tj[k];
     // walls the sphere can touch before the next rebuild: it moves less than skin/2 until then (walls only move
     // through dem_b200_set_wall_velocity, which requests a rebuild)
@@ -642,7 +818,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                 wc |= 1u << w;
         }
     }
-    B.ncnt[s] = (unsigned)cnt | (wc << 8);
+    B.ncnt[s] = (unsigned)cnt | (wc << 8) | ((unsigned)tcnt << 24);
     // staged history -> slots of the new list (a record whose partner is no longer a candidate is dropped: that
     // contact has broken)
     if (B.hist) {
@@ -654,15 +830,15 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
             const unsigned key = rec_key(r.w);
             r.w = (double)rec_steps(r.w);  // in the candidate slots the 4th component is the step count as a double
             size_t di;
-            if (key < P.shape_base) {
+            if (key < (unsigned)P.nW) {
                 di = (size_t)(P.Kn + key) * P.Np + s;
                 wmask |= 1u << key;
             } else {
-                const unsigned ps = key - P.shape_base;
+                const unsigned ps = key - P.shape_base;  // triangles: wraps, as stored in ts[]
                 int k = 0;
-                while (k < cnt && ts[k] != ps)
+                while (k < cnt + tcnt && ts[k] != ps)
                     k++;
-                if (k == cnt)
+                if (k == cnt + tcnt)
                     continue;
                 di = (size_t)k * P.Np + s;
                 amask |= 1ull << k;
@@ -1054,6 +1230,155 @@ __device__ __forceinline__ bool zcyl_sphere_dev(const Wall& W, V3 pos2, double r
     return true;
 }
 
+// snap_to_triangle (ChCollisionUtilsPRIMS.cpp:41-106) and triangle_sphere (ChNarrowphasePRIMS.cpp:379-437), rounding
+// pinned: the hit / no-hit decision defines the contact-pair set and must not depend on FMA contraction.
+__device__ __forceinline__ bool snap_to_triangle_rn(V3 A, V3 Bv, V3 Cv, V3 Pp, V3& res) {
+    const V3 AB = sub_rn(Bv, A), AC = sub_rn(Cv, A), AP = sub_rn(Pp, A);
+    const double d1 = dot_rn(AB, AP), d2 = dot_rn(AC, AP);
+    if (d1 <= 0 && d2 <= 0) { res = A; return true; }
+    const V3 BP = sub_rn(Pp, Bv);
+    const double d3 = dot_rn(AB, BP), d4 = dot_rn(AC, BP);
+    if (d3 >= 0 && d4 <= d3) { res = Bv; return true; }
+    const double vc = __dsub_rn(__dmul_rn(d1, d4), __dmul_rn(d3, d2));
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+        res = add_rn(A, scale_rn(__ddiv_rn(d1, __dsub_rn(d1, d3)), AB));
+        return true;
+    }
+    const V3 CP = sub_rn(Pp, Cv);
+    const double d5 = dot_rn(AB, CP), d6 = dot_rn(AC, CP);
+    if (d6 >= 0 && d5 <= d6) { res = Cv; return true; }
+    const double vb = __dsub_rn(__dmul_rn(d5, d2), __dmul_rn(d1, d6));
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+        res = add_rn(A, scale_rn(__ddiv_rn(d2, __dsub_rn(d2, d6)), AC));
+        return true;
+    }
+    const double va = __dsub_rn(__dmul_rn(d3, d6), __dmul_rn(d5, d4));
+    const double e43 = __dsub_rn(d4, d3), e56 = __dsub_rn(d5, d6);
+    if (va <= 0 && e43 >= 0 && e56 >= 0) {
+        res = add_rn(Bv, scale_rn(__ddiv_rn(e43, __dadd_rn(e43, e56)), sub_rn(Cv, Bv)));
+        return true;
+    }
+    const double denom = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(va, vb), vc));
+    res = add_rn(add_rn(A, scale_rn(__dmul_rn(vb, denom), AB)), scale_rn(__dmul_rn(vc, denom), AC));
+    return false;
+}
+
+__device__ __forceinline__ bool triangle_sphere_dev(V3 A, V3 Bv, V3 Cv, V3 pos2, double r2, Geom& g) {
+    const V3 nx = cross_rn(sub_rn(Bv, A), sub_rn(Cv, A));  // triangle_normal, ChCollisionUtils.h:467-474
+    const V3 nrm = div_rn(nx, sqrt(dot_rn(nx, nx)));
+    const double h = dot_rn(sub_rn(pos2, A), nrm);
+    if (h >= r2 || h <= 0)  // one-sided
+        return false;
+    V3 face;
+    if (snap_to_triangle_rn(A, Bv, Cv, pos2, face)) {
+        const V3 delta = sub_rn(pos2, face);
+        const double dist2 = dot_rn(delta, delta);
+        if (dist2 >= __dmul_rn(r2, r2) || dist2 <= (double)1e-12f)
+            return false;
+        const double dist = sqrt(dist2);
+        g.n = div_rn(delta, dist);
+        g.depth = __dsub_rn(dist, r2);
+        g.erad = r2 * 0.1 / (r2 + 0.1);
+    } else {
+        g.n = nrm;
+        g.depth = __dsub_rn(h, r2);
+        g.erad = r2;
+    }
+    g.pt1 = face;
+    g.pt2 = sub_rn(pos2, scale_rn(r2, g.n));
+    return true;
+}
+
+// Sphere against the mesh triangles of its candidate list (slots first .. first+tc-1).  Body 1 = mesh body (lower id),
+// body 2 = the sphere, exactly like a wall contact; every (sphere, triangle) pair is a contact of its own with its own
+// history slot, as in Multicore (one shape per triangle).  The wrench on the mesh (force, torque about the body
+// origin; reference: 6 atomics per contact, ChDemSMCtrimesh.cu:383-389) is summed over the lanes of the warp that hit
+// the same mesh before it goes to memory.  Kept out of line: spheres near a mesh are a surface population.
+struct MeshOut {
+    V3 F, T;
+    unsigned long long mask;
+    unsigned n;
+};
+
+template <bool HIST, bool ROLL, bool REC>
+__device__ __noinline__ void mesh_contacts(const Params& P, const Buffers& B, unsigned s, unsigned sid, double4 me, V3 v,
+                                           V3 w, double my_mass, unsigned first, unsigned tc,
+                                           unsigned long long amask_old, MeshOut& out) {
+    MeshSet& MS = *B.meshes;
+    Ctrl& C = *B.ctrl;
+    out.F = mk(0, 0, 0);
+    out.T = mk(0, 0, 0);
+    out.mask = 0ull;
+    out.n = 0;
+    if (!MS.enabled)
+        return;
+    const V3 mpos = mk(me.x, me.y, me.z);
+    double4* const hcol = HIST ? B.hist + s : nullptr;
+    double* const rcol = (HIST && B.hrel) ? B.hrel + s : nullptr;
+    for (unsigned k = 0; k < tc; k++) {
+        const unsigned slot = first + k;
+        const size_t hi = (size_t)slot * P.Np;
+        const unsigned t = B.nl[hi + s] & ~kTriFlag;
+        const double* tw = B.tri_w + 9 * (size_t)t;
+        Geom g;
+        if (!triangle_sphere_dev(mk(tw[0], tw[1], tw[2]), mk(tw[3], tw[4], tw[5]), mk(tw[6], tw[7], tw[8]), mpos, me.w, g))
+            continue;
+        out.n++;
+        if (REC) {
+            unsigned long long at = atomicAdd(&C.pair_count, 1ull);
+            if (at < B.pair_cap)
+                B.pairs[at] = ((unsigned long long)((unsigned)P.nW + t) << 32) | (unsigned long long)(P.shape_base + sid);
+        }
+        if (g.depth >= 0)
+            continue;
+        const int m = (int)B.tri_mesh[t];
+        const MeshBody& M = MS.m[m];
+        Hist h{mk(0, 0, 0), 0.0, 0.0, true};
+        double steps = 0.0;
+        if (HIST && ((amask_old >> slot) & 1ull)) {
+            const double4 r = hcol[hi];
+            h.disp = mk(r.x, r.y, r.z);
+            steps = r.w;
+            h.dur = steps * P.dt;
+            if (rcol)
+                h.relvel0 = rcol[hi];
+            h.isnew = false;
+            steps += 1.0;
+        }
+        Body b1{mk(M.pos[0], M.pos[1], M.pos[2]), mk(M.vel[0], M.vel[1], M.vel[2]), mk(M.omg[0], M.omg[1], M.omg[2]), M.mass};
+        Body b2{mpos, v, w, my_mass};
+        V3 F, T1, T2;
+        contact_force<HIST, ROLL>(P, P.comp[2], b1, b2, g, h, F, T1, T2);
+        out.F = out.F + F;
+        out.T = out.T + T2;
+        if (HIST) {
+            hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, steps);
+            if (rcol)
+                rcol[hi] = h.relvel0;
+            out.mask |= 1ull << slot;
+        }
+        // wrench on the mesh: -F at pt1; T1 is the torque about the body origin
+        double wv[6] = {-F.x, -F.y, -F.z, T1.x, T1.y, T1.z};
+        const unsigned peers = __match_any_sync(__activemask(), m);
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned leader = (unsigned)__ffs(peers) - 1u;
+        for (unsigned rem = peers & ~(1u << leader); rem; rem &= rem - 1) {
+            const int srcl = __ffs(rem) - 1;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const double o = __shfl_sync(peers, wv[c], srcl);
+                if (lane == leader)
+                    wv[c] += o;
+            }
+        }
+        if (lane == leader) {
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                atomicAdd(&MS.wrench[m][c], wv[c]);
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // fused narrowphase + force + integrate.  One thread per sphere in storage (cell) order.
 // --------------------------------------------------------------------------------------------
@@ -1062,7 +1387,7 @@ constexpr int kForceThreads = 128;
 #define DEMB200_FORCE_MINBLOCKS 4
 #endif
 
-template <bool HIST, bool ROLL, bool FAST, bool REC>
+template <bool HIST, bool ROLL, bool FAST, bool REC, bool MESH>
 __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
                                                                       const __grid_constant__ Buffers B) {
     __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
@@ -1081,6 +1406,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
     mv.v = mk(0, 0, 0); mv.w = mk(0, 0, 0); mv.sid = 0; mv.meta = 0; mv.amask = 0ull;
     int cnt = 0;
     unsigned wcand = 0;  // walls this sphere can reach before the next rebuild (k_build_list)
+    unsigned tfirst = 0, tcand = 0;  // mesh triangles in reach: candidate slots tfirst .. tfirst + tcand - 1
     if (valid) {
         me = pos_in[s];
         mv = load_vel(vel_in, s);
@@ -1097,7 +1423,11 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
         }
         const unsigned ncw = B.ncnt[s];
         const unsigned nc = ncw & 0xFFu;
-        wcand = ncw >> 8;
+        wcand = (ncw >> 8) & 0xFFFFu;
+        if (MESH) {
+            tfirst = nc;
+            tcand = ncw >> 24;
+        }
         const uint32_t* __restrict__ nl = B.nl + s;
         // batches of 4 candidates: the ids of the next batch and the 4 positions of this batch are in flight together
         unsigned jn[4];
@@ -1218,6 +1548,15 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
                 wmask_new |= 1u << w;
             }
         }
+    }
+
+    if (MESH && tcand && !ghost) {
+        MeshOut mo;
+        mesh_contacts<HIST, ROLL, REC>(P, B, s, sid, me, mv.v, mv.w, my_mass, tfirst, tcand, amask_old, mo);
+        Fsum = Fsum + mo.F;
+        Tsum = Tsum + mo.T;
+        amask_new |= mo.mask;
+        ncontacts += mo.n;
     }
 
     // ---- phase 2: all lanes evaluate their k-th sphere contact together (contacts are in stable-id order).
@@ -1466,7 +1805,7 @@ __device__ __forceinline__ unsigned walk_history(const Params& P, const Buffers&
         if (cnt < (unsigned)P.K) {
             const unsigned jo = B.nl[si];
             double4 r = B.hist[si];
-            r.w = pack_key(P.shape_base + vel_old[jo].sid, (unsigned)r.w);
+            r.w = pack_key((jo & kTriFlag) ? (unsigned)P.nW + (jo & ~kTriFlag) : P.shape_base + vel_old[jo].sid, (unsigned)r.w);
             emit(cnt, r, B.hrel ? B.hrel[si] : 0.0);
         }
         cnt++;

@@ -8,6 +8,8 @@
 //   nl   : uint32[Kn][Np] column-major Verlet candidate list (storage slots of spheres within r_i+r_j+skin at the
 //          last rebuild), each sphere's entries sorted by the partner's stable id so the summation order -- and
 //          therefore every bit of the result -- does not depend on storage order, rebuild cadence or partition.
+//          Mesh triangles within reach follow the sphere candidates in the same list (kTriFlag | triangle index,
+//          ascending), so a sphere-triangle contact owns a history slot and a live bit exactly like a sphere pair.
 //   hist : double4[Kn + nW][Np] column-major, ONE RECORD PER CANDIDATE SLOT (slot k of sphere s at k*Np + s, wall w
 //          at (Kn+w)*Np + s): tangential displacement of that contact in canonical orientation (as stored by the
 //          higher shape id, ChIterativeSolverMulticoreSMC.cpp:233-243) + steps in contact.  A 64-bit mask in the
@@ -27,13 +29,16 @@ constexpr int kMaxWalls = 16;
 constexpr unsigned kEmptyKey = 0xFFFFFFFFu;
 constexpr int kMaxSlots = 32;      // upper bound of K = simultaneous contacts of one sphere, walls included
 constexpr int kMaxNeighbors = 64;  // upper bound of Verlet candidate slots Kn (live mask is 64 bits)
+constexpr int kMaxMeshes = 16;     // triangle-mesh bodies (ChSystemDemMesh::AddMesh)
+constexpr unsigned kTriFlag = 0x80000000u;  // candidate-list entry = triangle (index in the low bits), not a sphere slot
 
 // device error bits (dem_b200 error codes are derived from these at sync points)
 enum : unsigned {
     ERR_HISTORY_OVERFLOW = 4u,
     ERR_NEIGHBOR_OVERFLOW = 8u,
     ERR_NAN = 16u,
-    ERR_PAIR_CAPACITY = 32u
+    ERR_PAIR_CAPACITY = 32u,
+    ERR_MESH_CAPACITY = 64u
 };
 
 enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1, WALL_ZCYL = 2 };
@@ -64,6 +69,24 @@ struct WallSet {
     int has_bb;
 };
 
+// One triangle-mesh body (Chrono::Dem "family"): rigid-body frame and velocity set by ApplyMeshMotion
+// (src/chrono_dem/physics/ChSystemDem.cpp:1527-1561); triangles [tri_begin, tri_end) of the soup belong to it.
+struct MeshBody {
+    double pos[3], rot[4];   // body frame (w,x,y,z)
+    double vel[3], omg[3];   // linear / angular velocity, world frame
+    double mass;             // enters m_eff like any Multicore body mass
+    unsigned tri_begin, tri_end;
+};
+
+// All meshes in one device block (moves without touching the CUDA graph, like WallSet).
+struct MeshSet {
+    MeshBody m[kMaxMeshes];
+    unsigned long long bb[kMaxMeshes][6];  // order-preserving encoded world AABB of each mesh's triangles
+    double wrench[kMaxMeshes][6];          // force and torque (about the body origin, world frame) of the last step
+    int n;
+    int enabled;                           // EnableMeshCollision
+};
+
 struct Params {
     unsigned N;   // spheres
     unsigned Np;  // N rounded up to a multiple of 32: pitch of the column-major arrays
@@ -82,6 +105,8 @@ struct Params {
     unsigned cell_cap;    // capacity of the search-cell arrays
     int track_wall_forces;  // accumulate the reaction force on every wall (GetBCReactionForces)
     int external_rebuild;   // slab mode: rebuilds happen only when the host asks (all ranks at the same step)
+    unsigned nT;            // mesh triangles (shape ids nW .. nW + nT - 1; spheres follow: shape_base = nW + nT)
+    unsigned tri_cap;       // capacity of the (search cell, triangle) pair list
 };
 
 constexpr unsigned FLAG_FIXED = 1u;
@@ -159,6 +184,11 @@ struct Buffers {
     double* recF; double* recT;      // by sid, 3 each
     unsigned long long* pairs; unsigned long long pair_cap;
     int* gmin; int* gmax;            // by sid, 3 each: Multicore HashMin / HashMax of the sphere AABB
+    // triangle meshes: soup in the body frame and in the world frame (9 doubles per triangle: A, B, C), owner mesh,
+    // and the CSR "triangles reaching search cell c" of the last rebuild
+    MeshSet* meshes;
+    double* tri_loc; double* tri_w; uint32_t* tri_mesh;
+    uint32_t* tcell_count; uint32_t* tcell_start; uint32_t* tblock_sums; uint32_t* tcell_tri;
 };
 
 }  // namespace demb200

@@ -87,6 +87,11 @@ def lib():
         L.dem_b200_time.restype = C.c_double
         L.dem_b200_time.argtypes = [C.c_void_p]
         L.dem_b200_num_walls.argtypes = [C.c_void_p]
+        L.dem_b200_num_triangles.restype = C.c_size_t
+        L.dem_b200_num_triangles.argtypes = [C.c_void_p]
+        L.dem_b200_add_mesh.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_double]
+        L.dem_b200_set_mesh_motion.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 4
+        L.dem_b200_mesh_wrench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -149,6 +154,27 @@ class DemSystem:
     def add_plane_wall(self, pos, normal):
         p, nrm = _f64(pos), _f64(normal)
         return self._ck(self.L.dem_b200_add_plane_wall(self.h, _dp(p), _dp(nrm)))
+
+    # ---- triangle meshes (ChSystemDemMesh) ----
+    def add_mesh(self, verts9, mass=0.0):
+        v = _f64(verts9, (-1, 9))
+        return self._ck(self.L.dem_b200_add_mesh(self.h, C.c_size_t(v.shape[0]), _dp(v), C.c_double(mass)))
+
+    def set_mesh_motion(self, mesh, pos=None, rot=None, lin_vel=None, ang_vel=None):
+        a = [_f64(x) if x is not None else None for x in (pos, rot, lin_vel, ang_vel)]
+        self._ck(self.L.dem_b200_set_mesh_motion(self.h, int(mesh), *[_dp(x) for x in a]))
+
+    def enable_mesh_collision(self, enabled=True):
+        self._ck(self.L.dem_b200_enable_mesh_collision(self.h, int(enabled)))
+
+    def mesh_wrench(self, mesh):
+        f, t = np.empty(3), np.empty(3)
+        self._ck(self.L.dem_b200_mesh_wrench(self.h, int(mesh), _dp(f), _dp(t)))
+        return f, t
+
+    @property
+    def num_triangles(self):
+        return self.L.dem_b200_num_triangles(self.h)
 
     def initialize(self):
         self._ck(self.L.dem_b200_initialize(self.h))

@@ -101,3 +101,74 @@ def settling_scene(n_target, radius=0.02, box_xy=None, seed=12345, jitter=0.005,
     bins = np.maximum(1, np.floor(ext / (bin_factor * rmax * 1.0001)).astype(np.int64))
     return dict(pos=np.ascontiguousarray(pts), radius=rad, box_size=size, walls=walls,
                 bins=tuple(int(b) for b in bins), n=n_target)
+
+
+def quat_from_axis_angle(axis, angle):
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    return np.concatenate([[math.cos(angle / 2)], math.sin(angle / 2) * a])
+
+
+def quat_rotate(v, q):
+    """Rotate (src/chrono/multicore_math/real4.cpp:158-161) for an array of vectors and one quaternion (w,x,y,z)."""
+    v = np.asarray(v, dtype=np.float64)
+    u = np.asarray(q[1:], dtype=np.float64)
+    t = 2 * np.cross(u, v)
+    return v + q[0] * t + np.cross(u, t)
+
+
+def heightfield_mesh(x0, x1, y0, y1, nx, ny, z_fn, flip=False):
+    """Triangulated height field z = z_fn(x, y) over [x0,x1] x [y0,y1] with nx x ny cells: (2 nx ny, 9) vertices.
+    Winding: (B-A) x (C-A) points to +z (the side Multicore's one-sided triangle_sphere collides on) unless flip."""
+    xs = np.linspace(x0, x1, nx + 1)
+    ys = np.linspace(y0, y1, ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    Z = z_fn(X, Y)
+    P = np.stack([X, Y, Z], axis=-1)
+    a, b, c, d = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
+    t1 = np.concatenate([a, b, c], axis=-1).reshape(-1, 9)
+    t2 = np.concatenate([a, c, d], axis=-1).reshape(-1, 9)
+    tri = np.concatenate([t1, t2], axis=0)
+    if flip:
+        tri = tri.reshape(-1, 3, 3)[:, [0, 2, 1], :].reshape(-1, 9)
+    return np.ascontiguousarray(tri)
+
+
+def mesh_to_body_frame(tri_world, pos, rot):
+    """World-frame triangles -> frame of a body at (pos, rot): v_loc = RotateT(v - pos, rot)."""
+    q = np.asarray(rot, dtype=np.float64)
+    qc = np.concatenate([q[:1], -q[1:]])
+    v = np.asarray(tri_world, dtype=np.float64).reshape(-1, 3) - np.asarray(pos, dtype=np.float64)
+    return np.ascontiguousarray(quat_rotate(v, qc).reshape(-1, 9))
+
+
+def cylinder_drum_mesh(radius, length, n_seg, axis=1, caps=True):
+    """Closed cylinder (the drum of BASELINE configs[3]) seen from inside: normals point to the axis.  Axis y (axis=1)
+    by default, centred at the origin.  n_seg segments around, 2 triangles each, + 2 n_seg cap triangles."""
+    th = np.linspace(0.0, 2 * math.pi, n_seg + 1)
+    c, s_ = np.cos(th), np.sin(th)
+    h = length / 2
+    tris = []
+
+    def P(i, yy):
+        return [radius * c[i], yy, radius * s_[i]]
+
+    for i in range(n_seg):
+        a, b, cc, d = P(i, -h), P(i + 1, -h), P(i + 1, h), P(i, h)
+        # inward normal: for axis y the outward radial is (cos, 0, sin); choose winding by test below
+        tris.append(a + cc + b)
+        tris.append(a + d + cc)
+        if caps:
+            tris.append([0, -h, 0] + P(i, -h) + P(i + 1, -h))   # normal +y (into the drum) checked below
+            tris.append([0, h, 0] + P(i + 1, h) + P(i, h))      # normal -y
+    tri = np.asarray(tris, dtype=np.float64).reshape(-1, 3, 3)
+    # make every normal point towards the drum centre
+    n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    cen = tri.mean(axis=1)
+    wrong = np.einsum("ij,ij->i", n, -cen) < 0
+    tri[wrong] = tri[wrong][:, [0, 2, 1], :]
+    if axis != 1:
+        perm = {0: [1, 0, 2], 2: [0, 2, 1]}[axis]
+        tri = tri[:, :, perm]
+        tri = tri[:, [0, 2, 1], :]  # a coordinate swap mirrors the winding
+    return np.ascontiguousarray(tri.reshape(-1, 9))

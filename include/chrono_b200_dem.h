@@ -35,7 +35,7 @@ enum {
     DEMB200_EGRID = -3,    /* reserved (the search grid adapts itself; kept for ABI stability) */
     DEMB200_EHISTORY = -4, /* a sphere has more simultaneous contacts than history_slots */
     DEMB200_ENAN = -5,     /* non-finite state detected */
-    DEMB200_ECAPACITY = -6, /* a recording buffer (pairs) overflowed */
+    DEMB200_ECAPACITY = -6, /* a recording buffer (pairs) or the mesh cell list overflowed */
     DEMB200_ENEIGHBORS = -7 /* a sphere has more neighbour candidates than neighbor_slots */
 };
 
@@ -119,6 +119,24 @@ typedef struct dem_b200_contact_class {
     double kn, kt, gn, gt;        /* used when !use_mat_props (Multicore convention) */
 } dem_b200_contact_class;
 int dem_b200_set_contact_class(dem_b200_system* s, int cls, const dem_b200_contact_class* c);
+
+/* ---- triangle meshes -- ChSystemDemMesh (src/chrono_dem/physics/ChSystemDem.h:398-523) ------------------------
+ * A mesh is a rigid body carrying one Multicore triangle shape per facet (ChNarrowphasePRIMS.cpp:379-437
+ * triangle_sphere: one-sided, the outside is where (B-A)x(C-A) points).  Shape ids: walls 0..nW-1, then the triangles
+ * of all meshes in insertion order, then the spheres.  All meshes must be added before initialize. */
+/* AddMesh (ChSystemDem.h:413): ntri triangles, 9 doubles each (A, B, C in the mesh frame); mass enters m_eff
+ * (<= 0 -> cfg.mesh_mass).  Returns the mesh id (>= 0) or an error. */
+int dem_b200_add_mesh(dem_b200_system* s, size_t ntri, const double* verts9, double mass);
+int dem_b200_num_meshes(const dem_b200_system* s);
+size_t dem_b200_num_triangles(const dem_b200_system* s);
+/* ApplyMeshMotion (ChSystemDem.h:436, ChSystemDem.cpp:627-630): frame position, orientation (w,x,y,z), linear and
+ * angular velocity in the world frame.  Any pointer may be NULL (unchanged).  Legal between steps; asynchronous. */
+int dem_b200_set_mesh_motion(dem_b200_system* s, int mesh, const double pos[3], const double rot[4],
+                             const double lin_vel[3], const double ang_vel[3]);
+int dem_b200_enable_mesh_collision(dem_b200_system* s, int enabled); /* EnableMeshCollision (ChSystemDem.h:430) */
+/* CollectMeshContactForces (ChSystemDem.h:493-496, ChSystemDem.cpp:1752-1766): force on the mesh and torque about its
+ * frame origin (world frame) exerted by the spheres during the last step. */
+int dem_b200_mesh_wrench(dem_b200_system* s, int mesh, double force[3], double torque[3]);
 
 /* ---- run -- ChSystemDem::Initialize / AdvanceSimulation --------------------------------------------------- */
 int dem_b200_initialize(dem_b200_system* s);

@@ -20,6 +20,7 @@
 #include "chrono/core/ChMatrix33.h"
 #include "chrono/core/ChQuaternion.h"
 #include "chrono/core/ChVector3.h"
+#include "chrono/geometry/ChTriangleMeshConnected.h"
 #include "chrono_dem/ChApiDem.h"
 #include "chrono_dem/ChDemDefines.h"
 
@@ -155,12 +156,79 @@ class CH_DEM_API ChSystemDem {
     float m_RTF;  // real-time factor
 };
 
+// -----------------------------------------------------------------------------
+
+/// Interface to a Chrono::Dem mesh system (reference: src/chrono_dem/physics/ChSystemDem.h:398-523).
+/// Meshes are rigid bodies carrying one triangle shape per facet; contact follows Chrono::Multicore's
+/// triangle_sphere (ChNarrowphasePRIMS.cpp:379-437), which is one-sided.  Chrono::Dem's own test is two-sided
+/// (ChDemCollision.cuh:145); to keep that behaviour for existing callers every facet is registered with
+/// both windings unless SetMeshTwoSided(false) is called (additive API).
+class CH_DEM_API ChSystemDemMesh : public ChSystemDem {
+  public:
+    ChSystemDemMesh(float sphere_rad, float density, const ChVector3f& boxDims, ChVector3f O = ChVector3f(0));
+    ChSystemDemMesh(const std::string& checkpoint);
+    ~ChSystemDemMesh();
+
+    unsigned int AddMesh(std::shared_ptr<ChTriangleMeshConnected> mesh, float mass);
+    unsigned int AddMesh(const std::string& filename, const ChVector3f& translation, const ChMatrix33<float>& rotscale, float mass);
+    std::vector<unsigned int> AddMeshes(const std::vector<std::string>& objfilenames,
+                                        const std::vector<ChVector3f>& translations,
+                                        const std::vector<ChMatrix33<float>>& rotscales,
+                                        const std::vector<float>& masses);
+    void EnableMeshCollision(bool val);
+    void UseMeshNormals(bool val) { use_mesh_normals = val; }
+    /// Additive: false = facets collide only on the side (B-A)x(C-A) points to (Multicore semantics); default true.
+    void SetMeshTwoSided(bool val) { m_two_sided = val; }
+    void ApplyMeshMotion(unsigned int mesh_id, const ChVector3d& pos, const ChQuaternion<>& rot, const ChVector3d& lin_vel,
+                         const ChVector3d& ang_vel);
+    unsigned int GetNumMeshes() const;
+    std::shared_ptr<ChTriangleMeshConnected> GetMesh(unsigned int mesh_id) const { return m_meshes[mesh_id]; }
+    float GetMeshMass(unsigned int mesh_id) const { return m_mesh_masses[mesh_id]; }
+
+    void SetStaticFrictionCoeff_SPH2MESH(float mu);
+    void SetRollingCoeff_SPH2MESH(float mu);
+    void SetSpinningCoeff_SPH2MESH(float mu);
+    void SetKn_SPH2MESH(double someValue);
+    void SetGn_SPH2MESH(double someValue);
+    void SetKt_SPH2MESH(double someValue);
+    void SetGt_SPH2MESH(double someValue);
+    void UseMaterialBasedModel(bool val);
+    void SetYoungModulus_MESH(double someValue);
+    void SetPoissonRatio_MESH(double someValue);
+    void SetRestitution_MESH(double someValue);
+    void SetAdhesionRatio_SPH2MESH(float someValue);
+    void SetMeshVerbosity(CHDEM_MESH_VERBOSITY level) { mesh_verbosity = level; }
+
+    virtual void Initialize() override;
+    void InitializeMeshes();
+    virtual double AdvanceSimulation(float duration) override;
+
+    void CollectMeshContactForces(std::vector<ChVector3d>& forces, std::vector<ChVector3d>& torques);
+    void CollectMeshContactForces(int mesh, ChVector3d& force, ChVector3d& torque);
+
+    void ReadCheckpointFile(const std::string& infilename, bool overwrite = false);
+    void WriteCheckpointFile(const std::string& outfilename);
+    void WriteMesh(const std::string& outfilename, unsigned int i) const;
+    void WriteMeshes(const std::string& outfilename) const;
+
+  private:
+    void SetMeshes();
+    CHDEM_MESH_VERBOSITY mesh_verbosity = CHDEM_MESH_VERBOSITY::QUIET;
+    std::vector<std::shared_ptr<ChTriangleMeshConnected>> m_meshes;
+    std::vector<float> m_mesh_masses;
+    bool use_mesh_normals = false;
+    bool m_two_sided = true;
+    virtual bool SetParamsFromIdentifier(const std::string& identifier, std::istringstream& iss1, bool overwrite) override;
+    void WriteCheckpointMeshParams(std::ofstream& cpFile) const;
+};
+
 }  // namespace dem
 
 // The module was called Chrono::Gpu before the rename; the checkpoint fixture and the CHANGELOG still use that name
 // (data/testing/dem/pyramid_checkpoint.dat:1, CHANGELOG.md:3584-3704).
 namespace gpu {
 using ChSystemGpu = ::chrono::dem::ChSystemDem;
+using ChSystemGpuMesh = ::chrono::dem::ChSystemDemMesh;
 }
 }  // namespace chrono
 #endif

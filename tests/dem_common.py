@@ -18,7 +18,7 @@ def settling_material(mu=0.4, cr=0.4, young=2e6, mu_roll=0.0, mu_spin=0.0, adhes
     return dict(young=young, poisson=0.3, mu_s=mu, mu_roll=mu_roll, mu_spin=mu_spin, cr=cr, adhesion=adhesion)
 
 
-def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
+def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
                 num_threads=0, history_slots=None, integrator=None, **model):
     mat = mat or settling_material()
     s = po.make_settings(dt=dt, bins=scene["bins"], gravity=gravity, num_threads=num_threads, **model)
@@ -30,24 +30,42 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None
         o.add_body(wall_mass, (1, 1, 1), (0, 0, 0), fixed=True)
         for p, h in scene["walls"]:
             o.add_box(0, m_w, p, h)
+    # mesh bodies follow the container and precede the spheres: triangle shapes nW .. nW+nT-1 (one per facet)
+    o.mesh_bodies = []
+    if scene.get("meshes"):
+        from chrono_b200 import scenes as _sc
+        m_m = o.add_material(po.make_material(**(mesh_mat or mat)))
+        for M in scene["meshes"]:
+            q = np.asarray(M.get("rot", (1, 0, 0, 0)), dtype=np.float64)
+            qc = np.concatenate([q[:1], -q[1:]])
+            om_loc = _sc.quat_rotate(np.asarray(M.get("omega", (0, 0, 0)), dtype=np.float64), qc)
+            b = o.add_body(M.get("mass", 1.0), (1, 1, 1), M.get("pos", (0, 0, 0)), rot=q, vel=M.get("vel", (0, 0, 0)),
+                           omega=om_loc, fixed=True)
+            o.add_triangles(b, m_m, M["tri"])
+            o.mesh_bodies.append(b)
     first = o.add_spheres(scene["pos"], scene["radius"], sphere_mass(scene["radius"]), m_s, vel=vel, omega=omega)
     o.first_sphere_body = first
     o.num_walls = len(scene["walls"])
+    o.num_triangles = sum(len(M["tri"]) for M in scene.get("meshes", []))
     return o
 
 
-def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
+def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
              integrator=None, history_slots=16, device=0, **model):
     from chrono_b200 import dem
     mat = mat or settling_material()
     kw = dict(model)
     cfg = dem.config(device=device, dt=dt, bins=scene["bins"], gravity=gravity, mat_sphere=dem.material(**mat),
-                     mat_wall=dem.material(**(wall_mat or mat)), mass_coef=MASS_COEF, wall_mass=wall_mass,
+                     mat_wall=dem.material(**(wall_mat or mat)), mat_mesh=dem.material(**(mesh_mat or mat)),
+                     mass_coef=MASS_COEF, wall_mass=wall_mass,
                      integrator=dem.CENTERED_DIFFERENCE if integrator is None else integrator,
                      history_slots=history_slots, **kw)
     g = dem.DemSystem(cfg)
     for p, h in scene["walls"]:
         g.add_box_wall(p, h)
+    for M in scene.get("meshes", []):
+        m = g.add_mesh(M["tri"], M.get("mass", 1.0))
+        g.set_mesh_motion(m, M.get("pos"), M.get("rot"), M.get("vel"), M.get("omega"))
     g.set_spheres(scene["pos"], scene["radius"], vel=vel, omega=omega)
     g.initialize()
     return g

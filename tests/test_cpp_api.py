@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "cpp", "_bin")
-PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api"]
+PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling"]
 
 
 def build_program(name):
@@ -56,6 +56,13 @@ def test_dem_frictionrolling():
 @pytest.mark.parametrize("mode", ["hold", "collapse"])
 def test_dem_pyramid_from_reference_checkpoint(mode):
     run("utest_DEM_pyramid", os.path.join(HERE, "golden", "pyramid_checkpoint.dat"), mode)
+
+
+@pytest.mark.gpu
+def test_dem_meshrolling_and_cosim_wrench(tmp_path):
+    """utest_DEM_meshrolling scenario through ChSystemDemMesh + ApplyMeshMotion / CollectMeshContactForces."""
+    out = run("utest_DEM_meshrolling", str(tmp_path))
+    assert "PASSED" in out
 
 
 @pytest.mark.gpu
