@@ -36,6 +36,16 @@ def build_scene(n):
     return scenes.settling_scene(n, radius=RADIUS, sep_factor=2.0, jitter=0.005, seed=12345 + 1)
 
 
+def build_scene_slabs(n_per_gpu, world):
+    """Weak scaling: the single-GPU box stretched `world` times along x (same depth and width of the bed), world * n
+    spheres, cut into `world` slabs of equal sphere count."""
+    from chrono_b200 import scenes
+    one = build_scene(n_per_gpu)
+    Lx, Ly = one["box_size"][0], one["box_size"][1]
+    return scenes.settling_scene(n_per_gpu * world, radius=RADIUS, sep_factor=2.0, jitter=0.005, seed=12345 + 1,
+                                 box_xy=(Lx * world, Ly))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -130,7 +140,121 @@ def workload_config(n, substeps, gpus):
                         "packing at 2R spacing (c_bar~6), R=0.02 rho=2000 Y=2e6 mu=0.4 cr=0.4 h=1e-4" % n,
             "spheres_per_gpu": n, "timesteps_per_step": substeps,
             "l2_policy": "working set (>=300 B/sphere x %d spheres) exceeds the 126 MB L2; no explicit flush" % n,
-            "parallelism": "1 process per GPU" if gpus == 1 else "slab decomposition, %d ranks" % gpus}
+            "parallelism": "1 process per GPU" if gpus == 1 else
+            "slab domain decomposition along x, %d ranks x %d spheres (box %d x as long), NCCL send/recv ghost halo" % (gpus, n, gpus)}
+
+
+def run_slabs(args):
+    """N > 1: slab domain decomposition (chrono_b200/slab.py).  One process per GPU, every rank owns n spheres of a box
+    N times as long; per step: ghost halo (pos, v, omega of the spheres within 2 r_max + skin of a slab face) over NCCL
+    send/recv, the same step graph as on one GPU, a 4-byte all-reduce of "rebuild now?"; spheres migrate at rebuilds."""
+    import torch
+    import torch.distributed as dist
+    from chrono_b200 import dem, slab
+    import dem_common as common
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, S = args.spheres, args.substeps
+    scene = build_scene_slabs(n, world)
+    x = scene["pos"][:, 0]
+    bounds = slab.slab_bounds(x, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    mine = np.nonzero((x >= lo) & (x < hi))[0]
+    mat = common.settling_material()
+    cfg = dem.config(device=local, dt=DT, bins=scene["bins"], mat_sphere=dem.material(**mat), mat_wall=dem.material(**mat),
+                     mass_coef=common.MASS_COEF, wall_mass=1.0, integrator=dem.CENTERED_DIFFERENCE, history_slots=16,
+                     force_model=dem.HERTZ, tangential_mode=dem.TANG_MULTISTEP)
+    g, backend = slab.make_engine_slab(cfg, scene["walls"], scene["pos"][mine], scene["radius"][mine], mine,
+                                       capacity=int(1.15 * len(mine)) + 65536, rmax_global=float(scene["radius"].max()))
+    drv = slab.SlabDriver(backend, rank, world, lo, hi, lag=1)
+    drv.rebuild()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        drv.step(S)
+    drv.drain()
+    g.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    st0 = dict(drv.stats)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        drv.step(S)
+    drv.drain()
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    g.sync()  # device error flags (skin exceeded, overflow, NaN) fail loudly here
+    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    nsteps = args.steps * S
+    value = world * n * nsteps / (ms_total * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- e2e: every bench step the owned state comes from / goes back to pinned host memory
+    sid, p0, v0, w0 = backend.export_owned()
+    n_own = len(sid)
+    bytes_io = int(3 * p0.nbytes)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        drv.step(S)
+        drv.drain()
+        sid, p0, v0, w0 = backend.export_owned()  # D2H of the owned spheres (ids + pos + vel + omega)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * S * e2e_steps / float(te.item())
+
+    halo = torch.tensor([drv.stats["halo_bytes"] - st0["halo_bytes"], drv.stats["migrated"] - st0["migrated"],
+                         drv.stats["rebuilds"] - st0["rebuilds"], n_own], device="cuda", dtype=torch.float64)
+    allh = [torch.zeros_like(halo) for _ in range(world)]
+    dist.all_gather(allh, halo)
+    rows = g.reduce(dem.RED_NUM_CONTACTS)
+    cb = torch.tensor([rows], device="cuda", dtype=torch.float64)
+    dist.all_reduce(cb)
+    cbar = float(cb.item()) / (world * n)
+    hbm, hbm_src = peaks()
+    B_step = 176.0 + 32.0 * cbar
+    if rank == 0:
+        halo_rank_max = max(float(h[0]) for h in allh)
+        line = {
+            "metric": "sphere-steps/sec", "value": value, "unit": "sphere-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n, S, world),
+            "contacts_per_sphere": cbar,
+            "roofline": {"bound": "hbm", "achieved": B_step * (value / world) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": B_step * (value / world) / 1e9 / hbm, "traffic": None, "kernel": "whole step, per GPU",
+                         "peak_source": hbm_src, "algorithmic_bytes_per_sphere": B_step},
+            "halo": {"bytes_received_per_rank_per_timestep": [float(h[0]) / nsteps for h in allh],
+                     "nvlink_GBps_busiest_rank": halo_rank_max / (ms_total * 1e-3) / 1e9, "nvlink_peak_GBps_per_direction": 900.0,
+                     "migrated_spheres": [int(h[1]) for h in allh], "rebuilds": int(allh[0][2]),
+                     "owned_spheres": [int(h[3]) for h in allh], "collectives_per_timestep": "1 x 4-byte all-reduce (rebuild vote)"},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_value, "unit": "sphere-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": bytes_io,
+                    "steps": e2e_steps, "note": "slab mode: owned state read back to the host every bench step; the state stays "
+                                                "resident on the GPUs between steps (uploading it would re-partition the domain)"},
+            "gpu_launches": int(nsteps * (KERNELS_PER_TIMESTEP + 5)),
+            "clocks": sampler.result(), "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -142,6 +266,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not args.replicas:
+        return run_slabs(args)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -253,6 +379,7 @@ def main():
     ap.add_argument("--substeps", type=int, default=100, help="DEM time steps per bench step")
     ap.add_argument("--ref-substeps", type=int, default=2, help="time steps per bench step of the reference arm")
     ap.add_argument("--cpu-steps", type=int, default=4, help="time steps of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of slab decomposition")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

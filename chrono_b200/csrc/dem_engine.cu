@@ -334,6 +334,7 @@ int check_device_error(dem_b200_system* s) {
     if (e & ERR_HISTORY_OVERFLOW) { s->err = "a sphere has more contacts than history_slots"; return DEMB200_EHISTORY; }
     if (e & ERR_NEIGHBOR_OVERFLOW) { s->err = "a sphere has more neighbour candidates than neighbor_slots"; return DEMB200_ENEIGHBORS; }
     if (e & ERR_PAIR_CAPACITY) { s->err = "pair recording buffer overflow"; return DEMB200_ECAPACITY; }
+    if (e & ERR_SKIN_EXCEEDED) { s->err = "slab mode: the Verlet skin was used up before the driver rebuilt the lists"; return DEMB200_EINVAL; }
     if (e & ERR_MESH_CAPACITY) { s->err = "mesh triangles cover more search cells than reserved (triangles much larger than the spheres: subdivide the mesh)"; return DEMB200_ECAPACITY; }
     s->err = "unknown device error";
     return DEMB200_ECUDA;
@@ -1540,13 +1541,14 @@ int dem_b200_mgpu_unpack(dem_b200_system* s, int dir, const void* in_dev) {
     return 0;
 }
 
-int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev) {
-    if (!s || !s->initialized || !s->mgpu || !flag_dev)
+int dem_b200_mgpu_want_rebuild_ahead(dem_b200_system* s, int* flag_dev, int steps_ahead) {
+    if (!s || !s->initialized || !s->mgpu || !flag_dev || steps_ahead < 0)
         return DEMB200_EINVAL;
-    k_mgpu_want<<<1, 32, 0, s->stream>>>(s->P, s->B, flag_dev);
+    k_mgpu_want<<<1, 32, 0, s->stream>>>(s->P, s->B, flag_dev, steps_ahead);
     CU(cudaGetLastError());
     return 0;
 }
+int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev) { return dem_b200_mgpu_want_rebuild_ahead(s, flag_dev, 0); }
 
 int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
                           size_t* n) {

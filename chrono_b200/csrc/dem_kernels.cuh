@@ -191,6 +191,8 @@ __global__ void k_step_begin(Params P, Buffers B) {
     const bool rebuild = (C.need_rebuild != 0) || (!P.external_rebuild && !(C.travel < 0.499 * P.skin));
     if (C.nrebuilds >= 1)
         C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
+    if (P.external_rebuild && !rebuild && !(C.travel < 0.5 * P.skin))
+        atomicOr(&C.err, ERR_SKIN_EXCEEDED);  // the slab driver asked for the rebuild too late: lists may miss contacts
 
     // ---- bounding box of all shapes at the start of this step ----
     double mn[3], mx[3];
@@ -2019,11 +2021,15 @@ __global__ void __launch_bounds__(256) k_mgpu_unpack(Buffers B, int dir, unsigne
     q[2] = make_double2(o[7], o[8]);
 }
 // Would the next step have to rebuild?  (travel so far + the displacement of the step that just ran)
-__global__ void k_mgpu_want(Params P, Buffers B, int* flag_out) {
+// `ahead` = further steps the caller will run before it acts on the answer (a driver that reads the flag one step late
+// passes 1): they are assumed to move the spheres as far as the last step did; k_step_begin traps the case where that
+// assumption fails (ERR_SKIN_EXCEEDED).
+__global__ void k_mgpu_want(Params P, Buffers B, int* flag_out, int ahead) {
     if (threadIdx.x || blockIdx.x)
         return;
     const Ctrl& C = *B.ctrl;
-    const double t = C.travel + sqrt(__longlong_as_double((long long)C.max_dx2));
+    const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
+    const double t = C.travel + dx * (double)(1 + ahead);
     *flag_out = (C.need_rebuild != 0 || !(t < 0.499 * P.skin)) ? 1 : 0;
 }
 // compact export of the owned spheres (any order): sid, pos, vel, omega

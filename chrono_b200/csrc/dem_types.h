@@ -38,7 +38,8 @@ enum : unsigned {
     ERR_NEIGHBOR_OVERFLOW = 8u,
     ERR_NAN = 16u,
     ERR_PAIR_CAPACITY = 32u,
-    ERR_MESH_CAPACITY = 64u
+    ERR_MESH_CAPACITY = 64u,
+    ERR_SKIN_EXCEEDED = 128u
 };
 
 enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1, WALL_ZCYL = 2 };

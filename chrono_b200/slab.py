@@ -33,8 +33,12 @@ def slab_bounds(x_all, world):
 
 
 class SlabDriver:
-    def __init__(self, backend, rank, world, lo, hi, group=None):
+    def __init__(self, backend, rank, world, lo, hi, group=None, lag=0):
+        """lag = 1: the "rebuild now?" answer of step i is read on the host while step i+1 is already enqueued (no host
+        sync in the step loop); the backend then asks one step early (want_rebuild(ahead=1))."""
         self.b, self.rank, self.world, self.lo, self.hi, self.group = backend, rank, world, float(lo), float(hi), group
+        self.lag = int(lag)
+        self._pending = []
         self.left = rank - 1 if rank > 0 else None
         self.right = rank + 1 if rank < world - 1 else None
         self.stats = dict(steps=0, rebuilds=0, halo_bytes=0, migrated=0, ghost_bytes=0)
@@ -126,11 +130,26 @@ class SlabDriver:
                 self.halo()
             self.fresh = False
             self.b.step()
-            flag = self.b.want_rebuild()  # 1-element int32 tensor on the backend's device
+            flag = self.b.want_rebuild(self.lag)  # 1-element int32 tensor on the backend's device
             if self.world > 1:
                 dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
             self.stats["steps"] += 1
-            if int(flag.item()):
+            if not self.lag:
+                if int(flag.item()):
+                    self.rebuild()
+                continue
+            # every rank sees the same all-reduced flags in the same order, so all take the same decision
+            self._pending.append(self.b.flag_to_host_async(flag))
+            if len(self._pending) > self.lag:
+                if self._pending.pop(0)():
+                    self._pending.clear()
+                    self.rebuild()
+
+    def drain(self):
+        """Act on the answers still in flight (call before reading results / at the end of a timed region)."""
+        while self._pending:
+            if self._pending.pop(0)():
+                self._pending.clear()
                 self.rebuild()
 
 
@@ -195,9 +214,26 @@ class EngineBackend:
     def step(self):
         self.g._ck(self.L.dem_b200_step(self.h, 1))
 
-    def want_rebuild(self):
-        self.g._ck(self.L.dem_b200_mgpu_want_rebuild(self.h, C.c_void_p(self.flag.data_ptr())))
+    def want_rebuild(self, ahead=0):
+        self.g._ck(self.L.dem_b200_mgpu_want_rebuild_ahead(self.h, C.c_void_p(self.flag.data_ptr()), int(ahead)))
         return self.flag
+
+    def flag_to_host_async(self, flag):
+        """Copy the (all-reduced) flag to pinned host memory on the current stream; returns a callable that waits for the
+        copy and gives the value."""
+        if not hasattr(self, "_pin"):
+            self._pin = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(8)]
+            self._pin_i = 0
+        h = self._pin[self._pin_i % len(self._pin)]
+        self._pin_i += 1
+        h.copy_(flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def wait():
+            ev.synchronize()
+            return int(h[0])
+        return wait
 
     def export_owned(self):
         cap = self.capacity

@@ -211,6 +211,9 @@ int dem_b200_mgpu_counts(dem_b200_system* s, size_t* n_own, size_t* n_ghost_left
 int dem_b200_mgpu_pack(dem_b200_system* s, int dir, void* out_dev);
 int dem_b200_mgpu_unpack(dem_b200_system* s, int dir, const void* in_dev);
 int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev); /* writes 1/0 to DEVICE memory (for an all-reduce) */
+/* Same for a driver that acts on the answer `steps_ahead` steps late (no host sync per step): those steps are assumed to
+ * move the spheres as far as the last one did; if they move further the next step fails loudly (DEMB200_EINVAL). */
+int dem_b200_mgpu_want_rebuild_ahead(dem_b200_system* s, int* flag_dev, int steps_ahead);
 /* owned spheres (ghosts excluded) in arbitrary order: global id, pos, vel, omega to HOST buffers */
 int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
                           size_t* n);

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spheres", type=int, default=20000)
     ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--lag", type=int, default=0, help="1: read the rebuild vote one step late (no host sync per step)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -53,9 +54,11 @@ def main():
     g, backend = slab.make_engine_slab(cfg, scene["walls"], scene["pos"][mine], scene["radius"][mine], mine, vel=vel[mine],
                                        omega=om[mine], capacity=int(1.6 * len(mine)) + 4096,
                                        rmax_global=float(scene["radius"].max()))
-    drv = slab.SlabDriver(backend, rank, world, lo, hi)
+    drv = slab.SlabDriver(backend, rank, world, lo, hi, lag=args.lag)
     drv.rebuild()
     drv.step(args.steps)
+    drv.drain()
+    g.sync()
     sid, p, v, w = backend.export_owned()
     ok = np.array_equal(p, rp[sid]) and np.array_equal(v, rv[sid]) and np.array_equal(w, rw[sid])
     worst = float(np.abs(p - rp[sid]).max()) if len(sid) else 0.0
