@@ -141,13 +141,13 @@ def workload_config(n, substeps, gpus):
             "spheres_per_gpu": n, "timesteps_per_step": substeps,
             "l2_policy": "working set (>=300 B/sphere x %d spheres) exceeds the 126 MB L2; no explicit flush" % n,
             "parallelism": "1 process per GPU" if gpus == 1 else
-            "slab domain decomposition along x, %d ranks x %d spheres (box %d x as long), NCCL send/recv ghost halo" % (gpus, n, gpus)}
+            "slab domain decomposition along x, %d ranks x %d spheres (box %d x as long), ghost halo over NVLink" % (gpus, n, gpus)}
 
 
 def run_slabs(args):
     """N > 1: slab domain decomposition (chrono_b200/slab.py).  One process per GPU, every rank owns n spheres of a box
     N times as long; per step: ghost halo (pos, v, omega of the spheres within 2 r_max + skin of a slab face) over NCCL
-    send/recv, the same step graph as on one GPU, a 4-byte all-reduce of "rebuild now?"; spheres migrate at rebuilds."""
+    stores, the same step graph as on one GPU, a device-side vote on "rebuild now?"; spheres migrate at rebuilds (NCCL)."""
     import torch
     import torch.distributed as dist
     from chrono_b200 import dem, slab
@@ -167,11 +167,13 @@ def run_slabs(args):
     mat = common.settling_material()
     cfg = dem.config(device=local, dt=DT, bins=scene["bins"], mat_sphere=dem.material(**mat), mat_wall=dem.material(**mat),
                      mass_coef=common.MASS_COEF, wall_mass=1.0, integrator=dem.CENTERED_DIFFERENCE, history_slots=16,
-                     force_model=dem.HERTZ, tangential_mode=dem.TANG_MULTISTEP)
+                     force_model=dem.HERTZ, tangential_mode=dem.TANG_MULTISTEP, verlet_skin=args.skin * RADIUS if args.skin > 0 else -1.0)
     g, backend = slab.make_engine_slab(cfg, scene["walls"], scene["pos"][mine], scene["radius"][mine], mine,
                                        capacity=int(1.15 * len(mine)) + 65536, rmax_global=float(scene["radius"].max()))
     drv = slab.SlabDriver(backend, rank, world, lo, hi, lag=1)
     drv.rebuild()
+    if not args.nccl_halo:
+        drv.enable_p2p(lag=args.slab_lag)
 
     def barrier():
         torch.cuda.synchronize()
@@ -192,8 +194,10 @@ def run_slabs(args):
         drv.step(S)
     drv.drain()
     ev1.record()
+    t_enqueue = time.perf_counter() - t_wall0  # host time to issue the work (close to t_wall = the host is the bottleneck)
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    rebuild_s_timed = drv.stats.get("rebuild_s", 0.0) - st0.get("rebuild_s", 0.0)
     g.sync()  # device error flags (skin exceeded, overflow, NaN) fail loudly here
     t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -221,7 +225,7 @@ def run_slabs(args):
     e2e_value = world * n * S * e2e_steps / float(te.item())
 
     halo = torch.tensor([drv.stats["halo_bytes"] - st0["halo_bytes"], drv.stats["migrated"] - st0["migrated"],
-                         drv.stats["rebuilds"] - st0["rebuilds"], n_own], device="cuda", dtype=torch.float64)
+                         drv.stats["rebuilds"] - st0["rebuilds"], n_own, rebuild_s_timed], device="cuda", dtype=torch.float64)
     allh = [torch.zeros_like(halo) for _ in range(world)]
     dist.all_gather(allh, halo)
     rows = g.reduce(dem.RED_NUM_CONTACTS)
@@ -244,13 +248,16 @@ def run_slabs(args):
             "halo": {"bytes_received_per_rank_per_timestep": [float(h[0]) / nsteps for h in allh],
                      "nvlink_GBps_busiest_rank": halo_rank_max / (ms_total * 1e-3) / 1e9, "nvlink_peak_GBps_per_direction": 900.0,
                      "migrated_spheres": [int(h[1]) for h in allh], "rebuilds": int(allh[0][2]),
-                     "owned_spheres": [int(h[3]) for h in allh], "collectives_per_timestep": "1 x 4-byte all-reduce (rebuild vote)"},
+                     "owned_spheres": [int(h[3]) for h in allh],
+                     "rebuild_ms_total_in_timed_region": [1e3 * float(h[4]) for h in allh],
+                     "ms_per_timestep_outside_rebuilds": (ms_total - 1e3 * max(float(h[4]) for h in allh)) / nsteps, "transport": "NCCL send/recv + 4-byte all-reduce per time step" if args.nccl_halo else
+                     "NVLink peer stores from the pack kernel (CUDA IPC), device-side flags and vote; no collective per time step"},
             "cpu_baseline": None,
             "e2e": {"value": e2e_value, "unit": "sphere-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": bytes_io,
                     "steps": e2e_steps, "note": "slab mode: owned state read back to the host every bench step; the state stays "
                                                 "resident on the GPUs between steps (uploading it would re-partition the domain)"},
             "gpu_launches": int(nsteps * (KERNELS_PER_TIMESTEP + 5)),
-            "clocks": sampler.result(), "wall_s_timed_region": t_wall,
+            "clocks": sampler.result(), "wall_s_timed_region": t_wall, "host_enqueue_s": t_enqueue,
         }
         print(json.dumps(line))
     dist.barrier()
@@ -379,6 +386,9 @@ def main():
     ap.add_argument("--substeps", type=int, default=100, help="DEM time steps per bench step")
     ap.add_argument("--ref-substeps", type=int, default=2, help="time steps per bench step of the reference arm")
     ap.add_argument("--cpu-steps", type=int, default=4, help="time steps of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: NCCL send/recv halo + all-reduce vote instead of P2P stores")
+    ap.add_argument("--slab-lag", type=int, default=2, help="N > 1: steps between casting the rebuild vote and acting on it")
+    ap.add_argument("--skin", type=float, default=0.0, help="N > 1: Verlet skin in sphere radii (0 = engine default 0.25)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of slab decomposition")
     args = ap.parse_args()
     if args.impl == "reference":

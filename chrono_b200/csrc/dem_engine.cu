@@ -44,6 +44,7 @@ struct dem_b200_system {
     bool any_fixed = false;
     bool initialized = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t cap_stream = nullptr;  // graph capture only
     unsigned ntiles = 0;               // scan tiles covering the search-cell capacity
     cudaGraphExec_t graph1 = nullptr;  // one step
     bool recording = false;
@@ -62,6 +63,14 @@ struct dem_b200_system {
     int mg_phase = 0;                  // 0 idle, 1 extracted, 2 ghosts selected
     bool mg_remap_pending = false;
     unsigned* d_count = nullptr;
+    // direct P2P halo (dem_b200_p2p_*)
+    bool p2p = false;
+    P2PDev X{};
+    void* p2p_region = nullptr;          // my exposed region (control block + landing buffers)
+    void* p2p_mapped[kMaxRanks] = {nullptr};  // peers' regions as opened here
+    size_t p2p_records = 0;
+    unsigned long long* h_vote = nullptr;     // pinned, mapped
+    unsigned long long step_no = 0;      // host mirror of Ctrl::nsteps (steps enqueued so far)
     double time = 0.0;
     std::string err;
     // scratch (device, by user index) and pinned host staging
@@ -258,6 +267,17 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
         if (ev)
             cudaEventRecord(ev[k++], st);
     };
+    if (s->p2p && !s->mg_remap_pending) {
+        // ghost halo of this step: my boundary spheres go straight into the neighbours' landing buffers (NVLink stores),
+        // theirs are picked up as soon as their step number shows up.  (Skipped right after a rebuild: the ghosts that
+        // were just exchanged are current.)  Timed with k_step_begin in the profile.
+        for (int d = 0; d < 2; d++)
+            if (s->mg_ns[d])
+                k_p2p_pack<<<(s->mg_ns[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ns[d]);
+        for (int d = 0; d < 2; d++)
+            if (s->mg_ng[d])
+                k_p2p_unpack<<<(s->mg_ng[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ng[d]);
+    }
     mark();
     k_step_begin<<<1, 32, 0, st>>>(P, B);
     mark();
@@ -291,9 +311,12 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
     } else {
         launch_force<false>(s, B, fb);
     }
+    if (s->p2p)
+        k_p2p_vote<<<1, 32, 0, st>>>(P, B, s->X);
     mark();
     CU(cudaGetLastError());
     s->time += P.dt;
+    s->step_no++;
     s->export_valid = false;
     return 0;
 }
@@ -307,11 +330,25 @@ void drop_graph(dem_b200_system* s) {
 
 int build_graph(dem_b200_system* s) {
     cudaGraph_t g = nullptr;
-    CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    // capture on a private stream: the caller's stream may be the legacy default stream (slab mode runs on torch's
+    // current stream), which cannot be captured; the instantiated graph is launched into s->stream
+    if (!s->cap_stream)
+        CU(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t run_stream = s->stream;
+    s->stream = s->cap_stream;
+    cudaError_t e0 = cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e0 != cudaSuccess) {
+        s->stream = run_stream;
+        s->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e0);
+        return DEMB200_ECUDA;
+    }
     double t = s->time;
+    const unsigned long long sn = s->step_no;
     int rc = enqueue_step(s, nullptr);
     s->time = t;  // capturing does not advance time
-    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->step_no = sn;
+    cudaError_t e = cudaStreamEndCapture(s->cap_stream, &g);
+    s->stream = run_stream;
     if (rc)
         return rc;
     if (e != cudaSuccess) {
@@ -374,7 +411,9 @@ int run_steps(dem_b200_system* s, int nsteps) {
         return DEMB200_EINVAL;
     }
     int done = 0;
-    if (!s->recording && !s->mgpu && nsteps >= 2) {
+    // slab mode: the step right after a rebuild runs un-captured (it is followed by the index remap below); the
+    // graph is re-captured after every slab rebuild because the local sphere count (grid sizes) changes
+    if (!s->recording && ((!s->mgpu && nsteps >= 2) || (s->mgpu && !s->mg_remap_pending))) {
         if (!s->graph1) {
             int rc = build_graph(s);
             if (rc)
@@ -383,6 +422,7 @@ int run_steps(dem_b200_system* s, int nsteps) {
         for (; done < nsteps; done++) {
             CU(cudaGraphLaunch(s->graph1, s->stream));
             s->time += s->P.dt;
+            s->step_no++;
         }
         s->export_valid = false;
     }
@@ -455,8 +495,17 @@ void dem_b200_destroy(dem_b200_system* s) {
         cudaFreeHost(s->h_pin);
     if (s->h_mesh_pin)
         cudaFreeHost(s->h_mesh_pin);
+    for (int r = 0; r < kMaxRanks; r++)
+        if (s->p2p_mapped[r])
+            cudaIpcCloseMemHandle(s->p2p_mapped[r]);
+    if (s->p2p_region)
+        cudaFree(s->p2p_region);
+    if (s->h_vote)
+        cudaFreeHost(s->h_vote);
     if (s->stream && s->own_stream)
         cudaStreamDestroy(s->stream);
+    if (s->cap_stream)
+        cudaStreamDestroy(s->cap_stream);
     delete s;
 }
 
@@ -1499,7 +1548,12 @@ int dem_b200_mgpu_finish_rebuild(dem_b200_system* s) {
         s->err = "mgpu: a slab without spheres is not supported";
         return DEMB200_EINVAL;
     }
+    if (s->p2p && (std::max(s->mg_ns[0], s->mg_ns[1]) > s->p2p_records || std::max(s->mg_ng[0], s->mg_ng[1]) > s->p2p_records)) {
+        s->err = "p2p: more ghosts than the landing buffers hold";
+        return DEMB200_ECAPACITY;
+    }
     s->P.N = s->mg_n_local;
+    drop_graph(s);
     s->mg_phase = 0;
     s->mg_remap_pending = true;
     s->export_valid = false;
@@ -1549,6 +1603,90 @@ int dem_b200_mgpu_want_rebuild_ahead(dem_b200_system* s, int* flag_dev, int step
     return 0;
 }
 int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev) { return dem_b200_mgpu_want_rebuild_ahead(s, flag_dev, 0); }
+
+// ---- direct peer-to-peer halo -----------------------------------------------------------------------------------
+static size_t p2p_region_bytes(size_t records) { return kP2PCtlBytes + 4 * records * kHaloDoubles * sizeof(double); }
+
+int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64) {
+    if (!s || !s->initialized || !s->mgpu || !handle64 || max_records == 0 || s->p2p_region)
+        return DEMB200_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    static_assert(sizeof(P2PCtl) <= kP2PCtlBytes, "control block");
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMalloc(&s->p2p_region, p2p_region_bytes(max_records)));
+    CU(cudaMemset(s->p2p_region, 0, p2p_region_bytes(max_records)));
+    CU(cudaDeviceSynchronize());
+    s->p2p_records = max_records;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->p2p_region));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* handles, int steps_ahead) {
+    if (!s || !s->p2p_region || !handles || world < 2 || world > kMaxRanks || rank < 0 || rank >= world || steps_ahead < 1)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    P2PDev& X = s->X;
+    memset(&X, 0, sizeof(X));
+    auto land_of = [&](void* base, int side, int parity) {
+        return reinterpret_cast<double*>((char*)base + kP2PCtlBytes) + (size_t)(2 * side + parity) * s->p2p_records * kHaloDoubles;
+    };
+    for (int r = 0; r < world; r++) {
+        void* base = s->p2p_region;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+            CU(cudaIpcOpenMemHandle(&s->p2p_mapped[r], h, cudaIpcMemLazyEnablePeerAccess));
+            base = s->p2p_mapped[r];
+        }
+        X.peer[r] = reinterpret_cast<P2PCtl*>(base);
+    }
+    X.self = reinterpret_cast<P2PCtl*>(s->p2p_region);
+    for (int side = 0; side < 2; side++)
+        for (int par = 0; par < 2; par++) {
+            X.land[side][par] = land_of(s->p2p_region, side, par);
+            const int nb = rank + (side == 0 ? -1 : 1);
+            // what I send to my left neighbour lands in ITS "from the right" buffer, and vice versa
+            X.peer_land[side][par] = (nb >= 0 && nb < world) ? land_of((void*)X.peer[nb], side == 0 ? 1 : 0, par) : nullptr;
+        }
+    int rc = dev_alloc(s, &X.done, 2);
+    if (rc)
+        return rc;
+    CU(cudaMemset(X.done, 0, 2 * sizeof(unsigned)));
+    CU(cudaHostAlloc((void**)&s->h_vote, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(s->h_vote, 0, 8 * sizeof(unsigned long long));
+    CU(cudaHostGetDevicePointer((void**)&X.host_vote, s->h_vote, 0));
+    X.rank = rank;
+    X.world = world;
+    X.ahead = steps_ahead;
+    X.first_step = s->step_no + 1;
+    CU(cudaDeviceSynchronize());
+    s->p2p = true;
+    drop_graph(s);
+    return 0;
+}
+
+// Blocks until the all-rank vote of time step `step` (as numbered by dem_b200_step_count) is known; *flag = 1 if any rank
+// wants the candidate lists rebuilt.  The vote of step k becomes available while step k+1 runs.
+int dem_b200_p2p_poll_vote(dem_b200_system* s, unsigned long long step, int* flag) {
+    if (!s || !s->p2p || !flag || step < s->X.first_step || step + 1 > s->step_no)
+        return DEMB200_EINVAL;
+    volatile unsigned long long* v = s->h_vote + (step & 7ull);
+    for (unsigned long long spins = 0;; spins++) {
+        const unsigned long long got = *v;
+        if ((got >> 1) == step) {
+            *flag = (int)(got & 1ull);
+            return 0;
+        }
+        if ((spins & 0xFFFFFull) == 0xFFFFFull && cudaStreamQuery(s->stream) == cudaSuccess && ((*v) >> 1) != step) {
+            s->err = "p2p_poll_vote: the stream is idle and the vote never arrived";
+            return DEMB200_EINVAL;
+        }
+    }
+}
+
+unsigned long long dem_b200_step_count(const dem_b200_system* s) { return s ? s->step_no : 0ull; }
 
 int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
                           size_t* n) {

@@ -2032,6 +2032,105 @@ __global__ void k_mgpu_want(Params P, Buffers B, int* flag_out, int ahead) {
     const double t = C.travel + dx * (double)(1 + ahead);
     *flag_out = (C.need_rebuild != 0 || !(t < 0.499 * P.skin)) ? 1 : 0;
 }
+// --------------------------------------------------------------------------------------------
+// direct P2P halo + vote (see P2PCtl in dem_types.h).  `step` = number of the time step the data belongs to = the
+// value Ctrl::nsteps will have once k_step_begin of that step has run.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// dir 0: my spheres near my LEFT face -> left neighbour's "from the right" buffer; dir 1: the mirror image.
+__global__ void __launch_bounds__(256) k_p2p_pack(Buffers B, P2PDev X, int dir, unsigned n) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned long long step = C.nsteps + 1ull;
+    double* out = X.peer_land[dir][step & 1ull];
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned s = B.send_slot[dir][i];
+        const double4 p = B.pos[C.cur][s];
+        const VelVal r = load_vel(B.vel[C.cur], s);
+        double* o = out + (size_t)i * kHaloDoubles;
+        o[0] = p.x; o[1] = p.y; o[2] = p.z;
+        o[3] = r.v.x; o[4] = r.v.y; o[5] = r.v.z; o[6] = r.w.x; o[7] = r.w.y; o[8] = r.w.z;
+    }
+    // the last block to finish publishes the step number on the receiver
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&X.done[dir], 1u);
+        if (prev == gridDim.x - 1) {
+            X.done[dir] = 0u;
+            __threadfence_system();
+            P2PCtl* peer = X.peer[X.rank + (dir == 0 ? -1 : 1)];
+            // I am their right neighbour when I send to my left (dir 0), and vice versa
+            st_release_sys(&peer->arrive[dir == 0 ? 1 : 0][step & 1ull], step);
+        }
+    }
+}
+
+// side 0: data from my left neighbour -> my ghost slots of side 0; side 1: from the right.
+__global__ void __launch_bounds__(256) k_p2p_unpack(Buffers B, P2PDev X, int side, unsigned n) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned long long step = C.nsteps + 1ull;
+    if (threadIdx.x == 0) {
+        const unsigned long long* f = &X.self->arrive[side][step & 1ull];
+        while (ld_acquire_sys(f) < step)
+            __nanosleep(64);
+    }
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double* o = X.land[side][step & 1ull] + (size_t)i * kHaloDoubles;
+    const unsigned s = B.ghost_slot[side][i];
+    double4 p = B.pos[C.cur][s];
+    p.x = __ldcv(o + 0); p.y = __ldcv(o + 1); p.z = __ldcv(o + 2);
+    B.pos[C.cur][s] = p;
+    double2* q = reinterpret_cast<double2*>(B.vel[C.cur] + s);
+    q[0] = make_double2(__ldcv(o + 3), __ldcv(o + 4));
+    q[1] = make_double2(__ldcv(o + 5), __ldcv(o + 6));
+    q[2] = make_double2(__ldcv(o + 7), __ldcv(o + 8));
+}
+
+// After the step: my vote on "rebuild before the lists go stale?" goes to every rank; then the votes of the PREVIOUS
+// step (every rank has long cast it) are OR-ed and handed to the host through mapped pinned memory.
+__global__ void k_p2p_vote(Params P, Buffers B, P2PDev X) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned long long step = C.nsteps;  // the step that just ran
+    const unsigned r = threadIdx.x;
+    if (r < (unsigned)X.world) {
+        const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
+        const double t = C.travel + dx * (double)(1 + X.ahead);
+        const unsigned long long flag = (C.need_rebuild != 0 || !(t < 0.499 * P.skin)) ? 1ull : 0ull;
+        st_release_sys(&X.peer[r]->vote[step & 7ull][X.rank], (step << 1) | flag);
+    }
+    if (step <= X.first_step)
+        return;
+    const unsigned long long prev = step - 1ull;
+    unsigned long long any = 0ull;
+    if (r < (unsigned)X.world) {
+        const unsigned long long* v = &X.self->vote[prev & 7ull][r];
+        unsigned long long got;
+        // a rank that has not run step `prev` in P2P mode yet (e.g. the very first step) never blocks us for long: the
+        // host only acts on votes of steps it issued in P2P mode
+        unsigned spins = 0;
+        while (((got = ld_acquire_sys(v)) >> 1) < prev && ++spins < 4000000u)
+            __nanosleep(64);
+        any = ((got >> 1) == prev) ? (got & 1ull) : 1ull;  // timed out: ask for a rebuild rather than run on stale lists
+    }
+    any = __reduce_or_sync(0xffffffffu, (unsigned)any);
+    if (r == 0) {
+        X.host_vote[prev & 7ull] = (prev << 1) | any;
+        __threadfence_system();
+    }
+}
+
 // compact export of the owned spheres (any order): sid, pos, vel, omega
 __global__ void __launch_bounds__(256) k_export_owned(Params P, Buffers B, unsigned* count, unsigned cap, unsigned* sid,
                                                       double* pos3, double* vel3, double* om3) {

@@ -159,6 +159,29 @@ struct SlabDev {
     unsigned want_rebuild;  // this rank's Verlet skin is (about to be) used up
 };
 
+// Direct peer-to-peer halo (slab mode, one process per GPU on one NVSwitch box).  Every rank exposes one region through
+// CUDA IPC: this control block followed by the halo landing buffers [from left | from right] x [step parity].  A rank's
+// pack kernel STORES its boundary spheres' state straight into the neighbour's landing buffer over NVLink and then
+// publishes the step number in `arrive`; the neighbour's unpack kernel waits for that number.  The per-step "rebuild
+// now?" vote is a store of (step << 1 | flag) into slot [step & 7][rank] of every peer; no collective, no host.
+constexpr int kMaxRanks = 8;
+struct P2PCtl {
+    unsigned long long arrive[2][2];         // [0: from the left neighbour, 1: from the right][parity] = step that landed
+    unsigned long long vote[8][kMaxRanks];   // [step & 7][rank] = (step << 1) | wants_rebuild
+};
+constexpr size_t kP2PCtlBytes = 1024;        // control block padded; landing buffers follow
+
+struct P2PDev {
+    P2PCtl* self;                  // my own control block
+    double* land[2][2];            // my landing buffers [from side][parity]
+    P2PCtl* peer[kMaxRanks];       // every rank's control block as mapped here (peer[rank] == self)
+    double* peer_land[2][2];       // [0: left neighbour, 1: right neighbour][parity]: THEIR buffer for data coming from me
+    unsigned* done;                // block counters of the pack kernels (2)
+    unsigned long long* host_vote; // pinned, mapped: [step & 7] = (step << 1) | any rank wants a rebuild
+    int rank, world, ahead;
+    unsigned long long first_step; // first step that ran in P2P mode: votes of earlier steps do not exist
+};
+
 struct Buffers {
     Ctrl* ctrl;
     WallSet* walls;

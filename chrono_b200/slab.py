@@ -81,6 +81,7 @@ class SlabDriver:
     # ---- rebuild: migration, new ghost set ---------------------------------------------------------------------------
     def rebuild(self):
         b = self.b
+        t0 = b.clock() if hasattr(b, "clock") else None  # synchronising wall clock: rebuilds only
         n_keep, out_l, out_r = b.extract(self.lo, self.hi)
         if self.left is None and out_l.shape[0] or self.right is None and out_r.shape[0]:
             raise RuntimeError("a sphere left the outermost slab (bounds must be infinite there)")
@@ -102,6 +103,8 @@ class SlabDriver:
         self.n_send = (int(g_l.shape[0]), int(g_r.shape[0]))
         self.stats["rebuilds"] += 1
         self.fresh = True
+        if t0 is not None:
+            self.stats["rebuild_s"] = self.stats.get("rebuild_s", 0.0) + (b.clock() - t0)
 
     # ---- per-step halo -------------------------------------------------------------------------------------------------
     def halo(self):
@@ -124,7 +127,35 @@ class SlabDriver:
                 b.unpack(d, recv[d])
         self.stats["halo_bytes"] += int((self.n_recv[0] + self.n_recv[1]) * b.halo_doubles * 8)
 
+    # ---- direct P2P halo (engine backend only) -------------------------------------------------------------------------
+    def enable_p2p(self, lag=2):
+        """Switch the per-step path to NVLink peer stores + device-side vote (include/chrono_b200_dem.h, dem_b200_p2p_*):
+        from now on one engine call per step does halo + step + vote; the host only polls the vote `lag` steps late and
+        runs rebuild() when it says so.  Handles travel through torch.distributed once."""
+        handle = self.b.p2p_export()
+        mine = torch.from_numpy(handle.copy()).to(self.b.device)
+        allh = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        self.b.p2p_import(self.rank, self.world, torch.stack(allh).cpu().numpy(), lag)
+        self.p2p, self.lag = True, int(lag)
+        self.first_vote = self.b.step_count() + 1
+        self.ignore_upto = 0
+
+    def _step_p2p(self, nsteps):
+        b = self.b
+        for _ in range(nsteps):
+            b.step()  # halo (unless the ghosts are fresh from a rebuild) + step + vote, one graph launch
+            self.fresh = False
+            self.stats["steps"] += 1
+            self.stats["halo_bytes"] += int((self.n_recv[0] + self.n_recv[1]) * b.halo_doubles * 8)
+            k = b.step_count() - self.lag
+            if k >= self.first_vote and k > self.ignore_upto and b.p2p_poll_vote(k):
+                self.rebuild()
+                self.ignore_upto = b.step_count()  # votes cast before the rebuild are void
+
     def step(self, nsteps=1):
+        if getattr(self, "p2p", False):
+            return self._step_p2p(nsteps)
         for _ in range(nsteps):
             if not self.fresh:
                 self.halo()
@@ -147,6 +178,8 @@ class SlabDriver:
 
     def drain(self):
         """Act on the answers still in flight (call before reading results / at the end of a timed region)."""
+        if getattr(self, "p2p", False):
+            return  # votes not yet polled are looked at by the next step() call
         while self._pending:
             if self._pending.pop(0)():
                 self._pending.clear()
@@ -176,6 +209,9 @@ class EngineBackend:
         self.hrecv = [torch.empty((self.max_records, self.halo_doubles), **f64) for _ in range(2)]
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.n_send = [0, 0]
+        self.L.dem_b200_step_count.restype = C.c_ulonglong
+        self.L.dem_b200_step_count.argtypes = [C.c_void_p]
+        self.L.dem_b200_p2p_poll_vote.argtypes = [C.c_void_p, C.c_ulonglong, C.POINTER(C.c_int)]
 
     @staticmethod
     def _p(t):
@@ -213,6 +249,28 @@ class EngineBackend:
 
     def step(self):
         self.g._ck(self.L.dem_b200_step(self.h, 1))
+
+    def p2p_export(self):
+        h = np.zeros(64, dtype=np.uint8)
+        self.g._ck(self.L.dem_b200_p2p_export(self.h, C.c_size_t(self.max_records), h.ctypes.data_as(C.c_void_p)))
+        return h
+
+    def p2p_import(self, rank, world, handles, ahead):
+        hs = np.ascontiguousarray(handles, dtype=np.uint8)
+        self.g._ck(self.L.dem_b200_p2p_import(self.h, int(rank), int(world), hs.ctypes.data_as(C.c_void_p), int(ahead)))
+
+    def p2p_poll_vote(self, step):
+        f = C.c_int(0)
+        self.g._ck(self.L.dem_b200_p2p_poll_vote(self.h, C.c_ulonglong(step), C.byref(f)))
+        return f.value
+
+    def step_count(self):
+        return int(self.L.dem_b200_step_count(self.h))
+
+    def clock(self):
+        import time
+        torch.cuda.synchronize()
+        return time.perf_counter()
 
     def want_rebuild(self, ahead=0):
         self.g._ck(self.L.dem_b200_mgpu_want_rebuild_ahead(self.h, C.c_void_p(self.flag.data_ptr()), int(ahead)))

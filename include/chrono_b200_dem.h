@@ -214,6 +214,18 @@ int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev); /* writes 1/0
 /* Same for a driver that acts on the answer `steps_ahead` steps late (no host sync per step): those steps are assumed to
  * move the spheres as far as the last one did; if they move further the next step fails loudly (DEMB200_EINVAL). */
 int dem_b200_mgpu_want_rebuild_ahead(dem_b200_system* s, int* flag_dev, int steps_ahead);
+/* Direct peer-to-peer halo for ranks on one NVLink/NVSwitch box (replaces pack -> send/recv -> unpack and the per-step
+ * all-reduce): every rank exports one region (control block + landing buffers for max_records ghosts per side) as a
+ * 64-byte CUDA IPC handle; after the handles of all ranks were gathered (any transport), import() maps them.  From then on
+ * dem_b200_step() itself moves the halo: the pack kernel stores into the neighbour's landing buffer and publishes the step
+ * number, the unpack kernel waits for it; the rebuild vote of every step is stored to all peers and OR-ed on the device.
+ * The host only polls the vote (steps_ahead >= 1 steps late, so that the GPUs never wait for it) and runs the rebuild
+ * protocol above when it says so. */
+int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64);
+int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* handles /* world x 64 bytes */, int steps_ahead);
+int dem_b200_p2p_poll_vote(dem_b200_system* s, unsigned long long step, int* flag);
+unsigned long long dem_b200_step_count(const dem_b200_system* s); /* time steps enqueued so far (numbering of the votes) */
+
 /* owned spheres (ghosts excluded) in arbitrary order: global id, pos, vel, omega to HOST buffers */
 int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
                           size_t* n);

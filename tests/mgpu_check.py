@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--spheres", type=int, default=20000)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--lag", type=int, default=0, help="1: read the rebuild vote one step late (no host sync per step)")
+    ap.add_argument("--p2p", action="store_true", help="halo through NVLink peer stores + device-side vote (no NCCL per step)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -56,6 +57,8 @@ def main():
                                        rmax_global=float(scene["radius"].max()))
     drv = slab.SlabDriver(backend, rank, world, lo, hi, lag=args.lag)
     drv.rebuild()
+    if args.p2p:
+        drv.enable_p2p(lag=2)
     drv.step(args.steps)
     drv.drain()
     g.sync()
