@@ -91,24 +91,38 @@ struct VelVal {
     unsigned sid, meta;
     unsigned long long amask;
 };
+// 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256, sm_100): a gather of a 32-byte record is ONE request of
+// 32 L1 wavefronts instead of two; the force kernel is bound by the L1 data pipe (ncu r01o: 74 % of its peak), not DRAM.
+// ld256: arrays that the running kernel only reads (the compiler may schedule it freely); ld256v: locations the same
+// thread also writes (history rows) -- ordered with respect to st256.
+__device__ __forceinline__ double4 ld256(const void* p) {
+    double4 r;
+    asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double4 ld256v(const void* p) {
+    double4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st256(void* p, double4 v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
 __device__ __forceinline__ VelVal load_vel(const VelRec* __restrict__ a, size_t i) {
-    const double2* q = reinterpret_cast<const double2*>(a + i);
-    const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    const double4 q0 = ld256(a + i), q1 = ld256(reinterpret_cast<const char*>(a + i) + 32);
     VelVal r;
-    r.v = mk(q0.x, q0.y, q1.x);
-    r.w = mk(q1.y, q2.x, q2.y);
-    r.sid = (unsigned)__double2loint(q3.x);
-    r.meta = (unsigned)__double2hiint(q3.x);
-    r.amask = (unsigned long long)__double_as_longlong(q3.y);
+    r.v = mk(q0.x, q0.y, q0.z);
+    r.w = mk(q0.w, q1.x, q1.y);
+    r.sid = (unsigned)__double2loint(q1.z);
+    r.meta = (unsigned)__double2hiint(q1.z);
+    r.amask = (unsigned long long)__double_as_longlong(q1.w);
     return r;
 }
 __device__ __forceinline__ void store_vel(VelRec* a, size_t i, V3 v, V3 w, unsigned sid, unsigned meta,
                                           unsigned long long amask) {
-    double2* q = reinterpret_cast<double2*>(a + i);
-    q[0] = make_double2(v.x, v.y);
-    q[1] = make_double2(v.z, w.x);
-    q[2] = make_double2(w.y, w.z);
-    q[3] = make_double2(__hiloint2double((int)meta, (int)sid), __longlong_as_double((long long)amask));
+    st256(a + i, make_double4(v.x, v.y, v.z, w.x));
+    st256(reinterpret_cast<char*>(a + i) + 32,
+          make_double4(w.y, w.z, __hiloint2double((int)meta, (int)sid), __longlong_as_double((long long)amask)));
 }
 // history record: (disp xyz, packed key | steps << 32); the key is only meaningful in the staging buffers
 __device__ __forceinline__ double pack_key(unsigned key, unsigned steps) { return __hiloint2double((int)steps, (int)key); }
@@ -179,10 +193,29 @@ __global__ void __launch_bounds__(256) k_bbox_reduce(Params P, Buffers B) {
 // --------------------------------------------------------------------------------------------
 // step control: runs as one thread at the head of every step
 // --------------------------------------------------------------------------------------------
-__global__ void k_step_begin(Params P, Buffers B) {
-    if (threadIdx.x != 0 || blockIdx.x != 0)
+__device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C);
+
+// The control block is staged through shared memory by the whole warp: the serial part then works at shared-memory
+// latency instead of paying a global round trip for every field it touches.
+__global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B) {
+    __shared__ Ctrl sC;
+    static_assert(sizeof(Ctrl) % 8 == 0, "Ctrl is copied in 8-byte words");
+    if (blockIdx.x != 0)
         return;
-    Ctrl& C = *B.ctrl;
+    unsigned long long* g = reinterpret_cast<unsigned long long*>(B.ctrl);
+    unsigned long long* l = reinterpret_cast<unsigned long long*>(&sC);
+    constexpr unsigned kWords = sizeof(Ctrl) / 8;
+    for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x)
+        l[i] = g[i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        step_begin_body(P, B, sC);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x)
+        g[i] = l[i];
+}
+
+__device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C) {
     const WallSet& WS = *B.walls;
     // ---- Verlet bookkeeping: every sphere moved at most `travel` since the lists were built ----
     const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
@@ -1077,7 +1110,16 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     const double eps = 2.220446049250313e-16;
     const double radSum = __dadd_rn(ra, rb);
     const double delta_n = radSum - dist;
-    const double erad = __dmul_rn(ra, rb) * fast_rcp(radSum);
+    // equal radii (every pair of a monodisperse packing; the test is symmetric in a <-> b, so both partners take the
+    // same route): R* = r/2 and m* = m/2 without the two reciprocals
+    double erad, m_eff;
+    if (ra == rb) {
+        erad = 0.5 * ra;
+        m_eff = 0.5 * ma;
+    } else {
+        erad = __dmul_rn(ra, rb) * fast_rcp(radSum);
+        m_eff = __dmul_rn(ma, mb) * fast_rcp(__dadd_rn(ma, mb));
+    }
     // velocity of b's contact point minus a's:  (vb + wb x (-n rb)) - (va + wa x (n ra))
     const V3 wsum = mk(__dadd_rn(__dmul_rn(ra, wa.x), __dmul_rn(rb, wb.x)), __dadd_rn(__dmul_rn(ra, wa.y), __dmul_rn(rb, wb.y)),
                        __dadd_rn(__dmul_rn(ra, wa.z), __dmul_rn(rb, wb.z)));
@@ -1085,7 +1127,6 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     const V3 relvel = (vb - va) - wxn;
     const double vn = dot(relvel, n);
     const V3 relvel_t = relvel - vn * n;
-    const double m_eff = __dmul_rn(ma, mb) * fast_rcp(__dadd_rn(ma, mb));
 
     V3 delta_t = mk(0, 0, 0);
     if (HIST) {
@@ -1385,6 +1426,15 @@ __device__ __noinline__ void mesh_contacts(const Params& P, const Buffers& B, un
 // fused narrowphase + force + integrate.  One thread per sphere in storage (cell) order.
 // --------------------------------------------------------------------------------------------
 constexpr int kForceThreads = 128;
+#ifndef DEMB200_P1_BATCH
+#define DEMB200_P1_BATCH 4
+#endif
+#ifndef DEMB200_EARLYPF
+#define DEMB200_EARLYPF 1
+#endif
+#ifndef DEMB200_PF2
+#define DEMB200_PF2 0
+#endif
 #ifndef DEMB200_FORCE_MINBLOCKS
 #define DEMB200_FORCE_MINBLOCKS 4
 #endif
@@ -1410,10 +1460,10 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
     unsigned wcand = 0;  // walls this sphere can reach before the next rebuild (k_build_list)
     unsigned tfirst = 0, tcand = 0;  // mesh triangles in reach: candidate slots tfirst .. tfirst + tcand - 1
     if (valid) {
-        me = pos_in[s];
+        me = ld256(pos_in + s);
         mv = load_vel(vel_in, s);
         // ---- phase 1: exact sphere_sphere test (ChNarrowphasePRIMS.cpp:50-59, separation = 0) on the candidates
-        if (HIST) {
+        if (HIST && DEMB200_EARLYPF) {
             // the live history records of this sphere are a pure stream (read once, by this thread): start them now
             unsigned long long m = mv.amask;
             const double4* hp = B.hist + s;
@@ -1431,25 +1481,26 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
             tcand = ncw >> 24;
         }
         const uint32_t* __restrict__ nl = B.nl + s;
-        // batches of 4 candidates: the ids of the next batch and the 4 positions of this batch are in flight together
-        unsigned jn[4];
+        // batches of kP1 candidates: the ids of the next batch and the positions of this batch are in flight together
+        constexpr int kP1 = DEMB200_P1_BATCH;
+        unsigned jn[kP1];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < kP1; u++)
             jn[u] = ((unsigned)u < nc) ? nl[(size_t)u * P.Np] : s;
-        for (unsigned k0 = 0; k0 < nc; k0 += 4) {
-            unsigned jj[4];
-            double4 pp[4];
+        for (unsigned k0 = 0; k0 < nc; k0 += kP1) {
+            unsigned jj[kP1];
+            double4 pp[kP1];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < kP1; u++)
                 jj[u] = jn[u];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                pp[u] = pos_in[jj[u]];
+            for (int u = 0; u < kP1; u++)
+                pp[u] = ld256(pos_in + jj[u]);
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                jn[u] = (k0 + 4 + u < nc) ? nl[(size_t)(k0 + 4 + u) * P.Np] : s;
+            for (int u = 0; u < kP1; u++)
+                jn[u] = (k0 + kP1 + u < nc) ? nl[(size_t)(k0 + kP1 + u) * P.Np] : s;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < kP1; u++) {
                 const V3 d = mk(__dsub_rn(pp[u].x, me.x), __dsub_rn(pp[u].y, me.y), __dsub_rn(pp[u].z, me.z));
                 const double dist2 = dot_rn(d, d);
                 const double rs = __dadd_rn(me.w, pp[u].w);
@@ -1460,7 +1511,9 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
                     clist[cnt * kForceThreads + tid] = jj[u];
                     cslot[cnt * kForceThreads + tid] = (unsigned char)(k0 + u);
                 }
+#if DEMB200_EARLYPF
                 prefetch_l1(vel_in + jj[u]);  // the partner's velocity record is needed in phase 2
+#endif
                 cnt++;
             }
         }
@@ -1523,7 +1576,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
             double steps = 0.0;
             const size_t hi = (size_t)(P.Kn + w) * P.Np;
             if (HIST && ((wmask_old >> w) & 1u)) {
-                const double4 r = hcol[hi];
+                const double4 r = ld256v(hcol + hi);
                 h.disp = mk(r.x, r.y, r.z);
                 steps = r.w;
                 h.dur = steps * P.dt;
@@ -1544,7 +1597,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
                 atomicAdd(&C.wall_force[w][2], -F.z);
             }
             if (HIST) {
-                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, steps);
+                st256(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
                 if (rcol)
                     rcol[hi] = h.relvel0;
                 wmask_new |= 1u << w;
@@ -1571,10 +1624,10 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
     if (cnt > 0) {
         const unsigned j0 = clist[tid];
         slot_next = cslot[tid];
-        pj_next = pos_in[j0];
+        pj_next = ld256(pos_in + j0);
         ov_next = load_vel(vel_in, j0);
         if (HIST && ((amask_old >> slot_next) & 1ull))
-            hr_next = hcol[(size_t)slot_next * P.Np];
+            hr_next = ld256v(hcol + (size_t)slot_next * P.Np);
     }
     for (int k = 0; k < maxc; k++) {
         if (k >= cnt)
@@ -1586,13 +1639,23 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
         // registers into their loop-carried homes right behind the load below and stalls on it (ncu r01d).
         asm volatile("" : "+d"(hr.x), "+d"(hr.y), "+d"(hr.z), "+d"(hr.w));
         const unsigned slot = slot_next;
+#if DEMB200_PF2
+        if (k + 2 < cnt) {  // two contacts ahead: lines into L1, so that the register loads below hit
+            const unsigned j2 = clist[(k + 2) * kForceThreads + tid];
+            const unsigned s2 = cslot[(k + 2) * kForceThreads + tid];
+            prefetch_l1(pos_in + j2);
+            prefetch_l1(vel_in + j2);
+            if (HIST && ((amask_old >> s2) & 1ull))
+                prefetch_l1(hcol + (size_t)s2 * P.Np);
+        }
+#endif
         if (k + 1 < cnt) {
             const unsigned jn = clist[(k + 1) * kForceThreads + tid];
             slot_next = cslot[(k + 1) * kForceThreads + tid];
-            pj_next = pos_in[jn];
+            pj_next = ld256(pos_in + jn);
             ov_next = load_vel(vel_in, jn);
             if (HIST && ((amask_old >> slot_next) & 1ull))
-                hr_next = hcol[(size_t)slot_next * P.Np];
+                hr_next = ld256v(hcol + (size_t)slot_next * P.Np);
         }
         const unsigned sj = ov.sid;
         const bool me1 = sid < sj;  // canonical orientation: body 1 = lower shape id
@@ -1625,7 +1688,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
             if (HIST) {
                 if (!me1)
                     disp = -disp;
-                hcol[hi] = make_double4(disp.x, disp.y, disp.z, steps);
+                st256(hcol + hi, make_double4(disp.x, disp.y, disp.z, steps));
                 amask_new |= 1ull << slot;
             }
         } else {
@@ -1676,7 +1739,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
                 Tsum = Tsum + T2;
             }
             if (HIST) {
-                hcol[hi] = make_double4(h.disp.x, h.disp.y, h.disp.z, steps);
+                st256(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
                 if (rcol)
                     rcol[hi] = h.relvel0;
                 amask_new |= 1ull << slot;
@@ -1741,7 +1804,7 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
         }
         if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z)))
             atomicOr(&C.err, ERR_NAN);
-        B.pos[dst][s] = make_double4(x.x, x.y, x.z, me.w);
+        st256(B.pos[dst] + s, make_double4(x.x, x.y, x.z, me.w));
         store_vel(B.vel[dst], s, vn, wn, sid, flags | (wmask_new << 8), amask_new);
         if (!ghost) {
             nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
