@@ -144,6 +144,30 @@ def workload_config(n, substeps, gpus):
             "slab domain decomposition along x, %d ranks x %d spheres (box %d x as long), ghost halo over NVLink" % (gpus, n, gpus)}
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: keep the host thread (and the threads NCCL / CUDA spawn) on the cores next to that GPU
+    (`nvidia-smi topo -m`, column "CPU Affinity")."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        lines = [l for l in out.splitlines() if l.strip()]
+        hdr = next(l for l in lines if "CPU Affinity" in l)
+        cols = [c.strip() for c in hdr.split("\t") if c.strip()]
+        ci = cols.index("CPU Affinity") + 1  # rows carry the row label in front
+        row = next(l for l in lines if l.startswith("GPU%d" % local))
+        cells = [c.strip() for c in row.split("\t") if c.strip()]
+        spec = cells[ci]
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
 def run_slabs(args):
     """N > 1: slab domain decomposition (chrono_b200/slab.py).  One process per GPU, every rank owns n spheres of a box
     N times as long; per step: ghost halo (pos, v, omega of the spheres within 2 r_max + skin of a slab face) over NCCL
@@ -156,6 +180,7 @@ def run_slabs(args):
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, S = args.spheres, args.substeps
@@ -185,7 +210,8 @@ def run_slabs(args):
     g.sync()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per job: the queries take driver locks that every rank's launches contend for
+        sampler.start()
     st0 = dict(drv.stats)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -205,7 +231,8 @@ def run_slabs(args):
     nsteps = args.steps * S
     value = world * n * nsteps / (ms_total * 1e-3)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     # ---- e2e: every bench step the owned state comes from / goes back to pinned host memory
     sid, p0, v0, w0 = backend.export_owned()
@@ -257,7 +284,7 @@ def run_slabs(args):
                     "steps": e2e_steps, "note": "slab mode: owned state read back to the host every bench step; the state stays "
                                                 "resident on the GPUs between steps (uploading it would re-partition the domain)"},
             "gpu_launches": int(nsteps * (KERNELS_PER_TIMESTEP + 5)),
-            "clocks": sampler.result(), "wall_s_timed_region": t_wall, "host_enqueue_s": t_enqueue,
+            "clocks": sampler.result(), "wall_s_timed_region": t_wall, "host_enqueue_s": t_enqueue, "cpu_affinity_rank0": affinity,
         }
         print(json.dumps(line))
     dist.barrier()
@@ -387,7 +414,7 @@ def main():
     ap.add_argument("--ref-substeps", type=int, default=2, help="time steps per bench step of the reference arm")
     ap.add_argument("--cpu-steps", type=int, default=4, help="time steps of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: NCCL send/recv halo + all-reduce vote instead of P2P stores")
-    ap.add_argument("--slab-lag", type=int, default=2, help="N > 1: steps between casting the rebuild vote and acting on it")
+    ap.add_argument("--slab-lag", type=int, default=3, help="N > 1: steps between casting the rebuild vote and acting on it")
     ap.add_argument("--skin", type=float, default=0.0, help="N > 1: Verlet skin in sphere radii (0 = engine default 0.25)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of slab decomposition")
     args = ap.parse_args()

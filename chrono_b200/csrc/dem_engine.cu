@@ -71,6 +71,7 @@ struct dem_b200_system {
     size_t p2p_records = 0;
     unsigned long long* h_vote = nullptr;     // pinned, mapped
     unsigned long long step_no = 0;      // host mirror of Ctrl::nsteps (steps enqueued so far)
+    unsigned long long p2p_rebuild_seq = 0;
     double time = 0.0;
     std::string err;
     // scratch (device, by user index) and pinned host staging
@@ -1605,7 +1606,12 @@ int dem_b200_mgpu_want_rebuild_ahead(dem_b200_system* s, int* flag_dev, int step
 int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev) { return dem_b200_mgpu_want_rebuild_ahead(s, flag_dev, 0); }
 
 // ---- direct peer-to-peer halo -----------------------------------------------------------------------------------
-static size_t p2p_region_bytes(size_t records) { return kP2PCtlBytes + 4 * records * kHaloDoubles * sizeof(double); }
+// region layout: control block | halo landing [2 sides][2 parities] | migrant landing [2 sides] | ghost landing [2 sides]
+static size_t p2p_mig_records(size_t records) { return std::max<size_t>(1024, records / 16); }
+static size_t p2p_region_bytes(size_t records, int K) {
+    return kP2PCtlBytes + sizeof(double) * (4 * records * kHaloDoubles + 2 * p2p_mig_records(records) * (size_t)migrant_doubles(K) +
+                                            2 * records * kGhostDoubles);
+}
 
 int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64) {
     if (!s || !s->initialized || !s->mgpu || !handle64 || max_records == 0 || s->p2p_region)
@@ -1613,8 +1619,8 @@ int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64) 
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     static_assert(sizeof(P2PCtl) <= kP2PCtlBytes, "control block");
     CU(cudaSetDevice(s->cfg.device));
-    CU(cudaMalloc(&s->p2p_region, p2p_region_bytes(max_records)));
-    CU(cudaMemset(s->p2p_region, 0, p2p_region_bytes(max_records)));
+    CU(cudaMalloc(&s->p2p_region, p2p_region_bytes(max_records, s->P.K)));
+    CU(cudaMemset(s->p2p_region, 0, p2p_region_bytes(max_records, s->P.K)));
     CU(cudaDeviceSynchronize());
     s->p2p_records = max_records;
     cudaIpcMemHandle_t h;
@@ -1650,6 +1656,25 @@ int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* han
             // what I send to my left neighbour lands in ITS "from the right" buffer, and vice versa
             X.peer_land[side][par] = (nb >= 0 && nb < world) ? land_of((void*)X.peer[nb], side == 0 ? 1 : 0, par) : nullptr;
         }
+    {
+        const size_t R = s->p2p_records, M = p2p_mig_records(R), md = (size_t)migrant_doubles(s->P.K);
+        auto mig_of = [&](void* base, int side) {
+            return reinterpret_cast<double*>((char*)base + kP2PCtlBytes) + 4 * R * kHaloDoubles + (size_t)side * M * md;
+        };
+        auto gho_of = [&](void* base, int side) {
+            return reinterpret_cast<double*>((char*)base + kP2PCtlBytes) + 4 * R * kHaloDoubles + 2 * M * md + (size_t)side * R * kGhostDoubles;
+        };
+        for (int side = 0; side < 2; side++) {
+            X.mig_land[side] = mig_of(s->p2p_region, side);
+            X.gho_land[side] = gho_of(s->p2p_region, side);
+            const int nb = rank + (side == 0 ? -1 : 1);
+            const bool have = nb >= 0 && nb < world;
+            X.peer_mig[side] = have ? mig_of((void*)X.peer[nb], side == 0 ? 1 : 0) : nullptr;
+            X.peer_gho[side] = have ? gho_of((void*)X.peer[nb], side == 0 ? 1 : 0) : nullptr;
+        }
+        X.cap_mig = (unsigned)M;
+        X.cap_gho = (unsigned)R;
+    }
     int rc = dev_alloc(s, &X.done, 2);
     if (rc)
         return rc;
@@ -1665,6 +1690,61 @@ int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* han
     s->p2p = true;
     drop_graph(s);
     return 0;
+}
+
+// The whole rebuild of the slab (migration + new ghost set) without a collective: records go straight into the
+// neighbours' landing buffers, counts and arrival flags with them; one host synchronisation at the end to learn the new
+// layout.  Every rank must call it at the same step.  counts = {n_own, ghosts from left, from right, sent as ghosts to
+// left, to right, migrated out left, out right}.
+int dem_b200_p2p_rebuild(dem_b200_system* s, double lo, double hi, size_t counts[7]) {
+    if (!s || !s->initialized || !s->mgpu || !s->p2p || s->mg_phase != 0)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    const unsigned long long seq = ++s->p2p_rebuild_seq;
+    cudaStream_t st = s->stream;
+    const P2PDev& X = s->X;
+    CU(cudaMemsetAsync(s->B.slab, 0, sizeof(SlabDev), st));
+    const unsigned N = s->P.N, Np = s->P.Np;
+    k_mgpu_extract<<<(N + 255) / 256, 256, 0, st>>>(s->P, s->B, lo, hi, X.peer_mig[0], X.peer_mig[1], X.cap_mig);
+    k_p2p_publish<<<1, 32, 0, st>>>(s->B, X, 0, seq);
+    const unsigned gm = std::min(64u, (X.cap_mig + 255) / 256), gg = std::min(512u, (X.cap_gho + 255) / 256);
+    k_p2p_append<<<gm, 256, 0, st>>>(s->P, s->B, X, 0, 0, seq);
+    k_p2p_append<<<gm, 256, 0, st>>>(s->P, s->B, X, 0, 1, seq);
+    k_mgpu_select_ghosts<<<(Np + 255) / 256, 256, 0, st>>>(s->P, s->B, 0xFFFFFFFFu, lo, hi, 2.0 * s->P.rmax + s->P.skin, X.peer_gho[0],
+                                                         X.peer_gho[1], X.cap_gho);
+    k_p2p_publish<<<1, 32, 0, st>>>(s->B, X, 1, seq);
+    k_p2p_append<<<gg, 256, 0, st>>>(s->P, s->B, X, 1, 0, seq);
+    k_p2p_append<<<gg, 256, 0, st>>>(s->P, s->B, X, 1, 1, seq);
+    CU(cudaGetLastError());
+    SlabDev sd;
+    CU(cudaMemcpyAsync(s->h_pin, s->B.slab, sizeof(SlabDev), cudaMemcpyDeviceToHost, st));
+    k_mgpu_finish<<<1, 32, 0, st>>>(s->B);  // after the copy: it clears the counters
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    memcpy(&sd, s->h_pin, sizeof(SlabDev));
+    s->mg_n_own = sd.n_own;
+    for (int d = 0; d < 2; d++) {
+        s->mg_ns[d] = sd.n_gsend[d];
+        s->mg_ng[d] = sd.g_in[d];
+    }
+    s->mg_n_local = s->mg_n_own + s->mg_ng[0] + s->mg_ng[1];
+    if (counts) {
+        counts[0] = sd.n_own; counts[1] = sd.g_in[0]; counts[2] = sd.g_in[1]; counts[3] = sd.n_gsend[0];
+        counts[4] = sd.n_gsend[1]; counts[5] = sd.n_out[0]; counts[6] = sd.n_out[1];
+    }
+    if (s->mg_n_local == 0 || s->mg_n_local > s->mg_cap || std::max(sd.n_gsend[0], sd.n_gsend[1]) > X.cap_gho ||
+        std::max(sd.n_out[0], sd.n_out[1]) > X.cap_mig) {
+        s->err = "p2p_rebuild: slab empty or a buffer capacity exceeded";
+        return DEMB200_ECAPACITY;
+    }
+    s->P.N = s->mg_n_local;
+    drop_graph(s);
+    s->mg_remap_pending = true;
+    s->export_valid = false;
+    int rc = recompute_bbox(s);
+    if (rc)
+        return rc;
+    return check_device_error(s);
 }
 
 // Blocks until the all-rank vote of time step `step` (as numbered by dem_b200_step_count) is known; *flag = 1 if any rank

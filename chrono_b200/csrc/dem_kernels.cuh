@@ -1930,6 +1930,10 @@ __global__ void __launch_bounds__(256) k_mgpu_extract(Params P, Buffers B, doubl
             atomicOr(&C.err, ERR_PAIR_CAPACITY);
             return;
         }
+        if ((dest == 0 ? out_left : out_right) == nullptr) {  // left the outermost slab: there is nobody to take it
+            atomicOr(&C.err, ERR_PAIR_CAPACITY);
+            return;
+        }
         double* o = (dest == 0 ? out_left : out_right) + (size_t)io * migrant_doubles(P.K);
         o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.w;
         o[4] = r.v.x; o[5] = r.v.y; o[6] = r.v.z; o[7] = r.w.x; o[8] = r.w.y; o[9] = r.w.z;
@@ -1947,18 +1951,26 @@ __global__ void __launch_bounds__(256) k_mgpu_extract(Params P, Buffers B, doubl
                 cnt = P.K;
         }
         o[18] = (double)cnt;
+        __threadfence_system();  // the message buffer may be the neighbour's memory (P2P rebuild)
     }
 }
 
 // Append received records behind the kept spheres (same pre-sort arrays).  ghost != 0: light records, flagged.
+__device__ __forceinline__ void append_record(const Params& P, const Buffers& B, const double* in, unsigned i, unsigned at,
+                                              int ghost);
+
 __global__ void __launch_bounds__(256) k_mgpu_append(Params P, Buffers B, const double* in, unsigned n, unsigned base,
                                                      int ghost) {
-    const Ctrl& C = *B.ctrl;
-    const unsigned b = C.cur ^ 1u;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    const unsigned at = base + i;
+    append_record(P, B, in, i, base + i, ghost);
+}
+
+__device__ __forceinline__ void append_record(const Params& P, const Buffers& B, const double* in, unsigned i, unsigned at,
+                                              int ghost) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned b = C.cur ^ 1u;
     const double* o = in + (size_t)i * (ghost ? kGhostDoubles : migrant_doubles(P.K));
     B.pos[b][at] = make_double4(o[0], o[1], o[2], o[3]);
     const unsigned sid = (unsigned)__double2loint(o[10]);
@@ -1996,6 +2008,8 @@ __global__ void __launch_bounds__(256) k_mgpu_select_ghosts(Params P, Buffers B,
     SlabDev& S = *B.slab;
     const unsigned b = C.cur ^ 1u;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_own == 0xFFFFFFFFu)
+        n_own = S.n_own;  // device-driven rebuild: the count is only known on the device
     const bool valid = i < n_own;
     double4 p = make_double4(0, 0, 0, 1);
     if (valid)
@@ -2020,6 +2034,7 @@ __global__ void __launch_bounds__(256) k_mgpu_select_ghosts(Params P, Buffers B,
         o[4] = r.v.x; o[5] = r.v.y; o[6] = r.v.z; o[7] = r.w.x; o[8] = r.w.y; o[9] = r.w.z;
         o[10] = __hiloint2double((int)(r.meta & 0xFFu), (int)r.sid);
         o[11] = 0.0;
+        __threadfence_system();  // the message buffer may be the neighbour's memory (P2P rebuild)
     }
 }
 
@@ -2159,6 +2174,76 @@ __global__ void __launch_bounds__(256) k_p2p_unpack(Buffers B, P2PDev X, int sid
     q[0] = make_double2(__ldcv(o + 3), __ldcv(o + 4));
     q[1] = make_double2(__ldcv(o + 5), __ldcv(o + 6));
     q[2] = make_double2(__ldcv(o + 7), __ldcv(o + 8));
+}
+
+// ---- device-driven rebuild (P2P mode): the same protocol as extract -> exchange -> append -> select_ghosts -> exchange
+// -> append, but records are stored straight into the neighbour's landing buffers and the counts travel with them; the
+// host only reads the final layout once.  `seq` = number of this rebuild.
+__global__ void k_p2p_publish(Buffers B, P2PDev X, int what, unsigned long long seq) {
+    if (threadIdx.x || blockIdx.x)
+        return;
+    const SlabDev& S = *B.slab;
+    __threadfence_system();
+    for (int d = 0; d < 2; d++) {
+        const int nb = X.rank + (d == 0 ? -1 : 1);
+        if (nb < 0 || nb >= X.world)
+            continue;
+        P2PCtl* peer = X.peer[nb];
+        const int side = d == 0 ? 1 : 0;  // I am their right neighbour when I send to my left
+        if (what == 0) {
+            peer->mig_count[side] = S.n_out[d];
+            __threadfence_system();
+            st_release_sys(&peer->mig_arrive[side], seq);
+        } else {
+            peer->gho_count[side] = S.n_gsend[d];
+            __threadfence_system();
+            st_release_sys(&peer->gho_arrive[side], seq);
+        }
+    }
+}
+
+// what = 0: migrants of both sides behind the kept spheres; what = 1: ghosts behind the owned spheres (left first)
+__global__ void __launch_bounds__(256) k_p2p_append(Params P, Buffers B, P2PDev X, int what, int side, unsigned long long seq) {
+    SlabDev& S = *B.slab;
+    Ctrl& C = *B.ctrl;
+    const int nb = X.rank + (side == 0 ? -1 : 1);
+    const bool have = nb >= 0 && nb < X.world;
+    __shared__ unsigned s_n, s_base;
+    if (threadIdx.x == 0) {
+        unsigned n = 0;
+        if (have) {
+            const unsigned long long* f = what == 0 ? &X.self->mig_arrive[side] : &X.self->gho_arrive[side];
+            while (ld_acquire_sys(f) < seq)
+                __nanosleep(64);
+            n = what == 0 ? X.self->mig_count[side] : X.self->gho_count[side];
+        }
+        unsigned base;
+        if (what == 0)
+            base = S.n_keep + (side == 1 ? S.n_in[0] : 0u);
+        else
+            base = S.n_own + (side == 1 ? S.g_in[0] : 0u);
+        if ((what == 0 ? n > X.cap_mig : n > X.cap_gho) || (size_t)base + n > (size_t)P.Np) {
+            atomicOr(&C.err, ERR_PAIR_CAPACITY);
+            n = 0;
+        }
+        s_n = n;
+        s_base = base;
+    }
+    __syncthreads();
+    const unsigned n = s_n, base = s_base;
+    const double* in = what == 0 ? X.mig_land[side] : X.gho_land[side];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        append_record(P, B, in, i, base + i, what);
+    // bookkeeping by the first thread of the grid, after which the next kernel in the stream reads it
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (what == 0) {
+            S.n_in[side] = n;
+            if (side == 1)
+                S.n_own = S.n_keep + S.n_in[0] + n;
+        } else {
+            S.g_in[side] = n;
+        }
+    }
 }
 
 // After the step: my vote on "rebuild before the lists go stale?" goes to every rank; then the votes of the PREVIOUS

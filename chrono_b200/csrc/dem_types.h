@@ -157,6 +157,10 @@ struct SlabDev {
     unsigned n_out[2];      // spheres leaving to the left / right neighbour
     unsigned n_gsend[2];    // owned spheres whose copies the left / right neighbour needs as ghosts
     unsigned want_rebuild;  // this rank's Verlet skin is (about to be) used up
+    // device-driven rebuild (P2P mode): what arrived, and the resulting layout [owned | ghosts from left | from right]
+    unsigned n_in[2];       // migrants received from the left / right neighbour
+    unsigned g_in[2];       // ghosts received from the left / right neighbour
+    unsigned n_own;         // n_keep + n_in[0] + n_in[1]
 };
 
 // Direct peer-to-peer halo (slab mode, one process per GPU on one NVSwitch box).  Every rank exposes one region through
@@ -168,6 +172,9 @@ constexpr int kMaxRanks = 8;
 struct P2PCtl {
     unsigned long long arrive[2][2];         // [0: from the left neighbour, 1: from the right][parity] = step that landed
     unsigned long long vote[8][kMaxRanks];   // [step & 7][rank] = (step << 1) | wants_rebuild
+    // rebuild: migrating spheres and the new ghost set are stored into the neighbour's landing buffers as well
+    unsigned long long mig_arrive[2], gho_arrive[2];  // [from side] = number of the rebuild whose records landed
+    unsigned mig_count[2], gho_count[2];              // how many
 };
 constexpr size_t kP2PCtlBytes = 1024;        // control block padded; landing buffers follow
 
@@ -180,6 +187,11 @@ struct P2PDev {
     unsigned long long* host_vote; // pinned, mapped: [step & 7] = (step << 1) | any rank wants a rebuild
     int rank, world, ahead;
     unsigned long long first_step; // first step that ran in P2P mode: votes of earlier steps do not exist
+    double* mig_land[2];           // my landing buffers for migrants / ghost records [from side]
+    double* gho_land[2];
+    double* peer_mig[2];           // [0: left neighbour, 1: right]: THEIR landing buffer for records coming from me
+    double* peer_gho[2];
+    unsigned cap_mig, cap_gho;     // records per landing buffer
 };
 
 struct Buffers {

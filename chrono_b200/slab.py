@@ -82,6 +82,16 @@ class SlabDriver:
     def rebuild(self):
         b = self.b
         t0 = b.clock() if hasattr(b, "clock") else None  # synchronising wall clock: rebuilds only
+        if getattr(self, "p2p", False):
+            # device-driven: records land in the neighbours' buffers by peer stores, one host sync for the new layout
+            c = b.p2p_rebuild(self.lo, self.hi)
+            self.n_recv, self.n_send = (c[1], c[2]), (c[3], c[4])
+            self.stats["migrated"] += c[5] + c[6]
+            self.stats["ghost_bytes"] += int((c[1] + c[2]) * b.ghost_doubles * 8)
+            self.stats["rebuilds"] += 1
+            self.fresh = True
+            self.stats["rebuild_s"] = self.stats.get("rebuild_s", 0.0) + (b.clock() - t0)
+            return
         n_keep, out_l, out_r = b.extract(self.lo, self.hi)
         if self.left is None and out_l.shape[0] or self.right is None and out_r.shape[0]:
             raise RuntimeError("a sphere left the outermost slab (bounds must be infinite there)")
@@ -258,6 +268,12 @@ class EngineBackend:
     def p2p_import(self, rank, world, handles, ahead):
         hs = np.ascontiguousarray(handles, dtype=np.uint8)
         self.g._ck(self.L.dem_b200_p2p_import(self.h, int(rank), int(world), hs.ctypes.data_as(C.c_void_p), int(ahead)))
+
+    def p2p_rebuild(self, lo, hi):
+        c = (C.c_size_t * 7)()
+        self.g._ck(self.L.dem_b200_p2p_rebuild(self.h, C.c_double(lo), C.c_double(hi), c))
+        self.n_send = [c[3], c[4]]
+        return [int(x) for x in c]
 
     def p2p_poll_vote(self, step):
         f = C.c_int(0)

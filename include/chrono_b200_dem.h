@@ -224,6 +224,11 @@ int dem_b200_mgpu_want_rebuild_ahead(dem_b200_system* s, int* flag_dev, int step
 int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64);
 int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* handles /* world x 64 bytes */, int steps_ahead);
 int dem_b200_p2p_poll_vote(dem_b200_system* s, unsigned long long step, int* flag);
+/* The rebuild protocol above (extract .. finish_rebuild) without a collective or a per-message host round trip: migrants
+ * and ghost records are stored into the neighbours' landing buffers, counts and arrival flags follow; one host
+ * synchronisation at the end.  Every rank calls it at the same step.  counts (may be NULL) = owned spheres, ghosts
+ * received from left / right, owned spheres sent as ghosts to left / right, spheres migrated out to left / right. */
+int dem_b200_p2p_rebuild(dem_b200_system* s, double lo, double hi, size_t counts[7]);
 unsigned long long dem_b200_step_count(const dem_b200_system* s); /* time steps enqueued so far (numbering of the votes) */
 
 /* owned spheres (ghosts excluded) in arbitrary order: global id, pos, vel, omega to HOST buffers */
