@@ -221,6 +221,7 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
     const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
     C.max_dx2 = 0ull;
     C.travel += dx;
+    C.last_dx = dx;
     const bool rebuild = (C.need_rebuild != 0) || (!P.external_rebuild && !(C.travel < 0.499 * P.skin));
     if (C.nrebuilds >= 1)
         C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
@@ -2099,6 +2100,18 @@ __global__ void __launch_bounds__(256) k_mgpu_unpack(Buffers B, int dir, unsigne
     q[2] = make_double2(o[7], o[8]);
 }
 // Would the next step have to rebuild?  (travel so far + the displacement of the step that just ran)
+// Travel since the last rebuild once the step that just ran and `ahead` more have been accounted for: those are assumed
+// to move the spheres as far as the last one did, extrapolated linearly if the displacement per step is growing
+// (accelerating bed), plus 25 %.
+__device__ __forceinline__ double predicted_travel(const Ctrl& C, int ahead) {
+    const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
+    const double grow = fmax(dx - C.last_dx, 0.0);
+    double t = C.travel + dx;
+    for (int a = 1; a <= ahead; a++)
+        t += 1.25 * (dx + (double)a * grow);
+    return t;
+}
+
 // `ahead` = further steps the caller will run before it acts on the answer (a driver that reads the flag one step late
 // passes 1): they are assumed to move the spheres as far as the last step did; k_step_begin traps the case where that
 // assumption fails (ERR_SKIN_EXCEEDED).
@@ -2106,9 +2119,7 @@ __global__ void k_mgpu_want(Params P, Buffers B, int* flag_out, int ahead) {
     if (threadIdx.x || blockIdx.x)
         return;
     const Ctrl& C = *B.ctrl;
-    const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
-    const double t = C.travel + dx * (double)(1 + ahead);
-    *flag_out = (C.need_rebuild != 0 || !(t < 0.499 * P.skin)) ? 1 : 0;
+    *flag_out = (C.need_rebuild != 0 || !(predicted_travel(C, ahead) < 0.499 * P.skin)) ? 1 : 0;
 }
 // --------------------------------------------------------------------------------------------
 // direct P2P halo + vote (see P2PCtl in dem_types.h).  `step` = number of the time step the data belongs to = the
@@ -2253,9 +2264,7 @@ __global__ void k_p2p_vote(Params P, Buffers B, P2PDev X) {
     const unsigned long long step = C.nsteps;  // the step that just ran
     const unsigned r = threadIdx.x;
     if (r < (unsigned)X.world) {
-        const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
-        const double t = C.travel + dx * (double)(1 + X.ahead);
-        const unsigned long long flag = (C.need_rebuild != 0 || !(t < 0.499 * P.skin)) ? 1ull : 0ull;
+        const unsigned long long flag = (C.need_rebuild != 0 || !(predicted_travel(C, X.ahead) < 0.499 * P.skin)) ? 1ull : 0ull;
         st_release_sys(&X.peer[r]->vote[step & 7ull][X.rank], (step << 1) | flag);
     }
     if (step <= X.first_step)

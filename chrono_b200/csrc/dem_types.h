@@ -142,6 +142,7 @@ struct Ctrl {
     unsigned long long bbox[6];   // order-preserving encoded doubles: min xyz, max xyz of the sphere AABBs
     unsigned long long max_dx2;   // raw bits of max |x_new - x_old|^2 over the spheres, last step
     double travel;                // sum of per-step max displacements since the last rebuild
+    double last_dx;               // max displacement of the step before the last one (growth estimate of the slab vote)
     // search grid (cells >= 2 rmax + skin), x fastest
     double s_org[3], s_inv[3];
     int s_dim[3];

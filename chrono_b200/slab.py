@@ -321,7 +321,8 @@ class EngineBackend:
         return sid[:k], pos[:k], vel[:k], om[:k]
 
 
-def make_engine_slab(cfg, scene_walls, pos, radius, ids, vel=None, omega=None, capacity=None, rmax_global=None, add_walls=None):
+def make_engine_slab(cfg, scene_walls, pos, radius, ids, vel=None, omega=None, capacity=None, rmax_global=None, add_walls=None,
+                     meshes=None):
     """Create a slab-mode engine for the given owned spheres (global ids `ids`) on the current CUDA device/stream."""
     from . import dem
     g = dem.DemSystem(cfg)
@@ -331,6 +332,9 @@ def make_engine_slab(cfg, scene_walls, pos, radius, ids, vel=None, omega=None, c
         g.add_box_wall(p, h)
     if add_walls:
         add_walls(g)
+    for M in (meshes or []):  # meshes (and walls) are replicated on every rank; each rank keeps the wrench of ITS spheres
+        m = g.add_mesh(M["tri"], M.get("mass", 1.0))
+        g.set_mesh_motion(m, M.get("pos"), M.get("rot"), M.get("vel"), M.get("omega"))
     n = len(ids)
     capacity = capacity or int(1.5 * n + 4096)
     g.set_spheres(pos, radius, vel=vel, omega=omega)
