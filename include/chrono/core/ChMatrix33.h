@@ -13,6 +13,9 @@ class ChMatrix33 {
     explicit ChMatrix33(Real diag) { SetIdentity(); m[0][0] = m[1][1] = m[2][2] = diag; }
     template <class R2>
     explicit ChMatrix33(const ChQuaternion<R2>& q) { SetFromQuaternion(q); }
+    /// Diagonal matrix (scaling), as ChMatrix33(const ChVector3d&) of the reference.
+    template <class R2>
+    explicit ChMatrix33(const ChVector3<R2>& diag) { SetIdentity(); m[0][0] = (Real)diag.x(); m[1][1] = (Real)diag.y(); m[2][2] = (Real)diag.z(); }
     void SetIdentity() { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = (i == j) ? (Real)1 : (Real)0; }
     Real& operator()(int i, int j) { return m[i][j]; }
     const Real& operator()(int i, int j) const { return m[i][j]; }

@@ -48,15 +48,15 @@ typedef ChQuaternion<double> ChQuaterniond;
 typedef ChQuaternion<float> ChQuaternionf;
 const ChQuaterniond QUNIT(1., 0., 0., 0.);
 
-template <class Real>
-ChQuaternion<Real> QuatFromAngleAxis(Real angle, const ChVector3<Real>& axis) {
-    ChQuaternion<Real> q;
+// src/chrono/core/ChRotation.h: rotations from angle-axis, double precision
+inline ChQuaterniond QuatFromAngleAxis(double angle, const ChVector3<double>& axis) {
+    ChQuaterniond q;
     q.SetFromAngleAxis(angle, axis);
     return q;
 }
-template <class Real> ChQuaternion<Real> QuatFromAngleX(Real a) { return QuatFromAngleAxis(a, ChVector3<Real>(1, 0, 0)); }
-template <class Real> ChQuaternion<Real> QuatFromAngleY(Real a) { return QuatFromAngleAxis(a, ChVector3<Real>(0, 1, 0)); }
-template <class Real> ChQuaternion<Real> QuatFromAngleZ(Real a) { return QuatFromAngleAxis(a, ChVector3<Real>(0, 0, 1)); }
+inline ChQuaterniond QuatFromAngleX(double a) { return QuatFromAngleAxis(a, ChVector3<double>(1, 0, 0)); }
+inline ChQuaterniond QuatFromAngleY(double a) { return QuatFromAngleAxis(a, ChVector3<double>(0, 1, 0)); }
+inline ChQuaterniond QuatFromAngleZ(double a) { return QuatFromAngleAxis(a, ChVector3<double>(0, 0, 1)); }
 
 }  // namespace chrono
 #endif

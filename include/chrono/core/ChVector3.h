@@ -3,6 +3,8 @@
 #ifndef CHRONO_B200_CHVECTOR3_H
 #define CHRONO_B200_CHVECTOR3_H
 #include <cmath>
+#include "chrono/core/ChTypes.h"
+#include "chrono/utils/ChConstants.h"
 
 namespace chrono {
 
