@@ -27,13 +27,15 @@ constexpr double kPi = 3.141592653589793238462643383279;
 }
 }  // namespace
 
-enum class BCKind { PLANE, ZCYL, UNSUPPORTED };
+enum class BCKind { PLANE, ZCYL, SPHERE, ZCONE, PLATE };
 
 struct BCInfo {
     BCKind kind = BCKind::PLANE;
     double pos[3] = {0, 0, 0};     // reference position (plane point / cylinder axis point), user units
     double normal[3] = {0, 0, 1};  // plane normal
-    double radius = 0;             // cylinder
+    double radius = 0;             // cylinder / ball
+    double slope = 0, hmin = 0, hmax = 0;  // cone
+    double vel[3] = {0, 0, 0};     // ball velocity (SetBCSphereVelocity)
     bool spheres_inside = true;
     bool track_forces = false;
     bool enabled = true;
@@ -297,15 +299,79 @@ size_t ChSystemDem::CreateBCCylinderZ(const ChVector3f& center, float radius, bo
     m_sys->bcs.push_back(bc);
     return m_sys->bcs.size() - 1;
 }
-size_t ChSystemDem::CreateBCSphere(const ChVector3f&, float, bool, bool, float) {
-    fail("CreateBCSphere: not supported yet (SURVEY 8f item 4; never called in-tree outside chrono_dem)");
+// Ball boundary (reference: ChSystemDem_impl.cpp:683-721).  outward_normal == false: obstacle the spheres stay outside of;
+// true: cavity.  The reference integrates a ball with mass under the reaction force on the host (:867-903); here the ball
+// moves only through SetBCSpherePosition / SetBCSphereVelocity / SetBCOffsetFunction.
+size_t ChSystemDem::CreateBCSphere(const ChVector3f& center, float radius, bool outward_normal, bool track_forces, float /*mass*/) {
+    if (m_sys->initialized) fail("boundary conditions must be created before Initialize");
+    BCInfo bc;
+    bc.kind = BCKind::SPHERE;
+    bc.pos[0] = center.x(); bc.pos[1] = center.y(); bc.pos[2] = center.z();
+    bc.radius = radius;
+    bc.spheres_inside = outward_normal;
+    bc.track_forces = track_forces;
+    m_sys->bcs.push_back(bc);
+    return m_sys->bcs.size() - 1;
 }
-size_t ChSystemDem::CreateBCConeZ(const ChVector3f&, float, float, float, bool, bool) {
-    fail("CreateBCConeZ: not supported yet (SURVEY 8f item 4; never called in-tree outside chrono_dem)");
+// Cone about z (reference: ChSystemDem_impl.cpp:723-750): hmax / hmin are world z; outward_normal == false keeps the
+// spheres above the surface (a hopper), true below it.
+size_t ChSystemDem::CreateBCConeZ(const ChVector3f& tip, float slope, float hmax, float hmin, bool outward_normal, bool track_forces) {
+    if (m_sys->initialized) fail("boundary conditions must be created before Initialize");
+    BCInfo bc;
+    bc.kind = BCKind::ZCONE;
+    bc.pos[0] = tip.x(); bc.pos[1] = tip.y(); bc.pos[2] = tip.z();
+    bc.slope = slope; bc.hmax = hmax; bc.hmin = hmin;
+    bc.spheres_inside = !outward_normal;
+    bc.track_forces = track_forces;
+    m_sys->bcs.push_back(bc);
+    return m_sys->bcs.size() - 1;
 }
-size_t ChSystemDem::CreateCustomizedPlate(const ChVector3f&, const ChVector3f&, float) {
-    fail("CreateCustomizedPlate: not supported (the reference has no force case for PLATE either, SURVEY Q5)");
+// The reference registers the plate but no kernel has a force case for BC_type::PLATE: the id is handed out,
+// the boundary exerts no force.
+size_t ChSystemDem::CreateCustomizedPlate(const ChVector3f& pos_center, const ChVector3f& normal, float /*hdim_y*/) {
+    if (m_sys->initialized) fail("boundary conditions must be created before Initialize");
+    BCInfo bc;
+    bc.kind = BCKind::PLATE;
+    bc.pos[0] = pos_center.x(); bc.pos[1] = pos_center.y(); bc.pos[2] = pos_center.z();
+    bc.normal[0] = normal.x(); bc.normal[1] = normal.y(); bc.normal[2] = normal.z();
+    bc.enabled = false;
+    m_sys->bcs.push_back(bc);
+    return m_sys->bcs.size() - 1;
 }
+void ChSystemDem::SetBCSpherePosition(size_t id, const ChVector3f& pos) {
+    if (id >= m_sys->bcs.size() || m_sys->bcs[id].kind != BCKind::SPHERE) fail("SetBCSpherePosition: not a sphere boundary");
+    BCInfo& bc = m_sys->bcs[id];
+    bc.pos[0] = pos.x(); bc.pos[1] = pos.y(); bc.pos[2] = pos.z();
+    if (m_sys->initialized)
+        m_sys->check(dem_b200_set_wall_state(m_sys->h, bc.wall, bc.pos, bc.vel), "SetBCSpherePosition");
+}
+void ChSystemDem::SetBCSphereVelocity(size_t id, const ChVector3f& v) {
+    if (id >= m_sys->bcs.size() || m_sys->bcs[id].kind != BCKind::SPHERE) fail("SetBCSphereVelocity: not a sphere boundary");
+    BCInfo& bc = m_sys->bcs[id];
+    bc.vel[0] = v.x(); bc.vel[1] = v.y(); bc.vel[2] = v.z();
+    if (m_sys->initialized)
+        m_sys->check(dem_b200_set_wall_state(m_sys->h, bc.wall, bc.pos, bc.vel), "SetBCSphereVelocity");
+}
+ChVector3f ChSystemDem::GetBCSpherePosition(size_t id) const {
+    if (id >= m_sys->bcs.size() || m_sys->bcs[id].kind != BCKind::SPHERE) fail("GetBCSpherePosition: not a sphere boundary");
+    const BCInfo& bc = m_sys->bcs[id];
+    return ChVector3f((float)bc.pos[0], (float)bc.pos[1], (float)bc.pos[2]);
+}
+ChVector3f ChSystemDem::GetBCSphereVelocity(size_t id) const {
+    if (id >= m_sys->bcs.size() || m_sys->bcs[id].kind != BCKind::SPHERE) fail("GetBCSphereVelocity: not a sphere boundary");
+    const BCInfo& bc = m_sys->bcs[id];
+    return ChVector3f((float)bc.vel[0], (float)bc.vel[1], (float)bc.vel[2]);
+}
+// Declared by the reference, not provided by this engine (never called in-tree outside src/chrono_dem): fail loudly.
+void ChSystemDem::SetBCPlaneRotation(size_t, ChVector3d, ChVector3d) { fail("SetBCPlaneRotation is not supported"); }
+ChVector3f ChSystemDem::GetParticleLinAcc(int) const { fail("GetParticleLinAcc is not supported"); }
+void ChSystemDem::WriteContactInfoFile(const std::string&) const { fail("WriteContactInfoFile / SetRecordingContactInfo are not supported"); }
+ChVector3f ChSystemDem::getRollingFrictionTorque(unsigned int, unsigned int) { fail("getRollingFrictionTorque is not supported"); }
+ChVector3f ChSystemDem::getSlidingFrictionForce(unsigned int, unsigned int) { fail("getSlidingFrictionForce is not supported"); }
+ChVector3f ChSystemDem::getNormalForce(unsigned int, unsigned int) { fail("getNormalForce is not supported"); }
+ChVector3f ChSystemDem::getRollingVrot(unsigned int, unsigned int) { fail("getRollingVrot is not supported"); }
+float ChSystemDem::getRollingCharContactTime(unsigned int, unsigned int) { fail("getRollingCharContactTime is not supported"); }
+void ChSystemDem::getNeighbors(unsigned int, std::vector<unsigned int>&) { fail("getNeighbors is not supported"); }
 bool ChSystemDem::DisableBCbyID(size_t id) {
     if (id >= m_sys->bcs.size()) return false;
     m_sys->bcs[id].enabled = false;
@@ -360,8 +426,12 @@ void ChSystemDem::Initialize() {
         }
     bool track = false;
     for (auto& bc : S.bcs) {
-        if (bc.kind == BCKind::PLANE)
-            bc.wall = dem_b200_add_plane_wall(S.h, bc.pos, bc.normal);
+        if (bc.kind == BCKind::PLANE || bc.kind == BCKind::PLATE)
+            bc.wall = dem_b200_add_plane_wall(S.h, bc.pos, bc.normal);  // a PLATE is created disabled: no force case upstream
+        else if (bc.kind == BCKind::SPHERE)
+            bc.wall = dem_b200_add_sphere_wall(S.h, bc.pos, bc.radius, bc.spheres_inside ? 0 : 1);
+        else if (bc.kind == BCKind::ZCONE)
+            bc.wall = dem_b200_add_zcone_wall(S.h, bc.pos, bc.slope, bc.hmin, bc.hmax, bc.spheres_inside ? 1 : 0);
         else
             bc.wall = dem_b200_add_zcylinder_wall(S.h, bc.pos, bc.radius, bc.spheres_inside ? 1 : 0);
         S.check(bc.wall, "CreateBC");

@@ -185,10 +185,13 @@ void refresh_params(dem_b200_system* s) {
     WS.has_bb = 0;
     for (int w = 0; w < P.nW; w++) {
         Wall& W = WS.w[w];
-        if (W.type != WALL_BOX)
+        if (W.type != WALL_BOX && !(W.type == WALL_SPHERE && W.hdims[1] > 0))
             continue;
         double ext[3];
-        abs_rotate(W.rot, W.hdims, ext);  // ComputeAABBBox, ChCollisionSystemMulticore.cpp:395-406 (envelope 0)
+        if (W.type == WALL_BOX)
+            abs_rotate(W.rot, W.hdims, ext);  // ComputeAABBBox, ChCollisionSystemMulticore.cpp:395-406 (envelope 0)
+        else
+            ext[0] = ext[1] = ext[2] = W.hdims[0];  // a fixed sphere shape: ComputeAABBSphere, :376-385
         for (int k = 0; k < 3; k++) {
             W.amin[k] = W.pos[k] - ext[k];
             W.amax[k] = W.pos[k] + ext[k];
@@ -610,6 +613,20 @@ int dem_b200_add_zcylinder_wall(dem_b200_system* s, const double center[3], doub
         return DEMB200_EINVAL;
     double hd[3] = {radius, spheres_inside ? 1.0 : -1.0, 0.0};
     return add_wall(s, WALL_ZCYL, center, nullptr, hd);
+}
+
+int dem_b200_add_sphere_wall(dem_b200_system* s, const double center[3], double radius, int spheres_outside) {
+    if (!(radius > 0))
+        return DEMB200_EINVAL;
+    double hd[3] = {radius, spheres_outside ? 1.0 : -1.0, 0.0};
+    return add_wall(s, WALL_SPHERE, center, nullptr, hd);
+}
+int dem_b200_add_zcone_wall(dem_b200_system* s, const double tip[3], double slope, double hmin, double hmax, int spheres_above) {
+    if (!(slope > 0) || !(hmax > hmin))
+        return DEMB200_EINVAL;
+    double hd[3] = {slope, hmin, hmax};
+    double side[4] = {spheres_above ? 1.0 : -1.0, 0.0, 0.0, 0.0};
+    return add_wall(s, WALL_ZCONE, tip, side, hd);
 }
 
 static int upload_walls(dem_b200_system* s) {

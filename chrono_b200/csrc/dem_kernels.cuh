@@ -846,6 +846,15 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                        W.amin[1] <= me.y + reach && me.z - reach <= W.amax[2] && W.amin[2] <= me.z + reach;
             } else if (W.type == WALL_PLANE) {
                 near = (me.x - W.pos[0]) * W.hdims[0] + (me.y - W.pos[1]) * W.hdims[1] + (me.z - W.pos[2]) * W.hdims[2] < reach;
+            } else if (W.type == WALL_SPHERE) {
+                const double dc = sqrt((me.x - W.pos[0]) * (me.x - W.pos[0]) + (me.y - W.pos[1]) * (me.y - W.pos[1]) +
+                                       (me.z - W.pos[2]) * (me.z - W.pos[2]));
+                near = (W.hdims[1] > 0) ? (dc - reach < W.hdims[0]) : (dc + reach > W.hdims[0]);
+            } else if (W.type == WALL_ZCONE) {
+                const double rho = sqrt((me.x - W.pos[0]) * (me.x - W.pos[0]) + (me.y - W.pos[1]) * (me.y - W.pos[1]));
+                // |height above the surface| bounds the distance to it from above
+                near = fabs((me.z - W.pos[2]) - W.hdims[0] * rho) < reach * sqrt(1.0 + W.hdims[0] * W.hdims[0]) + reach &&
+                       me.z < W.hdims[2] + reach && me.z > W.hdims[1] - reach;
             } else {
                 const double dxy = sqrt((me.x - W.pos[0]) * (me.x - W.pos[0]) + (me.y - W.pos[1]) * (me.y - W.pos[1]));
                 near = (W.hdims[1] > 0) ? (dxy + reach > W.hdims[0]) : (dxy - reach < W.hdims[0]);
@@ -1274,6 +1283,63 @@ __device__ __forceinline__ bool zcyl_sphere_dev(const Wall& W, V3 pos2, double r
     return true;
 }
 
+// Ball (Chrono::Dem CreateBCSphere, ChSystemDem.h:206; force form addBCForces_Sphere_*, ChDemBoundaryConditions.cuh:155-215):
+// hdims = (radius, side).  side +1: obstacle -- exactly Multicore's sphere_sphere against a fixed sphere (rounding pinned,
+// ChNarrowphasePRIMS.cpp:40-72); side -1: cavity (spheres live inside the ball), concave effective radius.
+__device__ __forceinline__ bool ball_sphere_dev(const Wall& W, V3 pos2, double r2, Geom& g) {
+    const double Rb = W.hdims[0];
+    const V3 c = mk(W.pos[0], W.pos[1], W.pos[2]);
+    const V3 delta = sub_rn(pos2, c);
+    const double d2 = dot_rn(delta, delta);
+    if (W.hdims[1] > 0) {
+        const double rs = __dadd_rn(Rb, r2);
+        if (d2 >= __dmul_rn(rs, rs) || d2 < 1e-12)
+            return false;
+        const double dist = sqrt(d2);
+        g.n = div_rn(delta, dist);
+        g.pt1 = add_rn(c, scale_rn(Rb, g.n));
+        g.pt2 = sub_rn(pos2, scale_rn(r2, g.n));
+        g.depth = __dsub_rn(dist, rs);
+        g.erad = __ddiv_rn(__dmul_rn(Rb, r2), rs);
+        return true;
+    }
+    const double dist = sqrt(d2);
+    const double gap = Rb - dist;  // distance from the sphere centre to the shell
+    if (gap >= r2 || !(dist > 1e-12 * Rb) || !(Rb > r2))
+        return false;
+    g.n = delta * (-1.0 / dist);  // from the shell towards the sphere = towards the centre
+    g.depth = gap - r2;
+    g.pt1 = pos2 - gap * g.n;
+    g.pt2 = pos2 - r2 * g.n;
+    g.erad = Rb * r2 / (Rb - r2);
+    return true;
+}
+
+// Cone about the z axis (Chrono::Dem CreateBCConeZ, ChSystemDem.h:212; geometry of addBCForces_ZCone_frictionless,
+// ChDemBoundaryConditions.cuh:217-291): surface z - tip.z = slope * rho, active for hmin < z < hmax; closest point along
+// the generator line below / above the sphere.  One-sided: rot[0] = +1 keeps spheres above the surface (hopper), -1 below.
+__device__ __forceinline__ bool zcone_sphere_dev(const Wall& W, V3 pos2, double r2, Geom& g) {
+    if (pos2.z >= W.hdims[2] || pos2.z <= W.hdims[1])
+        return false;
+    const V3 rel = pos2 - mk(W.pos[0], W.pos[1], W.pos[2]);
+    const double rho = sqrt(rel.x * rel.x + rel.y * rel.y);
+    const V3 l = mk(rel.x, rel.y, W.hdims[0] * rho);  // from the tip along the generator under the sphere
+    const double ll = dot(l, l);
+    if (!(ll > 0))
+        return false;
+    const V3 cv = rel - (dot(rel, l) / ll) * l;  // from the surface to the sphere centre
+    const double dist = len(cv);
+    const double side = rel.z - W.hdims[0] * rho;  // > 0: above the surface
+    if (dist >= r2 || !(dist > 0) || side * W.rot[0] <= 0)
+        return false;
+    g.n = cv / dist;
+    g.depth = dist - r2;
+    g.pt1 = pos2 - cv;
+    g.pt2 = pos2 - r2 * g.n;
+    g.erad = r2;
+    return true;
+}
+
 // snap_to_triangle (ChCollisionUtilsPRIMS.cpp:41-106) and triangle_sphere (ChNarrowphasePRIMS.cpp:379-437), rounding
 // pinned: the hit / no-hit decision defines the contact-pair set and must not depend on FMA contraction.
 __device__ __forceinline__ bool snap_to_triangle_rn(V3 A, V3 Bv, V3 Cv, V3 Pp, V3& res) {
@@ -1554,6 +1620,10 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
             bool hit;
             if (W.type == WALL_ZCYL) {
                 hit = zcyl_sphere_dev(W, mpos, me.w, g);
+            } else if (W.type == WALL_SPHERE) {
+                hit = ball_sphere_dev(W, mpos, me.w, g);
+            } else if (W.type == WALL_ZCONE) {
+                hit = zcone_sphere_dev(W, mpos, me.w, g);
             } else if (W.type == WALL_BOX) {
                 // broadphase AABB overlap on origin-offset boxes (ChCollisionUtils.h:83-87)
                 if (!(amin[0] <= G.wmax[w][0] && G.wmin[w][0] <= amax[0] && amin[1] <= G.wmax[w][1] &&

@@ -42,7 +42,7 @@ enum : unsigned {
     ERR_SKIN_EXCEEDED = 128u
 };
 
-enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1, WALL_ZCYL = 2 };
+enum WallType : int { WALL_BOX = 0, WALL_PLANE = 1, WALL_ZCYL = 2, WALL_SPHERE = 3, WALL_ZCONE = 4 };
 
 // Composite material of a contact class, widened from the float values the reference computes
 // (src/chrono/physics/ChContactMaterialSMC.cpp:107-130).
@@ -58,7 +58,9 @@ struct Wall {
     int enabled;       // DisableBCbyID / EnableBCbyID
     double pos[3];     // box centre / plane point / a point on the cylinder axis (world)
     double rot[4];     // box orientation (w,x,y,z)
-    double hdims[3];   // box half dimensions / plane unit normal / (cylinder radius, +1 spheres inside | -1 outside, -)
+    double hdims[3];   // box half dimensions / plane unit normal / (cylinder radius, +1 spheres inside | -1 outside, -) /
+                       // (ball radius, +1 obstacle | -1 cavity, -) / cone (slope dz/dr, hmin, hmax), rot[0] = +1 spheres above
+                       // the cone surface (inside a hopper) | -1 below it
     double vel[3];     // velocity of the wall body (moving boundaries)
     double amin[3], amax[3];  // world AABB (ChCollisionSystemMulticore.cpp:395-406); boxes only
 };

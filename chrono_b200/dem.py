@@ -151,6 +151,15 @@ class DemSystem:
         p, q, h = _f64(pos), _f64(rot), _f64(hdims)
         return self._ck(self.L.dem_b200_add_box_wall(self.h, _dp(p), _dp(q), _dp(h)))
 
+    def add_sphere_wall(self, center, radius, spheres_outside=True):
+        c = _f64(center)
+        return self._ck(self.L.dem_b200_add_sphere_wall(self.h, _dp(c), C.c_double(radius), int(spheres_outside)))
+
+    def add_zcone_wall(self, tip, slope, hmin, hmax, spheres_above=True):
+        t = _f64(tip)
+        return self._ck(self.L.dem_b200_add_zcone_wall(self.h, _dp(t), C.c_double(slope), C.c_double(hmin), C.c_double(hmax),
+                                                       int(spheres_above)))
+
     def add_plane_wall(self, pos, normal):
         p, nrm = _f64(pos), _f64(normal)
         return self._ck(self.L.dem_b200_add_plane_wall(self.h, _dp(p), _dp(nrm)))

@@ -99,6 +99,12 @@ int dem_b200_add_plane_wall(dem_b200_system* s, const double pos[3], const doubl
 /* Z-axis cylinder (Chrono::Dem CreateBCCylinderZ, src/chrono_dem/physics/ChSystemDem.h:235): spheres_inside != 0 ->
  * container wall (normal towards the axis), else an obstacle. */
 int dem_b200_add_zcylinder_wall(dem_b200_system* s, const double center[3], double radius, int spheres_inside);
+/* Ball (Chrono::Dem CreateBCSphere, src/chrono_dem/physics/ChSystemDem.h:206): spheres_outside != 0 -> obstacle, identical
+ * to Multicore's sphere_sphere against a fixed sphere of that radius; else a spherical cavity holding the spheres. */
+int dem_b200_add_sphere_wall(dem_b200_system* s, const double center[3], double radius, int spheres_outside);
+/* Cone about the z axis (Chrono::Dem CreateBCConeZ, src/chrono_dem/physics/ChSystemDem.h:212): surface
+ * z - tip.z = slope * rho, active for hmin < z < hmax (world z); spheres_above != 0 -> hopper (spheres above the surface). */
+int dem_b200_add_zcone_wall(dem_b200_system* s, const double tip[3], double slope, double hmin, double hmax, int spheres_above);
 /* Move a wall (SetBCOffsetFunction, src/chrono_dem/physics/ChSystemDem_impl.cpp:863-948): new reference point and
  * velocity (either may be NULL).  Legal between steps; does not invalidate the step graph. */
 int dem_b200_set_wall_state(dem_b200_system* s, int wall, const double pos[3], const double vel[3]);

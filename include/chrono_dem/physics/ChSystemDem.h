@@ -102,6 +102,11 @@ class CH_DEM_API ChSystemDem {
     bool DisableBCbyID(size_t BC_id);
     bool EnableBCbyID(size_t BC_id);
     bool SetBCOffsetFunction(size_t BC_id, const GranPositionFunction& offset_function);
+    void SetBCSpherePosition(size_t sphere_bc_id, const ChVector3f& pos);
+    void SetBCSphereVelocity(size_t sphere_bc_id, const ChVector3f& velo);
+    void SetBCPlaneRotation(size_t plane_id, ChVector3d center, ChVector3d omega);  ///< declared for source compatibility; throws
+    ChVector3f GetBCSpherePosition(size_t sphere_id) const;
+    ChVector3f GetBCSphereVelocity(size_t sphere_id) const;
     void setBDWallsMotionFunction(const GranPositionFunction& pos_fn);
 
     void SetParticlePosition(int nSphere, const ChVector3d pos);
@@ -119,6 +124,7 @@ class CH_DEM_API ChSystemDem {
     ChVector3f GetParticlePosition(int nSphere) const;
     ChVector3f GetParticleVelocity(int nSphere) const;
     ChVector3f GetParticleAngVelocity(int nSphere) const;
+    ChVector3f GetParticleLinAcc(int nSphere) const;  ///< declared for source compatibility; throws
     float GetParticlesKineticEnergy() const;
     ChVector3f GetBCPlanePosition(size_t plane_id) const;
     bool IsFixed(int nSphere) const;
@@ -134,6 +140,14 @@ class CH_DEM_API ChSystemDem {
     void WriteCheckpointFile(const std::string& outfilename);
     void WriteParticleFile(const std::string& outfilename) const;
     void WriteContactHistoryFile(const std::string& outfilename) const;
+    /// Per-contact debugging queries of the reference (ChSystemDem.h:320-341): declared for source compatibility; they throw.
+    void WriteContactInfoFile(const std::string& outfilename) const;
+    ChVector3f getRollingFrictionTorque(unsigned int i, unsigned int j);
+    ChVector3f getSlidingFrictionForce(unsigned int i, unsigned int j);
+    ChVector3f getNormalForce(unsigned int i, unsigned int j);
+    ChVector3f getRollingVrot(unsigned int i, unsigned int j);
+    float getRollingCharContactTime(unsigned int i, unsigned int j);
+    void getNeighbors(unsigned int ID, std::vector<unsigned int>& neighborList);
     size_t EstimateMemUsage() const;
     float GetRTF() const { return m_RTF; }
 

@@ -30,6 +30,10 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mas
         o.add_body(wall_mass, (1, 1, 1), (0, 0, 0), fixed=True)
         for p, h in scene["walls"]:
             o.add_box(0, m_w, p, h)
+    # ball boundaries (Chrono::Dem CreateBCSphere): fixed sphere bodies right behind the container, shapes nW, nW+1, ...
+    for c, rb in scene.get("balls", []):
+        b = o.add_spheres(np.asarray(c, dtype=np.float64)[None, :], [rb], [wall_mass], m_w)
+        o.L.orc_set_body_fixed(o.h, int(b), 1)
     # mesh bodies follow the container and precede the spheres: triangle shapes nW .. nW+nT-1 (one per facet)
     o.mesh_bodies = []
     if scene.get("meshes"):
@@ -47,6 +51,7 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mas
     o.first_sphere_body = first
     o.num_walls = len(scene["walls"])
     o.num_triangles = sum(len(M["tri"]) for M in scene.get("meshes", []))
+    o.first_sphere_shape = len(scene["walls"]) + len(scene.get("balls", [])) + o.num_triangles
     return o
 
 
@@ -63,6 +68,8 @@ def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1
     g = dem.DemSystem(cfg)
     for p, h in scene["walls"]:
         g.add_box_wall(p, h)
+    for c, rb in scene.get("balls", []):
+        g.add_sphere_wall(c, rb, spheres_outside=True)
     for M in scene.get("meshes", []):
         m = g.add_mesh(M["tri"], M.get("mass", 1.0))
         g.set_mesh_motion(m, M.get("pos"), M.get("rot"), M.get("vel"), M.get("omega"))

@@ -32,7 +32,7 @@ def compare_step(scene, vel, omega, steps=1, tol=TOL, **kw):
     from chrono_b200 import dem
     o = common.make_oracle(scene, vel=vel, omega=omega, **kw)
     g = common.make_gpu(scene, vel=vel, omega=omega, **kw)
-    nW, n = len(scene["walls"]) + o.num_triangles, scene["n"]  # first sphere shape (walls, mesh triangles, spheres)
+    nW, n = o.first_sphere_shape, scene["n"]  # first sphere shape (walls, ball boundaries, mesh triangles, spheres)
     g.enable_recording(True, max_pairs=40 * n)
     for it in range(steps):
         # one step on both sides; the oracle keeps the bins / contacts / forces it used during that step
