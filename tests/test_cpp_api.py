@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "cpp", "_bin")
-PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling"]
+PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling", "utest_utils"]
 
 
 def build_program(name):
@@ -40,6 +40,12 @@ def run(name, *args, timeout=600):
     r = subprocess.run([exe] + list(args), capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
+
+
+def test_lookalike_utilities_cpu(tmp_path):
+    """Samplers, JSON parameter reader, data-path helpers, OBJ reader: no GPU involved."""
+    out = run("utest_utils", str(tmp_path), os.path.join(HERE, "golden", "demo_json", "mixer_small.json"))
+    assert "PASSED" in out
 
 
 @pytest.mark.gpu
