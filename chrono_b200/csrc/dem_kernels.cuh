@@ -129,7 +129,16 @@ __device__ __forceinline__ double pack_key(unsigned key, unsigned steps) { retur
 __device__ __forceinline__ unsigned rec_key(double w) { return (unsigned)__double2loint(w); }
 __device__ __forceinline__ unsigned rec_steps(double w) { return (unsigned)__double2hiint(w); }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef DEMB200_PF_L2
+#define DEMB200_PF_L2 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#if DEMB200_PF_L2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 
 // Fast reciprocal / reciprocal square root for normal, positive, well-scaled arguments: hardware seed
 // (MUFU.RCP64H / MUFU.RSQ64H, ~2^-23) + one cubically convergent correction, error <= ~1 ulp, no special-case branch.
@@ -1492,18 +1501,23 @@ __device__ __noinline__ void mesh_contacts(const Params& P, const Buffers& B, un
 // --------------------------------------------------------------------------------------------
 // fused narrowphase + force + integrate.  One thread per sphere in storage (cell) order.
 // --------------------------------------------------------------------------------------------
-constexpr int kForceThreads = 128;
+// One warp per block: there is no block-level cooperation in this kernel, and single-warp blocks free their registers and
+// shared memory the moment the warp's longest contact list is done (r01x/r01y: 128 threads 328 us, 64: 316, 32: 311).
+#ifndef DEMB200_FORCE_THREADS
+#define DEMB200_FORCE_THREADS 32
+#endif
+constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #ifndef DEMB200_P1_BATCH
 #define DEMB200_P1_BATCH 4
 #endif
 #ifndef DEMB200_EARLYPF
-#define DEMB200_EARLYPF 1
+#define DEMB200_EARLYPF 0  /* L1 prefetch of history rows / partner records at first sight: a loss since the 256-bit gathers (r01v) */
 #endif
 #ifndef DEMB200_PF2
 #define DEMB200_PF2 0
 #endif
 #ifndef DEMB200_FORCE_MINBLOCKS
-#define DEMB200_FORCE_MINBLOCKS 4
+#define DEMB200_FORCE_MINBLOCKS (512 / DEMB200_FORCE_THREADS)  /* 16 warps per SM: 128 registers per thread */
 #endif
 
 template <bool HIST, bool ROLL, bool FAST, bool REC, bool MESH>
