@@ -46,6 +46,16 @@ def build_scene_slabs(n_per_gpu, world):
                                  box_xy=(Lx * world, Ly))
 
 
+def measured_traffic(n, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload), else None."""
+    p = os.path.join(ROOT, "profiles", "force_traffic.json")
+    if n != 1000000 or not kernel.startswith("k_force") or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return float(t["dram_bytes_read"] + t["dram_bytes_write"])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -385,7 +395,8 @@ def run_ours(args):
             "contacts_per_sphere": cbar, "history_records": rows,
             "neighbor_list_rebuilds": stats["rebuilds"], "timesteps_total": stats["steps"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "kernel": dom, "kernel_ms": prof[dom], "peak_source": hbm_src,
+                         "traffic": measured_traffic(n, dom), "traffic_source": "profiles/force_traffic.json (ncu, bytes per launch)",
+                         "kernel": dom, "kernel_ms": prof[dom], "peak_source": hbm_src,
                          "algorithmic_bytes_per_sphere": B_kernel,
                          "whole_step_frac": B_step * (value / world) / 1e9 / hbm},
             "kernel_ms_per_timestep": prof, "kernel_share": {k: v / step_ms for k, v in prof.items()},
