@@ -756,6 +756,9 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         return;
     }
     const double4 me = pos[s];
+    // Two fixed bodies never make a contact in Chrono::Multicore (both inactive: ChCollisionUtilsBroadphase.cpp:131-132),
+    // and the walls / meshes belong to fixed bodies too: a fixed sphere only keeps non-fixed sphere candidates.
+    const bool me_fixed = (vel[s].meta & FLAG_FIXED) != 0;
     const int cx = cell_coord(me.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
     const int cy = cell_coord(me.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
     const int cz = cell_coord(me.z, C.s_org[2], C.s_inv[2], C.s_dim[2]);
@@ -781,6 +784,8 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                 const double d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
                 const double rs = me.w + pj.w + P.skin;
                 if (d2 > rs * rs * (1.0 + 1e-12))
+                    continue;
+                if (me_fixed && (vel[j].meta & FLAG_FIXED))
                     continue;
                 if (cnt < P.Kn) {
                     tj[cnt] = j;
@@ -810,7 +815,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     // mesh triangles within reach (r + skin/2; the mesh's own motion uses up skin like a wall's), ascending triangle
     // index, behind the sphere candidates.  ts[] keeps the staging key (shape id - shape_base, wrapping for triangles).
     int tcnt = 0;
-    if (P.nT && B.meshes->enabled) {
+    if (P.nT && B.meshes->enabled && !me_fixed) {
         const unsigned cell = (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
         const unsigned tb = B.tcell_start[cell], te = min(B.tcell_start[cell + 1], P.tri_cap);
         const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
@@ -847,7 +852,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     unsigned wc = 0;
     {
         const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
-        for (int w = 0; w < P.nW; w++) {
+        for (int w = 0; w < (me_fixed ? 0 : P.nW); w++) {
             const Wall& W = B.walls->w[w];
             bool near;
             if (W.type == WALL_BOX) {

@@ -48,6 +48,9 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mas
             o.add_triangles(b, m_m, M["tri"])
             o.mesh_bodies.append(b)
     first = o.add_spheres(scene["pos"], scene["radius"], sphere_mass(scene["radius"]), m_s, vel=vel, omega=omega)
+    if scene.get("fixed") is not None:  # SetParticleFixed: inactive bodies
+        for i in np.nonzero(scene["fixed"])[0]:
+            o.L.orc_set_body_fixed(o.h, int(first + i), 1)
     o.first_sphere_body = first
     o.num_walls = len(scene["walls"])
     o.num_triangles = sum(len(M["tri"]) for M in scene.get("meshes", []))
@@ -73,7 +76,7 @@ def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1
     for M in scene.get("meshes", []):
         m = g.add_mesh(M["tri"], M.get("mass", 1.0))
         g.set_mesh_motion(m, M.get("pos"), M.get("rot"), M.get("vel"), M.get("omega"))
-    g.set_spheres(scene["pos"], scene["radius"], vel=vel, omega=omega)
+    g.set_spheres(scene["pos"], scene["radius"], vel=vel, omega=omega, fixed=scene.get("fixed"))
     g.initialize()
     return g
 

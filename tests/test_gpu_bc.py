@@ -101,3 +101,17 @@ def test_hopper_holds_a_bed():
     rho = np.hypot(p[:, 0], p[:, 1])
     assert (p[:, 2] > 0.05 + 0.9 * R).all() and (p[:, 2] - rho > -0.05 * R * math.sqrt(2)).all()  # above floor and cone
     assert p[:, 2].max() < 0.45  # the cloud has fallen into the hopper
+
+
+def test_fixed_spheres_are_inactive_bodies():
+    """SetParticleFixed (terrain made of fixed particles, demo_DEM_fixedTerrain): a fixed sphere is an inactive Multicore body --
+    no contact between two fixed spheres or between a fixed sphere and a wall, it pushes but is not pushed."""
+    sc = scenes.settling_scene(3000, sep_factor=1.985, seed=41)
+    z = sc["pos"][:, 2]
+    sc["fixed"] = (z < np.quantile(z, 0.3)).astype(np.uint8)  # the bottom layers are terrain
+    vel, om = kinematics(3000, 13)
+    vel[sc["fixed"] != 0] = 0.0
+    om[sc["fixed"] != 0] = 0.0
+    o, g, npairs = compare_step(sc, vel, om, steps=3, dt=1e-4, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP)
+    p, v, _ = g.state()
+    assert np.array_equal(p[sc["fixed"] != 0], sc["pos"][sc["fixed"] != 0]) and not v[sc["fixed"] != 0].any()

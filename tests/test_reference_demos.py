@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "cpp", "_bin")
 REF_DEMOS = "/root/reference/src/demos/dem"
-DEMOS = ["demo_DEM_movingBoundary", "demo_DEM_mixer", "demo_DEM_repose"]
+DEMOS = ["demo_DEM_movingBoundary", "demo_DEM_mixer", "demo_DEM_repose", "demo_DEM_fixedTerrain"]
 
 
 def build_demo(name):
@@ -72,12 +72,28 @@ def mixer_obj(path):
             f.write("f %d %d %d\n" % (a + 1, b + 1, c + 1))
 
 
+def terrain_obj(path):
+    """A bumpy height field over [-1, 1]^2 (the demo scales it by (box_X/2, box_Y/2, box_Z) and lowers it by box_Z/2)."""
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    n = 12
+    xs = np.linspace(-1, 1, n + 1)
+    with open(path, "w") as f:
+        for j in range(n + 1):
+            for i in range(n + 1):
+                f.write("v %.6f %.6f %.6f\n" % (xs[i], xs[j], 0.12 + 0.05 * np.sin(3 * xs[i]) * np.cos(2 * xs[j])))
+        for j in range(n):
+            for i in range(n):
+                a = j * (n + 1) + i + 1
+                f.write("f %d %d %d\nf %d %d %d\n" % (a, a + 1, a + n + 2, a, a + n + 2, a + n + 1))
+
+
 def run_demo(name, json_name, tmp_path, timeout=900):
     exe = build_demo(name)
     if exe is None:
         pytest.skip("demo binary was not built (needs /root/reference at build time)")
     data = tmp_path / "data"
     mixer_obj(str(data / "models" / "mixer" / "internal_mixer.obj"))
+    terrain_obj(str(data / "models" / "fixedterrain.obj"))
     env = dict(os.environ, CHRONO_DATA_DIR=str(data) + "/", CHRONO_OUTPUT_DIR=str(tmp_path / "out") + "/")
     r = subprocess.run([exe, os.path.join(HERE, "golden", "demo_json", json_name)], capture_output=True, text=True,
                        timeout=timeout, env=env, cwd=str(tmp_path))
@@ -107,3 +123,19 @@ def test_reference_demo_mixer_runs(tmp_path):
     pts = np.loadtxt(out / [f for f in files if f.endswith(".csv")][-1], delimiter=",", skiprows=1)
     assert pts.shape[0] > 300 and np.isfinite(pts).all()
     assert (np.hypot(pts[:, 0], pts[:, 1]) < 50.0).all()  # inside the cylinder BC of radius Bx / 2
+
+
+@pytest.mark.gpu
+def test_reference_demo_fixed_terrain_runs(tmp_path):
+    """Terrain of fixed particles (MeshSphericalDecomposition) + a layer of free ones poured onto it."""
+    out = run_demo("demo_DEM_fixedTerrain", "fixedTerrain_small.json", tmp_path) / "fixedTerrain"
+    files = sorted(os.listdir(out))
+    assert len(files) >= 2, files
+    hdr = open(out / files[0]).readline().strip()
+    assert hdr == "x,y,z,absv,fixed,wx,wy,wz", hdr
+    first = np.loadtxt(out / files[0], delimiter=",", skiprows=1)
+    last = np.loadtxt(out / files[-1], delimiter=",", skiprows=1)
+    fixed = first[:, 4] != 0
+    assert fixed.sum() > 100 and (~fixed).sum() > 100
+    assert np.array_equal(first[fixed, :3], last[fixed, :3])           # the terrain does not move
+    assert last[~fixed, 2].mean() < first[~fixed, 2].mean()             # the free particles fall
