@@ -1903,8 +1903,15 @@ __global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_forc
         const V3 dxv = x - mpos;
         dx2 = dot(dxv, dxv);
     }
-    // running bounding box of the new sphere AABBs -> next step's grids; largest displacement -> Verlet travel
-    block_bbox_commit(nmnx, nmny, nmnz, nmxx, nmxy, nmxz, C.bbox);
+    // running bounding box of the new sphere AABBs -> next step's grids; largest displacement -> Verlet travel.
+    // The accumulator starts at the walls' box: a warp whose spheres all lie inside what is already recorded (every warp
+    // of a bed inside its container) skips the reduction.
+    {
+        const bool grows = nmnx < dec_ord(C.bbox[0]) || nmny < dec_ord(C.bbox[1]) || nmnz < dec_ord(C.bbox[2]) ||
+                           nmxx > dec_ord(C.bbox[3]) || nmxy > dec_ord(C.bbox[4]) || nmxz > dec_ord(C.bbox[5]);
+        if (__any_sync(0xffffffffu, grows))
+            block_bbox_commit(nmnx, nmny, nmnz, nmxx, nmxy, nmxz, C.bbox);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         dx2 = fmax(dx2, __shfl_xor_sync(0xffffffffu, dx2, o));
