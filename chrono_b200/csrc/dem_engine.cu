@@ -35,7 +35,8 @@ struct dem_b200_system {
     std::vector<double> h_tri;         // triangle soup, body frame, 9 doubles per triangle
     std::vector<uint32_t> h_tri_mesh;  // owner mesh of each triangle
     double mesh_radius[kMaxMeshes] = {0};  // largest vertex distance from the body origin (bound of a rotation's travel)
-    MeshSet* h_mesh_pin = nullptr;     // pinned staging of MeshSet::m (mesh motion is applied every step by co-simulation)
+    MeshBody* h_mesh_pin = nullptr;    // pinned staging of MeshSet::m, a ring of kMeshRing copies (co-simulation applies mesh
+    unsigned mesh_ring_pos = 0;        // motion every step: no host wait except when the ring wraps)
     bool cls_override[3] = {false, false, false};
     dem_b200_contact_class cls[3]{};   // explicit contact-class coefficients (dem_b200_set_contact_class)
     // scene staged on the host until initialize()
@@ -84,6 +85,8 @@ struct dem_b200_system {
     struct HRow { uint32_t owner, other; double d[3], dur, rel; };
     std::vector<HRow> h_hist;
 };
+
+constexpr unsigned kMeshRing = 16;
 
 #define CU(call)                                                                                 \
     do {                                                                                         \
@@ -777,10 +780,14 @@ int dem_b200_set_mesh_motion(dem_b200_system* s, int m, const double pos[3], con
     if (!s->initialized)
         return 0;
     CU(cudaSetDevice(s->cfg.device));
-    // asynchronous on the engine's stream (pinned staging is re-used: wait for the previous upload only)
-    CU(cudaStreamSynchronize(s->stream));
-    memcpy(s->h_mesh_pin->m, s->M.m, sizeof(s->M.m));
-    CU(cudaMemcpyAsync(s->B.meshes->m, s->h_mesh_pin->m, sizeof(s->M.m), cudaMemcpyHostToDevice, s->stream));
+    // asynchronous on the engine's stream; a staging slot is re-used kMeshRing calls later, so the host only waits when
+    // the ring wraps
+    const unsigned slot = s->mesh_ring_pos++ % kMeshRing;
+    if (slot == 0 && s->mesh_ring_pos > 1)
+        CU(cudaStreamSynchronize(s->stream));
+    MeshBody* stage = s->h_mesh_pin + (size_t)slot * kMaxMeshes;
+    memcpy(stage, s->M.m, sizeof(s->M.m));
+    CU(cudaMemcpyAsync(s->B.meshes->m, stage, sizeof(s->M.m), cudaMemcpyHostToDevice, s->stream));
     if (pos || rot) {
         const unsigned nt = B.tri_end - B.tri_begin;
         k_mesh_begin<<<1, 32, 0, s->stream>>>(s->B, m);
@@ -1053,7 +1060,7 @@ int dem_b200_initialize(dem_b200_system* s) {
         CU(cudaMemcpy(B.tri_loc, s->h_tri.data(), 9 * (size_t)P.nT * sizeof(double), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(B.tri_mesh, s->h_tri_mesh.data(), (size_t)P.nT * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(B.meshes, &s->M, sizeof(MeshSet), cudaMemcpyHostToDevice));
-        CU(cudaMallocHost((void**)&s->h_mesh_pin, sizeof(MeshSet)));
+        CU(cudaMallocHost((void**)&s->h_mesh_pin, kMeshRing * sizeof(s->M.m)));
         for (int m = 0; m < s->M.n; m++) {
             const unsigned nt = s->M.m[m].tri_end - s->M.m[m].tri_begin;
             k_mesh_begin<<<1, 32, 0, s->stream>>>(B, m);
