@@ -73,6 +73,7 @@ struct dem_b200_system {
     unsigned long long* h_vote = nullptr;     // pinned, mapped
     unsigned long long step_no = 0;      // host mirror of Ctrl::nsteps (steps enqueued so far)
     unsigned long long p2p_rebuild_seq = 0;
+    int one_step_calls = 0;
     double time = 0.0;
     std::string err;
     // scratch (device, by user index) and pinned host staging
@@ -420,7 +421,11 @@ int run_steps(dem_b200_system* s, int nsteps) {
     int done = 0;
     // slab mode: the step right after a rebuild runs un-captured (it is followed by the index remap below); the
     // graph is re-captured after every slab rebuild because the local sphere count (grid sizes) changes
-    if (!s->recording && ((!s->mgpu && nsteps >= 2) || (s->mgpu && !s->mg_remap_pending))) {
+    // callers that advance one step per call (co-simulation, the reference's unit tests: SURVEY Q15) get the graph from
+    // their third call on
+    if (nsteps == 1 && s->one_step_calls < 3)
+        s->one_step_calls++;
+    if (!s->recording && ((!s->mgpu && (nsteps >= 2 || (nsteps == 1 && s->one_step_calls >= 3))) || (s->mgpu && !s->mg_remap_pending))) {
         if (!s->graph1) {
             int rc = build_graph(s);
             if (rc)
