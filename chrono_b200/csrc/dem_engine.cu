@@ -218,6 +218,9 @@ void refresh_params(dem_b200_system* s) {
         P.skin = c.verlet_skin;
     else
         P.skin = 0.25 * P.rmax;
+    P.skin_adaptive = (c.verlet_skin < 0 && !s->mgpu) ? 1 : 0;
+    P.skin_max = std::max(P.skin, 0.5 * P.rmax);
+    P.skin_tri = std::max(P.skin_max, 1.5 * P.rmax);
 }
 
 bool need_roll(const dem_b200_system* s) {
@@ -798,7 +801,7 @@ int dem_b200_set_mesh_motion(dem_b200_system* s, int m, const double pos[3], con
         k_mesh_begin<<<1, 32, 0, s->stream>>>(s->B, m);
         k_mesh_transform<<<(nt + 255) / 256, 256, 0, s->stream>>>(s->B, m);
         if (moved > 0)
-            k_wall_moved<<<1, 1, 0, s->stream>>>(s->B, moved);
+            k_mesh_moved<<<1, 1, 0, s->stream>>>(s->B, moved);
         CU(cudaGetLastError());
     }
     return 0;
@@ -926,7 +929,7 @@ int dem_b200_initialize(dem_b200_system* s) {
     if (P.nT) {
         // capacity of the (cell, triangle) list: every triangle reaches at most the cells of the cube around its longest
         // edge inflated by the reach of a sphere
-        const double e = 2.0 * P.rmax + P.skin, reach = P.rmax + 0.5 * P.skin;
+        const double e = 2.0 * P.rmax + P.skin, reach = P.rmax + 0.5 * P.skin_tri;
         double tot = 0;
         for (size_t t = 0; t < P.nT; t++) {
             const double* v = &s->h_tri[9 * t];

@@ -231,10 +231,20 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
     C.max_dx2 = 0ull;
     C.travel += dx;
     C.last_dx = dx;
-    const bool rebuild = (C.need_rebuild != 0) || (!P.external_rebuild && !(C.travel < 0.499 * P.skin));
+    if (!P.skin_adaptive || !(C.skin > 0))
+        C.skin = P.skin;
+    const bool mesh_used_up = P.nT && !(C.travel + C.travel_mesh < 0.499 * P.skin_tri);
+    const bool rebuild = (C.need_rebuild != 0) || (!P.external_rebuild && (!(C.travel < 0.499 * C.skin) || mesh_used_up));
+    if (rebuild && P.skin_adaptive && C.nrebuilds >= 1) {
+        if (C.since_rebuild < 12u)
+            C.skin = fmin(1.3 * C.skin, P.skin_max);
+        else if (C.since_rebuild > 60u)
+            C.skin = fmax(C.skin / 1.3, P.skin);
+    }
+    C.since_rebuild = rebuild ? 0u : C.since_rebuild + 1u;
     if (C.nrebuilds >= 1)
         C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
-    if (P.external_rebuild && !rebuild && !(C.travel < 0.5 * P.skin))
+    if (P.external_rebuild && !rebuild && (!(C.travel < 0.5 * C.skin) || (P.nT && !(C.travel + C.travel_mesh < 0.5 * P.skin_tri))))
         atomicOr(&C.err, ERR_SKIN_EXCEEDED);  // the slab driver asked for the rebuild too late: lists may miss contacts
 
     // ---- bounding box of all shapes at the start of this step ----
@@ -284,7 +294,7 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
 
     // ---- search grid for the rebuild: cells no smaller than the candidate cut-off 2 rmax + skin ----
     if (rebuild) {
-        double e = (2.0 * P.rmax + P.skin) * (1.0 + 1e-9);
+        double e = (2.0 * P.rmax + C.skin) * (1.0 + 1e-9);
         double ext[3];
         for (int k = 0; k < 3; k++) {
             ext[k] = (mx[k] - mn[k]) + 2e-6 * e;
@@ -317,6 +327,7 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
         }
         C.s_ncell = (unsigned)tot;
         C.travel = 0.0;
+        C.travel_mesh = 0.0;
         C.nrebuilds++;
     }
     C.rebuild_now = rebuild ? 1u : 0u;
@@ -340,6 +351,10 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
 __global__ void k_wall_moved(Buffers B, double dist) {
     if (threadIdx.x == 0 && blockIdx.x == 0)
         B.ctrl->travel += dist;
+}
+__global__ void k_mesh_moved(Buffers B, double dist) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        B.ctrl->travel_mesh += dist;
 }
 
 // HashMin of the sphere AABB lower corner, HashMax of the upper corner (ChCollisionUtils.h:44-60), computed on the
@@ -612,7 +627,7 @@ __global__ void __launch_bounds__(256) k_tri_count(Params P, Buffers B) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.nT)
         return;
-    const double reach = (P.rmax + 0.5 * P.skin) * (1.0 + 1e-9);
+    const double reach = (P.rmax + 0.5 * P.skin_tri) * (1.0 + 1e-9);
     tri_cells(C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) { atomicAdd(&B.tcell_count[cell], 1u); });
 }
 
@@ -623,7 +638,7 @@ __global__ void __launch_bounds__(256) k_tri_fill(Params P, Buffers B) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.nT)
         return;
-    const double reach = (P.rmax + 0.5 * P.skin) * (1.0 + 1e-9);
+    const double reach = (P.rmax + 0.5 * P.skin_tri) * (1.0 + 1e-9);
     tri_cells(C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) {
         // counts back down to zero: the histogram is clean again for the next rebuild
         const unsigned at = B.tcell_start[cell] + atomicSub(&B.tcell_count[cell], 1u) - 1u;
@@ -782,7 +797,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                 const double4 pj = pos[j];
                 const double dx = pj.x - me.x, dy2 = pj.y - me.y, dz2 = pj.z - me.z;
                 const double d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
-                const double rs = me.w + pj.w + P.skin;
+                const double rs = me.w + pj.w + C.skin;
                 if (d2 > rs * rs * (1.0 + 1e-12))
                     continue;
                 if (me_fixed && (vel[j].meta & FLAG_FIXED))
@@ -818,7 +833,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     if (P.nT && B.meshes->enabled && !me_fixed) {
         const unsigned cell = (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
         const unsigned tb = B.tcell_start[cell], te = min(B.tcell_start[cell + 1], P.tri_cap);
-        const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
+        const double reach = me.w + 0.5 * P.skin_tri + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
         const V3 c = mk(me.x, me.y, me.z);
         for (unsigned q = tb; q < te; q++) {
             const unsigned t = B.tcell_tri[q];
@@ -851,7 +866,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     // through dem_b200_set_wall_velocity, which requests a rebuild)
     unsigned wc = 0;
     {
-        const double reach = me.w + 0.5 * P.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
+        const double reach = me.w + 0.5 * C.skin + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
         for (int w = 0; w < (me_fixed ? 0 : P.nW); w++) {
             const Wall& W = B.walls->w[w];
             bool near;
@@ -2146,6 +2161,7 @@ __global__ void k_mgpu_finish(Buffers B) {
     C.init_stage = 1u;
     C.nrebuilds = 0ull;  // k_step_begin clears init_stage once nrebuilds >= 1: restart that latch
     C.travel = 0.0;
+    C.travel_mesh = 0.0;
     C.max_dx2 = 0ull;
     SlabDev& S = *B.slab;
     S.n_keep = S.n_out[0] = S.n_out[1] = S.n_gsend[0] = S.n_gsend[1] = 0u;
@@ -2208,6 +2224,14 @@ __device__ __forceinline__ double predicted_travel(const Ctrl& C, int ahead) {
     return t;
 }
 
+// Same for the facet candidates: the mesh is assumed to keep moving as fast as its average since the last rebuild.
+__device__ __forceinline__ bool mesh_travel_used_up(const Params& P, const Ctrl& C, int ahead) {
+    if (!P.nT)
+        return false;
+    const double per_step = C.travel_mesh * 0.2;  // generous: a fifth of everything so far per further step
+    return !(predicted_travel(C, ahead) + C.travel_mesh + (double)(1 + ahead) * per_step < 0.499 * P.skin_tri);
+}
+
 // `ahead` = further steps the caller will run before it acts on the answer (a driver that reads the flag one step late
 // passes 1): they are assumed to move the spheres as far as the last step did; k_step_begin traps the case where that
 // assumption fails (ERR_SKIN_EXCEEDED).
@@ -2215,7 +2239,7 @@ __global__ void k_mgpu_want(Params P, Buffers B, int* flag_out, int ahead) {
     if (threadIdx.x || blockIdx.x)
         return;
     const Ctrl& C = *B.ctrl;
-    *flag_out = (C.need_rebuild != 0 || !(predicted_travel(C, ahead) < 0.499 * P.skin)) ? 1 : 0;
+    *flag_out = (C.need_rebuild != 0 || !(predicted_travel(C, ahead) < 0.499 * C.skin) || mesh_travel_used_up(P, C, ahead)) ? 1 : 0;
 }
 // --------------------------------------------------------------------------------------------
 // direct P2P halo + vote (see P2PCtl in dem_types.h).  `step` = number of the time step the data belongs to = the
@@ -2360,7 +2384,8 @@ __global__ void k_p2p_vote(Params P, Buffers B, P2PDev X) {
     const unsigned long long step = C.nsteps;  // the step that just ran
     const unsigned r = threadIdx.x;
     if (r < (unsigned)X.world) {
-        const unsigned long long flag = (C.need_rebuild != 0 || !(predicted_travel(C, X.ahead) < 0.499 * P.skin)) ? 1ull : 0ull;
+        const unsigned long long flag =
+            (C.need_rebuild != 0 || !(predicted_travel(C, X.ahead) < 0.499 * C.skin) || mesh_travel_used_up(P, C, X.ahead)) ? 1ull : 0ull;
         st_release_sys(&X.peer[r]->vote[step & 7ull][X.rank], (step << 1) | flag);
     }
     if (step <= X.first_step)

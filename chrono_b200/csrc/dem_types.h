@@ -108,6 +108,11 @@ struct Params {
     unsigned cell_cap;    // capacity of the search-cell arrays
     int track_wall_forces;  // accumulate the reaction force on every wall (GetBCReactionForces)
     int external_rebuild;   // slab mode: rebuilds happen only when the host asks (all ranks at the same step)
+    int skin_adaptive;      // default skin only, not in slab mode: the skin grows (up to skin_max) while rebuilds come less than
+    double skin_max;        // 12 steps apart (fast flow) and shrinks back to `skin` when they are more than 60 apart.  No
+                            // result depends on the skin (summation order is by stable id), so this only moves cost around.
+    double skin_tri;        // skin of the sphere-facet candidates (>= skin): a moving mesh (drum, mixer) sweeps much faster
+                            // than the bed creeps, and only the spheres next to it pay for the longer facet lists
     unsigned nT;            // mesh triangles (shape ids nW .. nW + nT - 1; spheres follow: shape_base = nW + nT)
     unsigned tri_cap;       // capacity of the (search cell, triangle) pair list
 };
@@ -145,6 +150,11 @@ struct Ctrl {
     unsigned long long max_dx2;   // raw bits of max |x_new - x_old|^2 over the spheres, last step
     double travel;                // sum of per-step max displacements since the last rebuild
     double last_dx;               // max displacement of the step before the last one (growth estimate of the slab vote)
+    double skin;                  // Verlet skin the current lists were built with (Params::skin unless adaptive)
+    unsigned since_rebuild;       // steps since the lists were built
+    unsigned pad_;
+    double travel_mesh;           // how far mesh vertices moved since the last rebuild (ApplyMeshMotion); counts against the
+                                  // facet candidates' own, larger skin (Params::skin_tri) on top of `travel`
     // search grid (cells >= 2 rmax + skin), x fastest
     double s_org[3], s_inv[3];
     int s_dim[3];

@@ -142,22 +142,25 @@ def mesh_to_body_frame(tri_world, pos, rot):
     return np.ascontiguousarray(quat_rotate(v, qc).reshape(-1, 9))
 
 
-def cylinder_drum_mesh(radius, length, n_seg, axis=1, caps=True):
+def cylinder_drum_mesh(radius, length, n_seg, axis=1, caps=True, n_ax=1):
     """Closed cylinder (the drum of BASELINE configs[3]) seen from inside: normals point to the axis.  Axis y (axis=1)
-    by default, centred at the origin.  n_seg segments around, 2 triangles each, + 2 n_seg cap triangles."""
+    by default, centred at the origin.  n_seg segments around x n_ax along the axis, 2 triangles each, + 2 n_seg cap
+    triangles (fans)."""
     th = np.linspace(0.0, 2 * math.pi, n_seg + 1)
     c, s_ = np.cos(th), np.sin(th)
     h = length / 2
+    ys = np.linspace(-h, h, n_ax + 1)
     tris = []
 
     def P(i, yy):
         return [radius * c[i], yy, radius * s_[i]]
 
     for i in range(n_seg):
-        a, b, cc, d = P(i, -h), P(i + 1, -h), P(i + 1, h), P(i, h)
-        # inward normal: for axis y the outward radial is (cos, 0, sin); choose winding by test below
-        tris.append(a + cc + b)
-        tris.append(a + d + cc)
+        for k in range(n_ax):
+            a, b, cc, d = P(i, ys[k]), P(i + 1, ys[k]), P(i + 1, ys[k + 1]), P(i, ys[k + 1])
+            # inward normal: for axis y the outward radial is (cos, 0, sin); the winding is fixed by the test below
+            tris.append(a + cc + b)
+            tris.append(a + d + cc)
         if caps:
             tris.append([0, -h, 0] + P(i, -h) + P(i + 1, -h))   # normal +y (into the drum) checked below
             tris.append([0, h, 0] + P(i + 1, h) + P(i, h))      # normal -y
