@@ -236,11 +236,15 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
     const bool mesh_used_up = P.nT && !(C.travel + C.travel_mesh < 0.499 * P.skin_tri);
     const bool rebuild = (C.need_rebuild != 0) || (!P.external_rebuild && (!(C.travel < 0.499 * C.skin) || mesh_used_up));
     if (rebuild && P.skin_adaptive && C.nrebuilds >= 1) {
-        if (C.since_rebuild < 12u)
+        if (C.max_cand + 6u > (unsigned)P.Kn)  // the lists are nearly full: never trade rebuilds for an overflow
+            C.skin = fmax(C.skin / 1.3, P.skin);
+        else if (C.since_rebuild < 12u && C.max_cand + 12u <= (unsigned)P.Kn)
             C.skin = fmin(1.3 * C.skin, P.skin_max);
         else if (C.since_rebuild > 60u)
             C.skin = fmax(C.skin / 1.3, P.skin);
     }
+    if (rebuild)
+        C.max_cand = 0u;
     C.since_rebuild = rebuild ? 0u : C.since_rebuild + 1u;
     if (C.nrebuilds >= 1)
         C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
@@ -862,6 +866,8 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     }
     for (int k = 0; k < cnt + tcnt; k++)
         B.nl[(size_t)k * P.Np + s] = tj[k];
+    if ((unsigned)(cnt + tcnt) > C.max_cand)
+        atomicMax(&C.max_cand, (unsigned)(cnt + tcnt));
     // walls the sphere can touch before the next rebuild: it moves less than skin/2 until then (walls only move
     // through dem_b200_set_wall_velocity, which requests a rebuild)
     unsigned wc = 0;

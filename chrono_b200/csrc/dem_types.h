@@ -152,7 +152,7 @@ struct Ctrl {
     double last_dx;               // max displacement of the step before the last one (growth estimate of the slab vote)
     double skin;                  // Verlet skin the current lists were built with (Params::skin unless adaptive)
     unsigned since_rebuild;       // steps since the lists were built
-    unsigned pad_;
+    unsigned max_cand;            // longest candidate list of the last rebuild (the adaptive skin backs off near Kn)
     double travel_mesh;           // how far mesh vertices moved since the last rebuild (ApplyMeshMotion); counts against the
                                   // facet candidates' own, larger skin (Params::skin_tri) on top of `travel`
     // search grid (cells >= 2 rmax + skin), x fastest
