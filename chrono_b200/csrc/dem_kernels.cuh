@@ -1223,12 +1223,17 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     if (ROLL) {
         const double kPI = 3.141592653589793238462643383279;
         double muRoll = cm.mu_roll, muSpin = cm.mu_spin;
-        const double sq_d = sqrt(delta_n);
-        const double kn_simple = kn / sq_d;
-        const double gn_simple = gn / sqrt(sq_d);
-        const double d_coeff = gn_simple / (2.0 * m_eff * sqrt(kn_simple / m_eff));
+        // contact-duration gate (ChIterativeSolverMulticoreSMC.cpp:484-491) with reciprocal square roots instead of the five
+        // square roots and four divisions of the reference expression:
+        //   kn_simple = kn / sqrt(d), gn_simple = gn / d^(1/4), d_coeff = gn_simple / (2 m sqrt(kn_simple / m)),
+        //   t_collision = pi sqrt(m / (kn_simple (1 - d_coeff^2)))
+        const double ir_d = fast_rsqrt(delta_n);           // d^(-1/2)
+        const double kn_simple = kn * ir_d;
+        const double gn_simple = gn * fast_rsqrt(delta_n * ir_d);  // gn d^(-1/4)
+        const double inv_m = fast_rcp(m_eff);
+        const double d_coeff = 0.5 * gn_simple * inv_m * fast_rsqrt(kn_simple * inv_m);
         if (d_coeff < 1.0) {
-            const double t_collision = kPI * sqrt(m_eff / (kn_simple * (1 - d_coeff * d_coeff)));
+            const double t_collision = kPI * fast_rsqrt(kn_simple * (1 - d_coeff * d_coeff) * inv_m);
             const double t_contact = HIST ? steps * P.dt : 0.0;
             if (t_contact <= t_collision) {
                 muRoll = 0.0;
@@ -1238,9 +1243,9 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
         // v_rot = wb x (-n rb) - wa x (n ra) = -(wsum x n)
         const V3 v_rot = -wxn;
         const V3 rel_o = wb - wa;
-        const double lv = len(v_rot);
-        if (lv > P.min_roll && muRoll > eps)
-            Ta = Ta + (muRoll * fN * ra / lv) * cross(n, v_rot);
+        const double lv2 = dot(v_rot, v_rot);
+        if (lv2 > P.min_roll * P.min_roll && muRoll > eps)
+            Ta = Ta + (muRoll * fN * ra * fast_rsqrt(lv2)) * cross(n, v_rot);
         const double lo = len(rel_o);
         if (lo > P.min_spin && muSpin > eps) {
             // contact-circle radius, evaluated with body 1 = lower shape id as the reference does
@@ -1542,12 +1547,17 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #ifndef DEMB200_PF2
 #define DEMB200_PF2 0
 #endif
+// the rolling / spinning instantiations carry more live state: 12 warps per SM at 168 registers (no spills) beat 16 warps
+// at 128 registers with 172 B of spills (350 vs 400 us on the polydisperse + rolling-friction variant of the bench)
+#ifndef DEMB200_ROLL_MINBLOCKS
+#define DEMB200_ROLL_MINBLOCKS (384 / DEMB200_FORCE_THREADS)
+#endif
 #ifndef DEMB200_FORCE_MINBLOCKS
 #define DEMB200_FORCE_MINBLOCKS (512 / DEMB200_FORCE_THREADS)  /* 16 warps per SM: 128 registers per thread */
 #endif
 
 template <bool HIST, bool ROLL, bool FAST, bool REC, bool MESH>
-__global__ void __launch_bounds__(kForceThreads, DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS : DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
                                                                       const __grid_constant__ Buffers B) {
     __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
     __shared__ unsigned char cslot[kMaxSlots * kForceThreads];  // its index in the candidate list (= history slot)
