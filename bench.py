@@ -33,6 +33,7 @@ KERNELS_PER_TIMESTEP = 9  # launches of our own kernels per DEM time step (7 of 
 
 POLY = None      # --polydisperse lo,hi : radii U(lo, hi) * R (BASELINE configs[2]-style physics); not the default workload
 MU_ROLL = 0.0    # --mu-roll
+USER_COEFF = False  # --user-coeff
 
 
 def build_scene(n):
@@ -155,7 +156,7 @@ def workload_config(n, substeps, gpus):
     return {"workload": ("BASELINE configs[1]: %d spheres Hertz-Mindlin MultiStep history in a 5-wall box, jittered HCP "
                          "packing at 2R spacing (c_bar~6), R=0.02 rho=2000 Y=2e6 mu=0.4 cr=0.4 h=1e-4" % n) +
                         ((" -- VARIANT: radii U(%g,%g) R, mu_roll %g" % (POLY[0], POLY[1], MU_ROLL)) if POLY else
-                         ((" -- VARIANT: mu_roll %g" % MU_ROLL) if MU_ROLL else "")),
+                         ((" -- VARIANT: mu_roll %g" % MU_ROLL) if MU_ROLL else "")) + (" -- VARIANT: user coefficients" if USER_COEFF else ""),
             "spheres_per_gpu": n, "timesteps_per_step": substeps,
             "l2_policy": "working set (>=300 B/sphere x %d spheres) exceeds the 126 MB L2; no explicit flush" % n,
             "parallelism": "1 process per GPU" if gpus == 1 else
@@ -330,6 +331,11 @@ def run_ours(args):
     S = args.substeps
     scene = build_scene(n)
     extra = dict(mat=common.settling_material(mu_roll=MU_ROLL), history_slots=24) if (POLY or MU_ROLL) else {}
+    if USER_COEFF:  # the model every in-tree Chrono::Dem caller uses: explicit kn / kt / gn / gt (SetKn_SPH2SPH ...)
+        extra["use_mat_props"] = False
+        m = common.settling_material(mu_roll=MU_ROLL)
+        m.update(kn=2e7, kt=2e7, gn=40.0, gt=20.0)
+        extra["mat"] = m
     g = common.make_gpu(scene, dt=DT, force_model=dem.HERTZ, tangential_mode=dem.TANG_MULTISTEP, **extra)
     g.L.dem_b200_step  # the CUDA extension is loaded; there is no other path
 
@@ -439,9 +445,11 @@ def main():
     ap.add_argument("--skin", type=float, default=0.0, help="N > 1: Verlet skin in sphere radii (0 = engine default 0.25)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of slab decomposition")
     ap.add_argument("--polydisperse", default="", help="lo,hi: radii U(lo,hi)*R instead of monodisperse (configs[2]-style; N = 1 only)")
+    ap.add_argument("--user-coeff", action="store_true", help="explicit kn/kt/gn/gt instead of material properties (N = 1 only)")
     ap.add_argument("--mu-roll", type=float, default=0.0, help="rolling friction coefficient (configs[2]-style; N = 1 only)")
     args = ap.parse_args()
-    global POLY, MU_ROLL
+    global POLY, MU_ROLL, USER_COEFF
+    USER_COEFF = args.user_coeff
     if args.polydisperse:
         POLY = tuple(float(x) for x in args.polydisperse.split(","))
     MU_ROLL = args.mu_roll

@@ -231,7 +231,7 @@ bool need_roll(const dem_b200_system* s) {
 }
 
 bool fast_path(const dem_b200_system* s) {
-    return s->P.force_model == DEMB200_HERTZ && s->P.use_mat_props && s->P.adhesion_model == DEMB200_ADH_CONSTANT;
+    return s->P.force_model == DEMB200_HERTZ && s->P.adhesion_model == DEMB200_ADH_CONSTANT;
 }
 
 template <bool REC>
@@ -239,8 +239,8 @@ void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks) {
     const Params& P = s->P;
     const bool hist = (P.tang_mode == DEMB200_TANG_MULTISTEP);
     const bool roll = need_roll(s);
-    const bool fast = fast_path(s);
-    const int sel = (hist ? 4 : 0) | (roll ? 2 : 0) | (fast ? 1 : 0);
+    const int fast = fast_path(s) ? (P.use_mat_props ? 1 : 2) : 0;
+    const int sel = (hist ? 6 : 0) + (roll ? 3 : 0) + fast;
 #define LF(H, R, F)                                                                                  \
     do {                                                                                             \
         if (P.nT)                                                                                    \
@@ -249,14 +249,18 @@ void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks) {
             k_force_integrate<H, R, F, REC, false><<<blocks, kForceThreads, 0, s->stream>>>(P, B);   \
     } while (0)
     switch (sel) {
-        case 0: LF(false, false, false); break;
-        case 1: LF(false, false, true); break;
-        case 2: LF(false, true, false); break;
-        case 3: LF(false, true, true); break;
-        case 4: LF(true, false, false); break;
-        case 5: LF(true, false, true); break;
-        case 6: LF(true, true, false); break;
-        default: LF(true, true, true); break;
+        case 0: LF(false, false, 0); break;
+        case 1: LF(false, false, 1); break;
+        case 2: LF(false, false, 2); break;
+        case 3: LF(false, true, 0); break;
+        case 4: LF(false, true, 1); break;
+        case 5: LF(false, true, 2); break;
+        case 6: LF(true, false, 0); break;
+        case 7: LF(true, false, 1); break;
+        case 8: LF(true, false, 2); break;
+        case 9: LF(true, true, 0); break;
+        case 10: LF(true, true, 1); break;
+        default: LF(true, true, 2); break;
     }
 #undef LF
 }

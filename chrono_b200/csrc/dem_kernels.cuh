@@ -1139,7 +1139,7 @@ __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, cons
 }
 
 // --------------------------------------------------------------------------------------------
-// Fast path of the same law for the headline configuration: Hertz, material properties, constant adhesion, sphere
+// Fast path of the same law: Hertz (material properties OR user coefficients), constant adhesion, sphere
 // against sphere.  Written in the frame of the evaluating sphere ("a" = me, "b" = partner, n from a to b).  All
 // expressions are odd/even under the exchange a <-> b with IEEE-exact sign symmetry (products are formed with
 // commutative roundings), so both partners obtain bit-identical magnitudes and equal-and-opposite forces, and their
@@ -1147,7 +1147,7 @@ __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, cons
 // (body 1 = lower shape id, ChIterativeSolverMulticoreSMC.cpp:233-243): disp_ab = sgn * disp_canonical.
 // Divisions / square roots of the reference are replaced by rcp / rsqrt forms (<= 2 ulp); the bar is 1e-9.
 // --------------------------------------------------------------------------------------------
-template <bool HIST, bool ROLL>
+template <bool HIST, bool ROLL, bool MATPROPS>
 __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp& cm, V3 n, double dist, double ra,
                                                     double rb, V3 va, V3 wa, V3 vb, V3 wb, double ma, double mb,
                                                     bool a_is_body1, V3& disp, double& steps, bool isnew, V3& F_me,
@@ -1189,15 +1189,24 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
         delta_t = relvel_t * P.dt;
     }
 
-    const double x = erad * delta_n;
-    const double sqrt_Rd = x * fast_rsqrt(x);
-    const double Sn = 2 * cm.E_eff * sqrt_Rd;
-    const double St = 8 * cm.G_eff * sqrt_Rd;
-    const double kn = (2.0 / 3.0) * Sn;
-    const double kt = St;
-    const double y = Sn * m_eff;
-    const double gn = cm.hertz_damp * (y * fast_rsqrt(y));
-    const double gt = gn * cm.gt_ratio;
+    double kn, kt, gn, gt;
+    if (MATPROPS) {  // ChIterativeSolverMulticoreSMC.cpp:277-290
+        const double x = erad * delta_n;
+        const double sqrt_Rd = x * fast_rsqrt(x);
+        const double Sn = 2 * cm.E_eff * sqrt_Rd;
+        const double St = 8 * cm.G_eff * sqrt_Rd;
+        kn = (2.0 / 3.0) * Sn;
+        kt = St;
+        const double y = Sn * m_eff;
+        gn = cm.hertz_damp * (y * fast_rsqrt(y));
+        gt = gn * cm.gt_ratio;
+    } else {  // user coefficients (:291-297) -- the model every Chrono::Dem setter (SetKn_SPH2SPH ...) maps to
+        const double tmp = erad * (delta_n * fast_rsqrt(delta_n));
+        kn = tmp * cm.kn;
+        kt = tmp * cm.kt;
+        gn = tmp * m_eff * cm.gn;
+        gt = tmp * m_eff * cm.gt;
+    }
 
     const double fN = kn * delta_n - gn * vn;
     const V3 fT_damp = gt * relvel_t;
@@ -1556,7 +1565,8 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #define DEMB200_FORCE_MINBLOCKS (512 / DEMB200_FORCE_THREADS)  /* 16 warps per SM: 128 registers per thread */
 #endif
 
-template <bool HIST, bool ROLL, bool FAST, bool REC, bool MESH>
+// FAST: 0 = generic law (contact_force), 1 = Hertz with material properties, 2 = Hertz with user coefficients
+template <bool HIST, bool ROLL, int FAST, bool REC, bool MESH>
 __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS : DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
                                                                       const __grid_constant__ Buffers B) {
     __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
@@ -1802,7 +1812,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             if (had && !me1)
                 disp = -disp;  // canonical (body 1 -> body 2) to my frame
             V3 F, T;
-            sphere_contact_fast<HIST, ROLL>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass,
+            sphere_contact_fast<HIST, ROLL, FAST == 1>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass,
                                             sphere_mass(P, pj.w), me1, disp, steps, !had, F, T);
             Fsum = Fsum + F;
             Tsum = Tsum + T;
