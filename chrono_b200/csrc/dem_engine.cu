@@ -217,7 +217,7 @@ void refresh_params(dem_b200_system* s) {
     if (c.verlet_skin >= 0)
         P.skin = c.verlet_skin;
     else
-        P.skin = 0.25 * P.rmax;
+        P.skin = (s->mgpu ? 0.35 : 0.25) * P.rmax;  // slab mode: rebuilds cost a neighbour exchange and the skin is not adaptive
     P.skin_adaptive = (c.verlet_skin < 0 && !s->mgpu) ? 1 : 0;
     P.skin_max = std::max(P.skin, 0.5 * P.rmax);
     P.skin_tri = std::max(P.skin_max, 1.5 * P.rmax);

@@ -76,7 +76,8 @@ typedef struct dem_b200_config {
     double mesh_mass;     /* default mass of mesh bodies */
     double verlet_skin;   /* neighbour candidates = spheres closer than r_i + r_j + skin when the lists are built; the
                              lists are rebuilt (on the device, no host round trip) before any sphere can have moved
-                             skin/2.  < 0 -> 0.25 * largest radius; 0 -> rebuild every step */
+                             skin/2.  < 0 -> default: 0.25 * largest radius, adapting up to 0.5 on the device while rebuilds come less than 12
+                             steps apart (0.35, fixed, in slab mode); 0 -> rebuild every step */
     int neighbor_slots;   /* candidate slots per sphere; 0 -> 32, max 64 */
 } dem_b200_config;
 
