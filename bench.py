@@ -404,6 +404,8 @@ def run_ours(args):
 
     if rank == 0:
         cpu_val, cpu_cores, cpu_t = cpu_oracle_run(scene, args.cpu_steps) if args.cpu_steps > 0 else (None, 0, {})
+        # per-core figure: the same port on ONE thread, one time step of the same packing
+        cpu_1t = cpu_oracle_run(scene, 1, threads=1)[0] if args.cpu_steps > 0 else None
         line = {
             "metric": "sphere-steps/sec", "value": value, "unit": "sphere-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -419,7 +421,7 @@ def run_ours(args):
             "kernel_ms_per_timestep": prof, "kernel_share": {k: v / step_ms for k, v in prof.items()},
             "cpu_baseline": {"value": cpu_val, "unit": "sphere-steps/s", "cores": cpu_cores, "kind": "port",
                              "sample": "%d spheres x %d time steps of the same packing" % (n, args.cpu_steps),
-                             "phase_seconds": cpu_t},
+                             "phase_seconds": cpu_t, "value_one_thread": cpu_1t},
             "e2e": {"value": e2e_value, "unit": "sphere-steps/s", "h2d_bytes_per_step": bytes_io,
                     "d2h_bytes_per_step": bytes_io, "steps": e2e_steps},
             "gpu_launches": int(args.steps * S * KERNELS_PER_TIMESTEP),
