@@ -105,10 +105,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: do not let that shrink the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_run(scene, timesteps, threads=0):
     """Times the CPU oracle (restatement of Chrono::Multicore SMC) on the same packing for `timesteps` steps."""
     import dem_common as common
     from oracle import pyoracle as po
+    threads = threads or host_threads()
     o = common.make_oracle(scene, dt=DT, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP, num_threads=threads)
     o.step(1)  # untimed: first-touch of all arrays
     o.reset_timers()
@@ -116,7 +125,7 @@ def cpu_oracle_run(scene, timesteps, threads=0):
     rc = o.step(timesteps)
     t1 = time.perf_counter()
     assert rc == 0
-    return scene["n"] * timesteps / (t1 - t0), po.lib().orc_max_threads() if threads == 0 else threads, o.timers()
+    return scene["n"] * timesteps / (t1 - t0), threads, o.timers()
 
 
 def run_reference(args):
@@ -130,8 +139,8 @@ def run_reference(args):
     n = args.spheres
     scene = build_scene(n)
     sample_steps = args.ref_substeps
-    o = common.make_oracle(scene, dt=DT, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP)
-    cores = po.lib().orc_max_threads()
+    cores = host_threads()
+    o = common.make_oracle(scene, dt=DT, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP, num_threads=cores)
     for _ in range(args.warmup):
         o.step(sample_steps)
     t0 = time.perf_counter()
