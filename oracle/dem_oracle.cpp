@@ -34,6 +34,7 @@
 #include <climits>
 #include <cstdint>
 #include <cstring>
+#include <parallel/algorithm>
 #include <limits>
 #include <vector>
 #ifdef _OPENMP
@@ -526,6 +527,13 @@ struct System {
     std::vector<V3> shapeA_global;
     std::vector<Q4> shapeR_global;
     std::vector<V3> tri_global;  // 3 per shape (unused for non-triangles)
+    // narrowphase / force scratch (kept between steps)
+    std::vector<char> np_act;
+    std::vector<V3> np_norm, np_p1, np_p2;
+    std::vector<double> np_dep, np_er;
+    std::vector<long long> np_offs;
+    std::vector<int> pc_slot_of;
+    std::vector<char> pc_is_new;
     std::vector<long long> c_shape;
     std::vector<int> c_b1, c_b2;
     std::vector<V3> c_norm, c_pt1, c_pt2;
@@ -665,12 +673,15 @@ void broadphase(System& S) {
     }
     {  // Thrust_Sort_By_Key(bin_number, bin_aabb_number) -> stable sort (see header note)
         std::vector<unsigned> perm(nint);
-        for (unsigned i = 0; i < nint; i++)
-            perm[i] = i;
-        std::stable_sort(perm.begin(), perm.end(),
-                         [&](unsigned a, unsigned b) { return S.bin_number[a] < S.bin_number[b]; });
+#pragma omp parallel for
+        for (long long i = 0; i < (long long)nint; i++)
+            perm[i] = (unsigned)i;
+        // parallel (OpenMP) merge sort of libstdc++; stable, so the result equals std::stable_sort's
+        __gnu_parallel::stable_sort(perm.begin(), perm.end(),
+                                    [&](unsigned a, unsigned b) { return S.bin_number[a] < S.bin_number[b]; });
         std::vector<unsigned> k2(nint), v2(nint);
-        for (unsigned i = 0; i < nint; i++) {
+#pragma omp parallel for
+        for (long long i = 0; i < (long long)nint; i++) {
             k2[i] = S.bin_number[perm[i]];
             v2[i] = S.bin_aabb_number[perm[i]];
         }
@@ -774,9 +785,13 @@ void narrowphase(System& S) {
         S.shapeR_global[i] = Mult(r, sh.R);
     }
     const long long np = (long long)S.pair_shapeIDs.size();
-    std::vector<char> act(np, 0);
-    std::vector<V3> norm(np), p1(np), p2(np);
-    std::vector<double> dep(np), er(np);
+    // scratch of the pair loop lives in the system: no per-step allocation / serial zero fill of ~90 B per pair
+    std::vector<char>& act = S.np_act;
+    std::vector<V3>&norm = S.np_norm, &p1 = S.np_p1, &p2 = S.np_p2;
+    std::vector<double>&dep = S.np_dep, &er = S.np_er;
+    if ((long long)act.size() < np) {
+        act.resize(np); norm.resize(np); p1.resize(np); p2.resize(np); dep.resize(np); er.resize(np);
+    }
     const double separation = 0;  // 2 * envelope, envelope = 0 (ChSystemMulticoreSMC.cpp:27)
 #pragma omp parallel for
     for (long long idx = 0; idx < np; idx++) {  // DispatchPRIMS :267-288 + PRIMSCollision :1406-1531
@@ -809,20 +824,31 @@ void narrowphase(System& S) {
         act[idx] = hit;
     }
     // stream compaction (thrust::remove_if, order preserving): ChNarrowphase.cpp:362-385
-    S.c_shape.clear(); S.c_b1.clear(); S.c_b2.clear(); S.c_norm.clear(); S.c_pt1.clear(); S.c_pt2.clear();
-    S.c_depth.clear(); S.c_erad.clear();
+    // exclusive scan of the flags, then a parallel scatter (same order as the serial compaction)
+    std::vector<long long>& offs = S.np_offs;
+    if ((long long)offs.size() < np + 1)
+        offs.resize((size_t)np + 1);
+    long long nkeep = 0;
+    for (long long idx = 0; idx < np; idx++) {
+        offs[idx] = nkeep;
+        nkeep += act[idx] ? 1 : 0;
+    }
+    S.c_shape.resize(nkeep); S.c_b1.resize(nkeep); S.c_b2.resize(nkeep); S.c_norm.resize(nkeep); S.c_pt1.resize(nkeep);
+    S.c_pt2.resize(nkeep); S.c_depth.resize(nkeep); S.c_erad.resize(nkeep);
+#pragma omp parallel for
     for (long long idx = 0; idx < np; idx++) {
         if (!act[idx])
             continue;
+        const long long o = offs[idx];
         int a = int(S.pair_shapeIDs[idx] >> 32), b = int(S.pair_shapeIDs[idx] & 0xffffffff);
-        S.c_shape.push_back(S.pair_shapeIDs[idx]);
-        S.c_b1.push_back(S.shapes[a].body);
-        S.c_b2.push_back(S.shapes[b].body);
-        S.c_norm.push_back(norm[idx]);
-        S.c_pt1.push_back(p1[idx]);
-        S.c_pt2.push_back(p2[idx]);
-        S.c_depth.push_back(dep[idx]);
-        S.c_erad.push_back(er[idx]);
+        S.c_shape[o] = S.pair_shapeIDs[idx];
+        S.c_b1[o] = S.shapes[a].body;
+        S.c_b2[o] = S.shapes[b].body;
+        S.c_norm[o] = norm[idx];
+        S.c_pt1[o] = p1[idx];
+        S.c_pt2[o] = p2[idx];
+        S.c_depth[o] = dep[idx];
+        S.c_erad[o] = er[idx];
     }
 }
 
@@ -832,24 +858,46 @@ int process_contacts(System& S) {
     const int nb = (int)S.mass.size();
     ForceIn P{S.st.force_model, S.st.adhesion_model, S.st.tangential_mode, S.st.use_mat_props != 0, S.st.char_vel,
               S.st.min_slip_vel, S.st.min_roll_vel, S.st.min_spin_vel, S.st.dt};
-    S.c_force.assign(nc, V3(0));
-    S.c_tq1.assign(nc, V3(0));
-    S.c_tq2.assign(nc, V3(0));
-    std::vector<int> slot_of(nc, -1);
-    std::vector<char> is_new(nc, 0);
+    S.c_force.resize(nc);
+    S.c_tq1.resize(nc);
+    S.c_tq2.resize(nc);
+    std::vector<int>& slot_of = S.pc_slot_of;
+    std::vector<char>& is_new = S.pc_is_new;
+    slot_of.resize(nc);
+    is_new.resize(nc);
+#pragma omp parallel for
+    for (long long i = 0; i < nc; i++) {
+        S.c_force[i] = V3(0);
+        S.c_tq1[i] = V3(0);
+        S.c_tq2[i] = V3(0);
+        slot_of[i] = -1;
+        is_new[i] = 0;
+    }
     int err = 0;
     const bool multi = (P.displ_mode == ORC_TANG_MULTISTEP);
     if (multi) {
-        for (auto& h : S.hist)
-            h.touch = 0;  // :661-662
+        {
+            const long long nh = (long long)S.hist.size();
+#pragma omp parallel for
+            for (long long i = 0; i < nh; i++)
+                S.hist[i].touch = 0;  // :661-662
+        }
         // serial slot assignment in contact order (reference: inside the parallel loop, :194-227).
         // Contacts with depth >= 0 return before touching the history (:96-104).
+        // Every thread walks all contacts in order but only serves the owner bodies of its own range: the rows fill in
+        // exactly the order of the serial loop, without locks.
+#pragma omp parallel reduction(| : err)
+        {
+        const int nth = omp_get_num_threads(), tid = omp_get_thread_num();
+        const int b_lo = (int)((long long)nb * tid / nth), b_hi = (int)((long long)nb * (tid + 1) / nth);
         for (long long i = 0; i < nc; i++) {
             if (S.c_depth[i] >= 0)
                 continue;
             int b1 = S.c_b1[i], b2 = S.c_b2[i];
-            int s1 = int(S.c_shape[i] >> 32), s2 = int(S.c_shape[i] & 0xffffffff);
             int sb1 = std::max(b1, b2), sb2 = std::min(b1, b2);
+            if (sb1 < b_lo || sb1 >= b_hi)
+                continue;
+            int s1 = int(S.c_shape[i] >> 32), s2 = int(S.c_shape[i] & 0xffffffff);
             int ss1 = std::max(s1, s2), ss2 = std::min(s1, s2);
             HistSlot* row = &S.hist[(size_t)kMaxShear * sb1];
             int id = -1;
@@ -875,6 +923,7 @@ int process_contacts(System& S) {
             }
             slot_of[i] = kMaxShear * sb1 + id;
         }
+        }  // omp parallel
         if (err)
             return err;
     }
@@ -889,19 +938,36 @@ int process_contacts(System& S) {
                            S.c_force[i], S.c_tq1[i], S.c_tq2[i]);
     }
     if (multi) {  // :677-685
-        for (auto& h : S.hist)
-            if (!h.touch)
-                h.nb = -1;
+        const long long nh = (long long)S.hist.size();
+#pragma omp parallel for
+        for (long long i = 0; i < nh; i++)
+            if (!S.hist[i].touch)
+                S.hist[i].nb = -1;
     }
     // reduce per body (:692-711); body 1 of a contact gets -force, body 2 gets +force
-    S.body_force.assign(nb, V3(0));
-    S.body_torque.assign(nb, V3(0));
-    for (long long i = 0; i < nc; i++) {
-        int b1 = S.c_b1[i], b2 = S.c_b2[i];
-        S.body_force[b1] = S.body_force[b1] + (-S.c_force[i]);
-        S.body_torque[b1] = S.body_torque[b1] + S.c_tq1[i];
-        S.body_force[b2] = S.body_force[b2] + S.c_force[i];
-        S.body_torque[b2] = S.body_torque[b2] + S.c_tq2[i];
+    S.body_force.resize(nb);
+    S.body_torque.resize(nb);
+    // same trick: per body the contributions are added in contact order, as the serial loop (and the reference's
+    // sort-by-body + segmented sum) would
+#pragma omp parallel
+    {
+        const int nth = omp_get_num_threads(), tid = omp_get_thread_num();
+        const int b_lo = (int)((long long)nb * tid / nth), b_hi = (int)((long long)nb * (tid + 1) / nth);
+        for (int b = b_lo; b < b_hi; b++) {
+            S.body_force[b] = V3(0);
+            S.body_torque[b] = V3(0);
+        }
+        for (long long i = 0; i < nc; i++) {
+            const int b1 = S.c_b1[i], b2 = S.c_b2[i];
+            if (b1 >= b_lo && b1 < b_hi) {
+                S.body_force[b1] = S.body_force[b1] + (-S.c_force[i]);
+                S.body_torque[b1] = S.body_torque[b1] + S.c_tq1[i];
+            }
+            if (b2 >= b_lo && b2 < b_hi) {
+                S.body_force[b2] = S.body_force[b2] + S.c_force[i];
+                S.body_torque[b2] = S.body_torque[b2] + S.c_tq2[i];
+            }
+        }
     }
     return 0;
 }
