@@ -209,8 +209,8 @@ def run_slabs(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     affinity = bind_to_gpu_numa_node(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # NCCL writes its version banner (NCCL_DEBUG >= VERSION) to stdout: send its log to stderr, rank 0 prints ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, S = args.spheres, args.substeps
