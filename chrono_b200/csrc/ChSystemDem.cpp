@@ -36,6 +36,7 @@ struct BCInfo {
     double radius = 0;             // cylinder / ball
     double slope = 0, hmin = 0, hmax = 0;  // cone
     double vel[3] = {0, 0, 0};     // ball velocity (SetBCSphereVelocity)
+    double mass = 0;               // ball: > 0 -> the ball is a free body driven by the spheres' reaction force and gravity
     bool spheres_inside = true;
     bool track_forces = false;
     bool enabled = true;
@@ -300,16 +301,20 @@ size_t ChSystemDem::CreateBCCylinderZ(const ChVector3f& center, float radius, bo
     return m_sys->bcs.size() - 1;
 }
 // Ball boundary (reference: ChSystemDem_impl.cpp:683-721).  outward_normal == false: obstacle the spheres stay outside of;
-// true: cavity.  The reference integrates a ball with mass under the reaction force on the host (:867-903); here the ball
-// moves only through SetBCSpherePosition / SetBCSphereVelocity / SetBCOffsetFunction.
-size_t ChSystemDem::CreateBCSphere(const ChVector3f& center, float radius, bool outward_normal, bool track_forces, float /*mass*/) {
+// true: cavity.  A ball with mass > 0 is a free body: after every step it is advanced on the host under the reaction force
+// of the spheres and gravity (semi-implicit Euler, as ChSystemDem_impl.cpp:867-903; the reaction torque is not used:
+// boundary bodies carry no spin in the contact law).
+size_t ChSystemDem::CreateBCSphere(const ChVector3f& center, float radius, bool outward_normal, bool track_forces, float mass) {
     if (m_sys->initialized) fail("boundary conditions must be created before Initialize");
     BCInfo bc;
     bc.kind = BCKind::SPHERE;
     bc.pos[0] = center.x(); bc.pos[1] = center.y(); bc.pos[2] = center.z();
     bc.radius = radius;
     bc.spheres_inside = outward_normal;
-    bc.track_forces = track_forces;
+    bc.mass = mass > 0 ? mass : 0;
+    bc.track_forces = track_forces || bc.mass > 0;
+    if (bc.mass > 0)
+        m_sys->any_offset = true;  // stepwise driver below
     m_sys->bcs.push_back(bc);
     return m_sys->bcs.size() - 1;
 }
@@ -501,6 +506,17 @@ double ChSystemDem::AdvanceSimulation(float duration) {
                 S.check(dem_b200_set_wall_state(S.h, bc.wall, p, v), "SetBCOffsetFunction");
             }
             S.check(dem_b200_step(S.h, 1), "AdvanceSimulation");
+            for (auto& bc : S.bcs) {
+                if (bc.kind != BCKind::SPHERE || !(bc.mass > 0) || !bc.enabled)
+                    continue;
+                double f[3];
+                S.check(dem_b200_wall_force(S.h, bc.wall, f), "BC sphere reaction force");  // synchronises: one step at a time
+                for (int k = 0; k < 3; k++) {
+                    bc.vel[k] += (f[k] / bc.mass + S.grav[k]) * S.step;
+                    bc.pos[k] += bc.vel[k] * S.step;
+                }
+                S.check(dem_b200_set_wall_state(S.h, bc.wall, bc.pos, bc.vel), "BC sphere motion");
+            }
         }
     }
     S.elapsed += (double)nsteps * S.step;

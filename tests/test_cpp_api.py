@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "cpp", "_bin")
-PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling", "utest_utils"]
+PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling", "utest_utils", "utest_DEM_bcsphere"]
 
 
 def build_program(name):
@@ -68,6 +68,12 @@ def test_dem_pyramid_from_reference_checkpoint(mode):
 def test_dem_meshrolling_and_cosim_wrench(tmp_path):
     """utest_DEM_meshrolling scenario through ChSystemDemMesh + ApplyMeshMotion / CollectMeshContactForces."""
     out = run("utest_DEM_meshrolling", str(tmp_path))
+    assert "PASSED" in out
+
+
+@pytest.mark.gpu
+def test_dem_bc_ball_with_mass_and_cone_hopper():
+    out = run("utest_DEM_bcsphere")
     assert "PASSED" in out
 
 
