@@ -154,7 +154,8 @@ class ChSystemDem_impl {
         c.wall_mass = 1e30;  // Dem walls are infinitely heavy: m_eff = m (ChDemBoundaryConditions.cuh:446)
         c.mesh_mass = 1e30;
         c.verlet_skin = -1.0;
-        c.neighbor_slots = 0;
+        // candidate slots per sphere hold sphere candidates AND the mesh facets in reach: leave room for fine meshes
+        c.neighbor_slots = meshes.empty() ? 0 : 48;
         return c;
     }
 };
