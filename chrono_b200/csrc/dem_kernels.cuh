@@ -737,7 +737,10 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
 // --------------------------------------------------------------------------------------------
 // rebuild, part 3: Verlet candidate list.  One thread per sphere (cell order), 3x3 rows of 3 contiguous cells.
 // --------------------------------------------------------------------------------------------
-constexpr int kListThreads = 128;
+#ifndef DEMB200_LIST_THREADS
+#define DEMB200_LIST_THREADS 64  /* r02: 32 -> 437 us, 64 -> 343, 128 -> 412, 256 -> 418 per rebuild of 1 M spheres */
+#endif
+constexpr int kListThreads = DEMB200_LIST_THREADS;
 
 // Closest point of triangle ABC to P (Ericson, Real-time collision detection, p.141); plain arithmetic: only used
 // to select candidates, with slack.
