@@ -22,6 +22,10 @@
 
 using namespace demb200;
 
+#ifndef DEMB200_COND_GRAPH
+#define DEMB200_COND_GRAPH 1
+#endif
+
 namespace {
 thread_local std::string g_create_error;
 }
@@ -46,6 +50,7 @@ struct dem_b200_system {
     bool initialized = false;
     cudaStream_t stream = nullptr;
     cudaStream_t cap_stream = nullptr;  // graph capture only
+    cudaStream_t cap_stream2 = nullptr; // body of the conditional node
     unsigned ntiles = 0;               // scan tiles covering the search-cell capacity
     cudaGraphExec_t graph1 = nullptr;  // one step
     bool recording = false;
@@ -271,21 +276,15 @@ const char* kKernelNames[kNumKernels] = {"k_step_begin", "k_bin_count", "k_scan_
                                          "k_force_integrate"};
 
 // Enqueue one step.  ev: optional kNumKernels+1 events recorded around each launch (profiling).
-int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
+// One step = halo + control kernel | rebuild kernels (they return at once unless k_step_begin said "rebuild") | force kernel.
+// The three parts are separate so that the step graph can put the middle one into a conditional node.
+void enqueue_pre(dem_b200_system* s, cudaStream_t st, unsigned long long cond) {
     const Params& P = s->P;
     Buffers& B = s->B;
-    const unsigned N = P.N;
-    const unsigned nb256 = (N + 255) / 256;
-    cudaStream_t st = s->stream;
-    int k = 0;
-    auto mark = [&]() {
-        if (ev)
-            cudaEventRecord(ev[k++], st);
-    };
     if (s->p2p && !s->mg_remap_pending) {
         // ghost halo of this step: my boundary spheres go straight into the neighbours' landing buffers (NVLink stores),
         // theirs are picked up as soon as their step number shows up.  (Skipped right after a rebuild: the ghosts that
-        // were just exchanged are current.)  Timed with k_step_begin in the profile.
+        // were just exchanged are current.)
         for (int d = 0; d < 2; d++)
             if (s->mg_ns[d])
                 k_p2p_pack<<<(s->mg_ns[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ns[d]);
@@ -293,10 +292,19 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
             if (s->mg_ng[d])
                 k_p2p_unpack<<<(s->mg_ng[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ng[d]);
     }
-    mark();
-    k_step_begin<<<1, 32, 0, st>>>(P, B);
-    mark();
-    // the rebuild kernels return immediately unless k_step_begin decided that the Verlet skin is used up
+    k_step_begin<<<1, 32, 0, st>>>(P, B, cond);
+}
+
+// ev: optional events recorded after each of the seven rebuild kernels (profiling), starting at ev[*k]
+void enqueue_rebuild(dem_b200_system* s, cudaStream_t st, cudaEvent_t* ev, int* k) {
+    const Params& P = s->P;
+    Buffers& B = s->B;
+    const unsigned N = P.N;
+    const unsigned nb256 = (N + 255) / 256;
+    auto mark = [&]() {
+        if (ev)
+            cudaEventRecord(ev[(*k)++], st);
+    };
     k_bin_count<<<nb256, 256, 0, st>>>(P, B);
     mark();
     k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(B, 0);
@@ -309,7 +317,7 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
     mark();
     k_gather_sorted<<<nb256, 256, 0, st>>>(P, B);
     mark();
-    if (P.nT) {  // mesh triangles -> search cells (rebuild steps only; timed with k_build_list in the profile)
+    if (P.nT) {  // mesh triangles -> search cells (timed with k_build_list in the profile)
         const unsigned tb = (P.nT + 255) / 256;
         k_tri_count<<<tb, 256, 0, st>>>(P, B);
         k_scan_tile_sums<<<s->ntiles, kScanThreads, 0, st>>>(B, 1);
@@ -319,18 +327,41 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
     }
     k_build_list<<<(N + kListThreads - 1) / kListThreads, kListThreads, 0, st>>>(P, B);
     mark();
+}
+
+void enqueue_post(dem_b200_system* s, cudaStream_t st) {
+    const Params& P = s->P;
+    Buffers& B = s->B;
+    const unsigned N = P.N;
     const unsigned fb = (N + kForceThreads - 1) / kForceThreads;
+    cudaStream_t keep = s->stream;
+    s->stream = st;  // launch_force uses s->stream
     if (s->recording) {
-        k_record_bins<<<nb256, 256, 0, st>>>(P, B);
+        k_record_bins<<<(N + 255) / 256, 256, 0, st>>>(P, B);
         launch_force<true>(s, B, fb);
     } else {
         launch_force<false>(s, B, fb);
     }
+    s->stream = keep;
     if (s->p2p)
         k_p2p_vote<<<1, 32, 0, st>>>(P, B, s->X);
-    mark();
+}
+
+// Enqueue one step.  ev: optional kNumKernels+1 events recorded around each launch (profiling).
+int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
+    cudaStream_t st = s->stream;
+    int k = 0;
+    if (ev)
+        cudaEventRecord(ev[k++], st);
+    enqueue_pre(s, st, 0ull);
+    if (ev)
+        cudaEventRecord(ev[k++], st);
+    enqueue_rebuild(s, st, ev, &k);
+    enqueue_post(s, st);
+    if (ev)
+        cudaEventRecord(ev[k++], st);
     CU(cudaGetLastError());
-    s->time += P.dt;
+    s->time += s->P.dt;
     s->step_no++;
     s->export_valid = false;
     return 0;
@@ -343,12 +374,80 @@ void drop_graph(dem_b200_system* s) {
     }
 }
 
+// The step graph: [halo, k_step_begin] -> IF(rebuild) { rebuild kernels } -> [force kernel, vote].  k_step_begin sets the
+// condition on the device (cudaGraphSetConditional), so a step that does not rebuild launches nothing in between.  Falls
+// back to the flat capture (rebuild kernels that return at once) if conditional nodes are not available.
+int build_graph_conditional(dem_b200_system* s, cudaGraph_t* out) {
+#if DEMB200_COND_GRAPH
+    cudaStream_t cs = s->cap_stream;
+    if (!s->cap_stream2 && cudaStreamCreateWithFlags(&s->cap_stream2, cudaStreamNonBlocking) != cudaSuccess)
+        return 1;
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return 1;
+    cudaGraph_t g = nullptr;
+    auto bail = [&]() {
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(cs, &junk);
+        if (junk)
+            cudaGraphDestroy(junk);
+        cudaGetLastError();
+        return 1;
+    };
+    cudaStreamCaptureStatus status;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    if (cudaStreamGetCaptureInfo_v2(cs, &status, nullptr, &g, &deps, &ndeps) != cudaSuccess || !g)
+        return bail();
+    cudaGraphConditionalHandle handle;
+    if (cudaGraphConditionalHandleCreate(&handle, g, 0, cudaGraphCondAssignDefault) != cudaSuccess)
+        return bail();
+    enqueue_pre(s, cs, (unsigned long long)handle);
+    if (cudaStreamGetCaptureInfo_v2(cs, &status, nullptr, &g, &deps, &ndeps) != cudaSuccess)
+        return bail();
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.size = 1;
+    cudaGraphNode_t cnode;
+    if (cudaGraphAddNode(&cnode, g, deps, ndeps, &cp) != cudaSuccess)
+        return bail();
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    if (cudaStreamBeginCaptureToGraph(s->cap_stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return bail();
+    enqueue_rebuild(s, s->cap_stream2, nullptr, nullptr);
+    cudaGraph_t body_out = nullptr;
+    if (cudaStreamEndCapture(s->cap_stream2, &body_out) != cudaSuccess)
+        return bail();
+    if (cudaStreamUpdateCaptureDependencies(cs, &cnode, 1, cudaStreamSetCaptureDependencies) != cudaSuccess)
+        return bail();
+    enqueue_post(s, cs);
+    if (cudaStreamEndCapture(cs, &g) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    *out = g;
+    return 0;
+#else
+    (void)s; (void)out;
+    return 1;
+#endif
+}
+
 int build_graph(dem_b200_system* s) {
     cudaGraph_t g = nullptr;
     // capture on a private stream: the caller's stream may be the legacy default stream (slab mode runs on torch's
     // current stream), which cannot be captured; the instantiated graph is launched into s->stream
     if (!s->cap_stream)
         CU(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    if (build_graph_conditional(s, &g) == 0) {
+        cudaError_t ei = cudaGraphInstantiate(&s->graph1, g, 0);
+        cudaGraphDestroy(g);
+        if (ei == cudaSuccess)
+            return 0;
+        cudaGetLastError();
+        s->graph1 = nullptr;
+    }
+    g = nullptr;
     cudaStream_t run_stream = s->stream;
     s->stream = s->cap_stream;
     cudaError_t e0 = cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal);
@@ -525,6 +624,8 @@ void dem_b200_destroy(dem_b200_system* s) {
         cudaStreamDestroy(s->stream);
     if (s->cap_stream)
         cudaStreamDestroy(s->cap_stream);
+    if (s->cap_stream2)
+        cudaStreamDestroy(s->cap_stream2);
     delete s;
 }
 

@@ -206,7 +206,9 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
 
 // The control block is staged through shared memory by the whole warp: the serial part then works at shared-memory
 // latency instead of paying a global round trip for every field it touches.
-__global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B) {
+// `cond` != 0: handle of the conditional node of the step graph that holds the rebuild kernels; its body only runs in the
+// steps that rebuild (no empty launches of N / 256-block grids in the other ~97 % of the steps).
+__global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned long long cond) {
     __shared__ Ctrl sC;
     static_assert(sizeof(Ctrl) % 8 == 0, "Ctrl is copied in 8-byte words");
     if (blockIdx.x != 0)
@@ -217,8 +219,11 @@ __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B) {
     for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x)
         l[i] = g[i];
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         step_begin_body(P, B, sC);
+        if (cond)
+            cudaGraphSetConditional((cudaGraphConditionalHandle)cond, sC.rebuild_now);
+    }
     __syncthreads();
     for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x)
         g[i] = l[i];
