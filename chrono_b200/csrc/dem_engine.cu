@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -439,9 +440,16 @@ int build_graph(dem_b200_system* s) {
     // current stream), which cannot be captured; the instantiated graph is launched into s->stream
     if (!s->cap_stream)
         CU(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
-    // slab mode re-captures the graph after every slab rebuild (the local sphere count changes): there the flat capture,
-    // which is cheaper to build, wins (2 x B200: 36.2 vs 37.3 ms per 100 steps)
-    if (!s->mgpu && build_graph_conditional(s, &g) == 0) {
+    // The conditional step graph is opt-in (DEMB200_COND_GRAPH=1 in the environment): it saves the seven empty rebuild
+    // launches of a non-rebuilding step (32.0 vs 32.4 - 33.2 ms per 100 steps at 1 M spheres), but ncu cannot see the kernel
+    // nodes of a graph that holds a conditional node, so the default is the flat capture whose launches are all profilable.
+    // Slab mode re-captures the graph after every slab rebuild (the local sphere count changes): there the flat capture,
+    // which is cheaper to build, wins anyway (2 x B200: 36.2 vs 37.3 ms per 100 steps).
+    static const bool want_cond = [] {
+        const char* e = getenv("DEMB200_COND_GRAPH");
+        return e && e[0] == '1';
+    }();
+    if (want_cond && !s->mgpu && build_graph_conditional(s, &g) == 0) {
         cudaError_t ei = cudaGraphInstantiate(&s->graph1, g, 0);
         cudaGraphDestroy(g);
         if (ei == cudaSuccess)
