@@ -370,14 +370,21 @@ ChVector3f ChSystemDem::GetBCSphereVelocity(size_t id) const {
 }
 // Declared by the reference, not provided by this engine (never called in-tree outside src/chrono_dem): fail loudly.
 void ChSystemDem::SetBCPlaneRotation(size_t, ChVector3d, ChVector3d) { fail("SetBCPlaneRotation is not supported"); }
-ChVector3f ChSystemDem::GetParticleLinAcc(int) const { fail("GetParticleLinAcc is not supported"); }
+// acceleration of the last step, gravity included (the reference returns its sphere_acc array: ChSystemDem_impl.cpp:1290-1296)
+ChVector3f ChSystemDem::GetParticleLinAcc(int i) const {
+    const ChSystemDem_impl& S = *m_sys;
+    if (!S.initialized)
+        return ChVector3f(0, 0, 0);
+    double a[3];
+    S.check(dem_b200_get_sphere_accel(S.h, (size_t)i, a), "GetParticleLinAcc");
+    return ChVector3f((float)a[0], (float)a[1], (float)a[2]);
+}
 void ChSystemDem::WriteContactInfoFile(const std::string&) const { fail("WriteContactInfoFile / SetRecordingContactInfo are not supported"); }
 ChVector3f ChSystemDem::getRollingFrictionTorque(unsigned int, unsigned int) { fail("getRollingFrictionTorque is not supported"); }
 ChVector3f ChSystemDem::getSlidingFrictionForce(unsigned int, unsigned int) { fail("getSlidingFrictionForce is not supported"); }
 ChVector3f ChSystemDem::getNormalForce(unsigned int, unsigned int) { fail("getNormalForce is not supported"); }
 ChVector3f ChSystemDem::getRollingVrot(unsigned int, unsigned int) { fail("getRollingVrot is not supported"); }
 float ChSystemDem::getRollingCharContactTime(unsigned int, unsigned int) { fail("getRollingCharContactTime is not supported"); }
-void ChSystemDem::getNeighbors(unsigned int, std::vector<unsigned int>&) { fail("getNeighbors is not supported"); }
 bool ChSystemDem::DisableBCbyID(size_t id) {
     if (id >= m_sys->bcs.size()) return false;
     m_sys->bcs[id].enabled = false;
@@ -648,7 +655,15 @@ void ChSystemDem::WriteCsvParticles(std::ofstream& ptFile) const {
     if (f & ABSV) o << ",absv";
     if (f & FIXITY) o << ",fixed";
     if (fr && (f & ANG_VEL_COMPONENTS)) o << ",wx,wy,wz";
+    if (f & FORCE_COMPONENTS) o << ",fx,fy,fz";
     o << "\n";
+    // contact force on each sphere = (acceleration of the last step - g) * mass (ChSystemDem_impl.cpp:322-327)
+    std::vector<double> acc;
+    if (f & FORCE_COMPONENTS) {
+        acc.assign(3 * S.n(), 0.0);
+        if (S.initialized)
+            S.check(dem_b200_get_accel(S.h, acc.data()), "WriteParticleFile");
+    }
     for (size_t i = 0; i < S.n(); i++) {
         const float x = (float)s.pos[3 * i], y = (float)s.pos[3 * i + 1], z = (float)s.pos[3 * i + 2];
         o << x << "," << y << "," << z;
@@ -658,6 +673,12 @@ void ChSystemDem::WriteCsvParticles(std::ofstream& ptFile) const {
         if (f & FIXITY) o << "," << (int)S.fixed[i];
         if (fr && (f & ANG_VEL_COMPONENTS))
             o << "," << (float)s.omg[3 * i] << "," << (float)s.omg[3 * i + 1] << "," << (float)s.omg[3 * i + 2];
+        if (f & FORCE_COMPONENTS) {
+            const double r = S.rad.size() == S.n() ? S.rad[i] : (double)S.radius;
+            const double m = 4.0 / 3.0 * 3.14159265358979323846 * r * r * r * S.density;
+            for (int k = 0; k < 3; k++)  // before the first step the acceleration is zero, as the reference's sphere_acc
+                o << "," << (acc[3 * i + k] - (double)S.grav[k]) * m;
+        }
         o << "\n";
     }
     ptFile << o.str();
@@ -739,11 +760,10 @@ void ChSystemDem::WriteCheckpointParams(std::ofstream& cp) const {
 // nSpheres + BC_id + 1 for a boundary (ChDemBoundaryConditions.cuh:102), NULL_CHDEM_ID for an empty slot.  Each sphere
 // lists every contact it takes part in (as the reference does); the displacement is written from that sphere's point of
 // view (sign flipped for the higher-id partner, see the reader).
-void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
-    const ChSystemDem_impl& S = *m_sys;
+using PartnerRows = std::vector<std::vector<std::pair<uint32_t, std::array<float, 3>>>>;
+static PartnerRows partner_rows(const ChSystemDem_impl& S) {
     const size_t n = S.n();
-    const unsigned K = MAX_SPHERES_TOUCHED_BY_SPHERE;
-    std::vector<std::vector<std::pair<uint32_t, std::array<float, 3>>>> rows(n);
+    PartnerRows rows(n);
     if (S.initialized && S.friction == CHDEM_FRICTION_MODE::MULTI_STEP) {
         size_t m = 0;
         S.check(dem_b200_get_history(S.h, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &m), "WriteHstHistory");
@@ -779,6 +799,14 @@ void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
             }
         }
     }
+    return rows;
+}
+
+void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
+    const ChSystemDem_impl& S = *m_sys;
+    const size_t n = S.n();
+    const unsigned K = MAX_SPHERES_TOUCHED_BY_SPHERE;
+    const PartnerRows rows = partner_rows(S);
     std::ostringstream o;
     o << "partners " << K << " history " << K << "\n";
     for (size_t i = 0; i < n; i++) {
@@ -793,6 +821,18 @@ void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
         o << "\n";
     }
     hf << o.str();
+}
+
+// partner labels of one sphere, as the reference's contact_partners_map row (ChSystemDem_impl.cpp:469-480): sphere
+// indices, nSpheres + BC_id + 1 for boundaries, the mesh-family label for facets.  MULTI_STEP friction only (the engine
+// keeps a contact map only where there is history to keep).
+void ChSystemDem::getNeighbors(unsigned int ID, std::vector<unsigned int>& neighborList) {
+    const ChSystemDem_impl& S = *m_sys;
+    if (ID >= S.n())
+        fail("getNeighbors: bad sphere id");
+    const PartnerRows rows = partner_rows(S);
+    for (auto& r : rows[ID])
+        neighborList.push_back(r.first);
 }
 
 void ChSystemDem::WriteContactHistoryFile(const std::string& outfilename) const {

@@ -87,6 +87,9 @@ struct dem_b200_system {
     double* d_red = nullptr;            // reduction scratch (2 x 8 bytes)
     double* h_pin = nullptr;            // pinned, 16 doubles
     bool export_valid = false;
+    double* d_acc3 = nullptr;        // user-order acceleration of the last step (allocated at the first dem_b200_get_accel)
+    bool accel_src_valid = false;    // the last thing that changed the state was a step (the other ping-pong buffer is its input)
+    bool accel_export_valid = false;
     std::vector<void*> allocs;
     // history staged before initialize (add_history)
     struct HRow { uint32_t owner, other; double d[3], dur, rel; };
@@ -365,6 +368,8 @@ int enqueue_step(dem_b200_system* s, cudaEvent_t* ev) {
     s->time += s->P.dt;
     s->step_no++;
     s->export_valid = false;
+    s->accel_src_valid = true;
+    s->accel_export_valid = false;
     return 0;
 }
 
@@ -553,6 +558,10 @@ int run_steps(dem_b200_system* s, int nsteps) {
             s->step_no++;
         }
         s->export_valid = false;
+        if (nsteps > 0) {
+            s->accel_src_valid = true;
+            s->accel_export_valid = false;
+        }
     }
     for (; done < nsteps; done++) {
         int rc = enqueue_step(s, nullptr);
@@ -1326,9 +1335,57 @@ int dem_b200_set_state(dem_b200_system* s, const double* pos3, const double* vel
                                                                 vel3 ? s->d_vel3 : nullptr, omega3 ? s->d_om3 : nullptr);
     CU(cudaGetLastError());
     s->export_valid = false;
+    s->accel_src_valid = s->accel_export_valid = false;
     if (pos3)
         return recompute_bbox(s);
     return 0;
+}
+
+namespace {
+int export_accel(dem_b200_system* s) {
+    if (s->mgpu)
+        return DEMB200_EINVAL;  // slab mode: the owned set changes at every slab rebuild; not offered there
+    const size_t N = s->P.N;
+    if (!s->d_acc3) {
+        int rc = dev_alloc(s, &s->d_acc3, 3 * N);
+        if (rc)
+            return rc;
+    }
+    if (s->accel_export_valid)
+        return 0;
+    if (!s->accel_src_valid) {  // no step since Initialize / set_state: zero, as the reference's freshly reset sphere_acc
+        CU(cudaMemsetAsync(s->d_acc3, 0, 3 * N * sizeof(double), s->stream));
+    } else {
+        k_export_accel<<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>(s->P, s->B, s->d_acc3);
+        CU(cudaGetLastError());
+    }
+    s->accel_export_valid = true;
+    return 0;
+}
+}  // namespace
+
+int dem_b200_get_accel(dem_b200_system* s, double* acc3) {
+    if (!s || !s->initialized || !acc3)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    int rc = export_accel(s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(acc3, s->d_acc3, 3 * (size_t)s->P.N * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return check_device_error(s);
+}
+
+int dem_b200_get_sphere_accel(dem_b200_system* s, size_t i, double acc[3]) {
+    if (!s || !s->initialized || !acc || i >= s->P.N)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    int rc = export_accel(s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(s->h_pin + 1, s->d_acc3 + 3 * i, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    rc = check_device_error(s);  // synchronises
+    memcpy(acc, s->h_pin + 1, 3 * sizeof(double));
+    return rc;
 }
 
 int dem_b200_advance_host(dem_b200_system* s, size_t n, const double* pos3_in, const double* vel3_in,

@@ -2520,6 +2520,31 @@ __global__ void __launch_bounds__(256) k_export_state(Params P, Buffers B, doubl
     if (om3) { om3[o] = r.w.x; om3[o + 1] = r.w.y; om3[o + 2] = r.w.z; }
 }
 
+// Linear acceleration of the last step, user order (GetParticleLinAcc, the fx,fy,fz columns of WriteParticleFile:
+// ChSystemDem_impl.cpp:1290-1296, 322-327).  The fused force kernel does not keep the acceleration; after a step the
+// other ping-pong buffer still holds the state the step started from, in the same slot order, and every integrator but
+// Chung advances v by h * a, so a = (v+ - v) / h.  Chung keeps (a, alpha) of the step in B.acc.  Fixed spheres: 0.
+__global__ void __launch_bounds__(256) k_export_accel(Params P, Buffers B, double* acc3) {
+    const Ctrl& C = *B.ctrl;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N)
+        return;
+    const VelVal r1 = load_vel(B.vel[C.cur], i);
+    V3 a = mk(0.0, 0.0, 0.0);
+    if (!(r1.meta & (FLAG_FIXED | FLAG_GHOST))) {
+        if (P.integrator == 1) {
+            const double* ap = B.acc[C.cur] + 6 * (size_t)i;
+            a = mk(ap[0], ap[1], ap[2]);
+        } else {
+            const VelVal r0 = load_vel(B.vel[C.cur ^ 1u], i);
+            const double inv_h = 1.0 / P.dt;
+            a = mk((r1.v.x - r0.v.x) * inv_h, (r1.v.y - r0.v.y) * inv_h, (r1.v.z - r0.v.z) * inv_h);
+        }
+    }
+    const size_t o = 3 * (size_t)r1.sid;
+    acc3[o] = a.x; acc3[o + 1] = a.y; acc3[o + 2] = a.z;
+}
+
 __global__ void __launch_bounds__(256) k_import_state(Params P, Buffers B, const double* pos3, const double* vel3,
                                                       const double* om3) {
     Ctrl& C = *B.ctrl;

@@ -248,6 +248,12 @@ class DemSystem:
         self._ck(self.L.dem_b200_get_forces(self.h, _dp(f), _dp(t)))
         return f, t
 
+    def accel(self):
+        """Linear acceleration of the last step, gravity included, user order (GetParticleLinAcc)."""
+        a = np.empty((self.n, 3))
+        self._ck(self.L.dem_b200_get_accel(self.h, _dp(a)))
+        return a
+
     def pairs(self):
         n = C.c_size_t(0)
         self._ck(self.L.dem_b200_get_pairs(self.h, None, C.c_size_t(0), C.byref(n)))

@@ -166,6 +166,11 @@ size_t dem_b200_num_spheres(const dem_b200_system* s);
 int dem_b200_get_state(dem_b200_system* s, double* pos3, double* vel3, double* omega3);
 int dem_b200_set_state(dem_b200_system* s, const double* pos3, const double* vel3, const double* omega3);
 int dem_b200_get_sphere(dem_b200_system* s, size_t i, double pos[3], double vel[3], double omega[3]);
+/* Linear acceleration (gravity included) each sphere had in the last step, user order -- GetParticleLinAcc
+ * (ChSystemDem.h:273, ChSystemDem_impl.cpp:1290-1296) and the fx,fy,fz columns of WriteParticleFile (:322-327).  Zero
+ * before the first step and right after dem_b200_set_state; zero for fixed spheres.  Not available in slab mode. */
+int dem_b200_get_accel(dem_b200_system* s, double* acc3);
+int dem_b200_get_sphere_accel(dem_b200_system* s, size_t i, double acc[3]);
 double dem_b200_time(const dem_b200_system* s);
 
 /* ---- reductions -- GetMaxParticleZ, GetParticlesKineticEnergy, ... (ChSystemDem.h:246-262) ------------------ */

@@ -65,6 +65,49 @@ void demApi(int argc, char** argv) {
         while (std::getline(f, line)) rows += !line.empty();
         ASSERT_TRUE(rows == n);
     }
+    // force columns: (acceleration of the last step - g) * mass (ChSystemDem_impl.cpp:322-327), consistent with GetParticleLinAcc
+    a.SetParticleOutputFlags(FORCE_COMPONENTS);
+    a.WriteParticleFile(dir + "/pf.csv");
+    a.SetParticleOutputFlags(ABSV | VEL_COMPONENTS | FIXITY | ANG_VEL_COMPONENTS);
+    {
+        std::ifstream f(dir + "/pf.csv");
+        std::string header, line;
+        std::getline(f, header);
+        ASSERT_TRUE(header == "x,y,z,fx,fy,fz");
+        const double mass = 4.0 / 3.0 * 3.14159265358979323846 * R * R * R * 2500.0;
+        double fz_sum = 0, worst = 0;
+        for (size_t i = 0; i < n; i++) {
+            ASSERT_TRUE((bool)std::getline(f, line));
+            for (char& ch : line) if (ch == ',') ch = ' ';
+            std::istringstream is(line);
+            double x, y, z, fx, fy, fz;
+            is >> x >> y >> z >> fx >> fy >> fz;
+            ASSERT_TRUE(!is.fail());
+            const ChVector3f acc = a.GetParticleLinAcc((int)i);
+            const double want[3] = {acc.x() * mass, acc.y() * mass, (acc.z() + 9.81f) * mass};
+            const double got[3] = {fx, fy, fz};
+            for (int k = 0; k < 3; k++)
+                worst = std::max(worst, std::abs(got[k] - want[k]) / (mass * 9.81));
+            fz_sum += fz;
+        }
+        std::printf("force columns vs GetParticleLinAcc: worst difference %.3g of a sphere's weight; sum fz / bed weight %.4f\n",
+                    worst, fz_sum / (n * mass * 9.81));
+        ASSERT_TRUE(worst < 1e-4);                                     // float getter + 6-digit text
+        ASSERT_NEAR(fz_sum / (n * mass * 9.81), 1.0, 0.25);            // a bed (nearly) at rest carries its weight
+    }
+    // contact partners of a bottom-layer sphere of the settled columns: the sphere above it and the floor (BC 4 = bottom
+    // z plane, label nSpheres + BC_id + 1: ChDemBoundaryConditions.cuh:102)
+    {
+        std::vector<unsigned int> nb;
+        a.getNeighbors(0, nb);
+        bool has_above = false, has_wall = false;
+        for (unsigned int l : nb) {
+            has_above |= (l == 36u);
+            has_wall |= (l > n);
+        }
+        std::printf("sphere 0 touches %zu partners\n", nb.size());
+        ASSERT_TRUE(has_above && has_wall);
+    }
     a.SetParticleOutputMode(CHDEM_OUTPUT_MODE::BINARY);
     a.WriteParticleFile(dir + "/p.raw");
     {
@@ -122,6 +165,11 @@ void demApi(int argc, char** argv) {
     c.SetParticleFixed({false, true});
     c.CreateBCCylinderZ(ChVector3f(0, 0, 0), 0.4f, false, false);
     c.Initialize();
+    ASSERT_NEAR(c.GetParticleLinAcc(0).Length(), 0.0, 0.0);      // no step yet
+    c.AdvanceSimulation(1e-4f);
+    ASSERT_NEAR(c.GetParticleLinAcc(0).z(), -9.81, 1e-5);         // free flight: gravity alone
+    ASSERT_NEAR(c.GetParticleLinAcc(0).x(), 0.0, 1e-6);
+    ASSERT_NEAR(c.GetParticleLinAcc(1).Length(), 0.0, 0.0);      // fixed
     c.AdvanceSimulation(0.5f);
     ChVector3f p0 = c.GetParticlePosition(0), p1 = c.GetParticlePosition(1);
     ASSERT_TRUE(std::sqrt(p0.x() * p0.x() + p0.y() * p0.y()) < 0.4 - R + 0.01);  // bounced off the cylinder wall

@@ -183,6 +183,40 @@ def test_reductions_and_single_sphere_access():
     assert np.array_equal(p7, pos[7]) and np.array_equal(v7, v[7]) and np.array_equal(w7, w[7])
 
 
+@pytest.mark.parametrize("integ", ["CENTERED_DIFFERENCE", "EXTENDED_TAYLOR", "CHUNG"])
+def test_acceleration_of_the_last_step(integ):
+    """dem_b200_get_accel (GetParticleLinAcc, the fx,fy,fz columns of WriteParticleFile: ChSystemDem_impl.cpp:1290-1296,
+    322-327) against g + F / m with F the recorded contact force of the same step; zero before the first step and for
+    fixed spheres; graph path == recorded path."""
+    from chrono_b200 import dem
+    n = 3000
+    scene = scenes.settling_scene(n, sep_factor=1.985, seed=5)
+    fixed = np.zeros(n, dtype=np.uint8)
+    fixed[::17] = 1
+    scene["fixed"] = fixed
+    vel, om = kinematics(n, 21)
+    g = common.make_gpu(scene, vel=vel, omega=om, dt=1e-4, integrator=getattr(dem, integ))
+    assert not g.accel().any()
+    g.enable_recording(True, max_pairs=40 * n)
+    g.step(3)
+    F, _ = g.forces()
+    m = np.broadcast_to(common.sphere_mass(scene["radius"]), (n,))[:, None]
+    want = np.array([0, 0, -9.81]) + F / m
+    want[fixed != 0] = 0
+    got = g.accel()
+    assert np.abs(F).max() > 0
+    assert common.rel_err(got, want) < 1e-8
+    assert not got[fixed != 0].any()
+    # the same three steps through the step graph
+    g2 = common.make_gpu(scene, vel=vel, omega=om, dt=1e-4, integrator=getattr(dem, integ))
+    g2.step(3)
+    assert common.rel_err(g2.accel(), got) < 1e-8
+    # replacing the state makes the last step's acceleration meaningless: zero again
+    p, v, w = g2.state()
+    g2.set_state(vel=v)
+    assert not g2.accel().any()
+
+
 def test_bins_smaller_than_a_sphere():
     """Multicore registers a shape in every bin its AABB overlaps, so a resolution with bins smaller than a sphere
     diameter is legal there.  The engine's own search grid is independent of bins_per_axis: pair lists, bin ranges
