@@ -1582,7 +1582,7 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
         for (size_t k = 0; k < Kn; k++) {
             if (!((vr[i].amask >> k) & 1ull))
                 continue;
-            const uint32_t jo = nl[k * Np + i];
+            const uint32_t jo = nl[k * Np + i] & ~kHiFlag;
             const uint32_t key = (jo & kTriFlag) ? (uint32_t)s->P.nW + (jo & ~kTriFlag) : s->P.shape_base + vr[jo].sid;
             if (key < me)
                 emit(me, key, k * Np + i);

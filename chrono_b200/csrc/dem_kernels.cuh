@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
             amask &= amask - 1;
             const size_t si = (size_t)k * P.Np + src;
             if (cnt < (unsigned)P.K) {
-                const unsigned jo = B.nl[si];  // old storage slot of the partner, or kTriFlag | triangle
+                const unsigned jo = B.nl[si] & ~kHiFlag;  // old storage slot of the partner, or kTriFlag | triangle
                 double4 r = B.hist[si];
                 r.w = pack_key((jo & kTriFlag) ? (unsigned)P.nW + (jo & ~kTriFlag) : P.shape_base + B.vel[a][jo].sid, (unsigned)r.w);
                 B.stage[(size_t)cnt * P.Np + s] = r;
@@ -872,8 +872,11 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         if (overflow)
             atomicOr(&C.err, ERR_NEIGHBOR_OVERFLOW);
     }
-    for (int k = 0; k < cnt + tcnt; k++)
-        B.nl[(size_t)k * P.Np + s] = tj[k];
+    {
+        const unsigned my_sid = vel[s].sid;
+        for (int k = 0; k < cnt + tcnt; k++)
+            B.nl[(size_t)k * P.Np + s] = tj[k] | ((k < cnt && ts[k] > my_sid) ? kHiFlag : 0u);
+    }
     if ((unsigned)(cnt + tcnt) > C.max_cand)
         atomicMax(&C.max_cand, (unsigned)(cnt + tcnt));
     // walls the sphere can touch before the next rebuild: it moves less than skin/2 until then (walls only move
@@ -1630,7 +1633,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 jj[u] = jn[u];
 #pragma unroll
             for (int u = 0; u < kP1; u++)
-                pp[u] = ld256(pos_in + jj[u]);
+                pp[u] = ld256(pos_in + (jj[u] & ~kHiFlag));
 #pragma unroll
             for (int u = 0; u < kP1; u++)
                 jn[u] = (k0 + kP1 + u < nc) ? nl[(size_t)(k0 + kP1 + u) * P.Np] : s;
@@ -1643,11 +1646,11 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
                     continue;
                 if (cnt < kMaxSlots) {
-                    clist[cnt * kForceThreads + tid] = jj[u];
-                    cslot[cnt * kForceThreads + tid] = (unsigned char)(k0 + u);
+                    clist[cnt * kForceThreads + tid] = jj[u] & ~kHiFlag;
+                    cslot[cnt * kForceThreads + tid] = (unsigned char)((k0 + u) | ((jj[u] & kHiFlag) ? kSlotHi : 0u));
                 }
 #if DEMB200_EARLYPF
-                prefetch_l1(vel_in + jj[u]);  // the partner's velocity record is needed in phase 2
+                prefetch_l1(vel_in + (jj[u] & ~kHiFlag));  // the partner's velocity record is needed in phase 2
 #endif
                 cnt++;
             }
@@ -1762,11 +1765,11 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
     unsigned slot_next = 0;
     if (cnt > 0) {
         const unsigned j0 = clist[tid];
-        slot_next = cslot[tid];
+        slot_next = cslot[tid];  // slot | kSlotHi
         pj_next = ld256(pos_in + j0);
         ov_next = load_vel(vel_in, j0);
-        if (HIST && ((amask_old >> slot_next) & 1ull))
-            hr_next = ld256v(hcol + (size_t)slot_next * P.Np);
+        if (HIST && ((amask_old >> (slot_next & 63u)) & 1ull))
+            hr_next = ld256v(hcol + (size_t)(slot_next & 63u) * P.Np);
     }
     for (int k = 0; k < maxc; k++) {
         if (k >= cnt)
@@ -1777,11 +1780,14 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         // Keep the consumer of the prefetched record HERE: without this the compiler copies the freshly loaded
         // registers into their loop-carried homes right behind the load below and stalls on it (ncu r01d).
         asm volatile("" : "+d"(hr.x), "+d"(hr.y), "+d"(hr.z), "+d"(hr.w));
-        const unsigned slot = slot_next;
+        const unsigned slot = slot_next & 63u;
+        // canonical orientation: body 1 = lower stable id.  Decided by k_build_list (kHiFlag) and carried in the slot
+        // byte: the partner's id is not gathered for it (the only other use of that id is the recorded pair key).
+        const bool me1 = (slot_next & kSlotHi) != 0;
 #if DEMB200_PF2
         if (k + 2 < cnt) {  // two contacts ahead: lines into L1, so that the register loads below hit
             const unsigned j2 = clist[(k + 2) * kForceThreads + tid];
-            const unsigned s2 = cslot[(k + 2) * kForceThreads + tid];
+            const unsigned s2 = cslot[(k + 2) * kForceThreads + tid] & 63u;
             prefetch_l1(pos_in + j2);
             prefetch_l1(vel_in + j2);
             if (HIST && ((amask_old >> s2) & 1ull))
@@ -1793,11 +1799,10 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             slot_next = cslot[(k + 1) * kForceThreads + tid];
             pj_next = ld256(pos_in + jn);
             ov_next = load_vel(vel_in, jn);
-            if (HIST && ((amask_old >> slot_next) & 1ull))
-                hr_next = ld256v(hcol + (size_t)slot_next * P.Np);
+            if (HIST && ((amask_old >> (slot_next & 63u)) & 1ull))
+                hr_next = ld256v(hcol + (size_t)(slot_next & 63u) * P.Np);
         }
-        const unsigned sj = ov.sid;
-        const bool me1 = sid < sj;  // canonical orientation: body 1 = lower shape id
+        const unsigned sj = REC ? ov.sid : 0u;
         const bool had = HIST && ((amask_old >> slot) & 1ull);
         const size_t hi = (size_t)slot * P.Np;
         ncontacts++;
@@ -2014,7 +2019,7 @@ __device__ __forceinline__ unsigned walk_history(const Params& P, const Buffers&
         amask &= amask - 1;
         const size_t si = (size_t)k * P.Np + src;
         if (cnt < (unsigned)P.K) {
-            const unsigned jo = B.nl[si];
+            const unsigned jo = B.nl[si] & ~kHiFlag;
             double4 r = B.hist[si];
             r.w = pack_key((jo & kTriFlag) ? (unsigned)P.nW + (jo & ~kTriFlag) : P.shape_base + vel_old[jo].sid, (unsigned)r.w);
             emit(cnt, r, B.hrel ? B.hrel[si] : 0.0);

@@ -31,6 +31,10 @@ constexpr int kMaxSlots = 32;      // upper bound of K = simultaneous contacts o
 constexpr int kMaxNeighbors = 64;  // upper bound of Verlet candidate slots Kn (live mask is 64 bits)
 constexpr int kMaxMeshes = 16;     // triangle-mesh bodies (ChSystemDemMesh::AddMesh)
 constexpr unsigned kTriFlag = 0x80000000u;  // candidate-list entry = triangle (index in the low bits), not a sphere slot
+constexpr unsigned kHiFlag = 0x40000000u;   // sphere entry: the partner's stable id is higher than the owner's, i.e. the owner is body 1 of
+                                            // the canonical (lower id, higher id) orientation -- decided once per list build so that the
+                                            // force kernel does not have to gather the partner's id for it
+constexpr unsigned kSlotHi = 0x80u;         // the same bit in the force kernel's shared-memory contact list (slot byte: slot < 64)
 
 // device error bits (dem_b200 error codes are derived from these at sync points)
 enum : unsigned {
