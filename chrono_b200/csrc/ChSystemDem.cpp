@@ -586,7 +586,7 @@ unsigned int ChSystemDem::GetNumParticleAboveX(float x) const {
 }
 float ChSystemDem::GetParticlesKineticEnergy() const {
     // the reference sums m v^2 / 2 only (ChSystemDem_impl.cpp:1250-1264); the engine adds the rotational part
-    return (float)reduce(*m_sys, DEMB200_RED_KE, 0, "GetParticlesKineticEnergy");
+    return (float)reduce(*m_sys, DEMB200_RED_KE_TRANSLATIONAL, 0, "GetParticlesKineticEnergy");
 }
 unsigned int ChSystemDem::GetNumContacts() const {
     if (m_sys->friction != CHDEM_FRICTION_MODE::MULTI_STEP)

@@ -79,6 +79,9 @@ struct dem_b200_system {
     unsigned long long* h_vote = nullptr;     // pinned, mapped
     unsigned long long step_no = 0;      // host mirror of Ctrl::nsteps (steps enqueued so far)
     unsigned long long p2p_rebuild_seq = 0;
+    unsigned long long slab_rebuilds = 0;  // host-driven slab rebuilds (dem_b200_mgpu_finish_rebuild)
+    size_t owned_export_n = (size_t)-1;    // dem_b200_export_owned bookkeeping for dem_b200_import_owned
+    unsigned long long owned_export_step = ~0ull, owned_export_seq = ~0ull;
     int one_step_calls = 0;
     double time = 0.0;
     std::string err;
@@ -986,6 +989,17 @@ int dem_b200_initialize(dem_b200_system* s) {
         s->err = "set_sphere_ids: size differs from set_spheres";
         return DEMB200_EINVAL;
     }
+    if (!s->h_ids.empty() && !s->mgpu) {
+        // without slab mode the ids index user-order buffers of n entries (get_state, recording ...): a permutation of 0 .. n-1
+        std::vector<uint8_t> seen(n, 0);
+        for (uint32_t id : s->h_ids) {
+            if (id >= n || seen[id]) {
+                s->err = "set_sphere_ids: outside slab mode the ids must be a permutation of 0 .. n-1";
+                return DEMB200_EINVAL;
+            }
+            seen[id] = 1;
+        }
+    }
     refresh_params(s);
     if (P.bins[0] < 1 || P.bins[1] < 1 || P.bins[2] < 1) {
         s->err = "bad bins_per_axis";
@@ -1293,6 +1307,10 @@ double dem_b200_time(const dem_b200_system* s) { return s ? s->time : 0.0; }
 int dem_b200_get_state(dem_b200_system* s, double* pos3, double* vel3, double* omega3) {
     if (!s || !s->initialized)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     int rc = export_state(s);
     if (rc)
@@ -1307,6 +1325,10 @@ int dem_b200_get_state(dem_b200_system* s, double* pos3, double* vel3, double* o
 int dem_b200_get_sphere(dem_b200_system* s, size_t i, double pos[3], double vel[3], double omega[3]) {
     if (!s || !s->initialized || i >= s->P.N)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     int rc = export_state(s);
     if (rc)
@@ -1326,6 +1348,10 @@ int dem_b200_get_sphere(dem_b200_system* s, size_t i, double pos[3], double vel[
 int dem_b200_set_state(dem_b200_system* s, const double* pos3, const double* vel3, const double* omega3) {
     if (!s || !s->initialized)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     const size_t bytes = 3 * (size_t)s->P.N * sizeof(double);
     if (pos3) CU(cudaMemcpyAsync(s->d_pos3, pos3, bytes, cudaMemcpyHostToDevice, s->stream));
@@ -1393,6 +1419,10 @@ int dem_b200_advance_host(dem_b200_system* s, size_t n, const double* pos3_in, c
                           double* omega3_out) {
     if (!s || !s->initialized || n != s->P.N)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     int rc = 0;
     if (pos3_in || vel3_in || omega3_in)
         rc = dem_b200_set_state(s, pos3_in, vel3_in, omega3_in);
@@ -1409,7 +1439,7 @@ int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out) {
         return DEMB200_EINVAL;
     CU(cudaSetDevice(s->cfg.device));
     const unsigned N = s->P.N;
-    if (which < 0 || which > 6)
+    if (which < 0 || which > 7)
         return DEMB200_EINVAL;
     if (which == DEMB200_RED_NUM_CONTACTS && s->P.tang_mode != DEMB200_TANG_MULTISTEP) {
         s->err = "NUM_CONTACTS needs MultiStep history (or use recording)";
@@ -1439,6 +1469,10 @@ int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out) {
 int dem_b200_enable_recording(dem_b200_system* s, int enable, size_t max_pairs) {
     if (!s || !s->initialized)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     drop_graph(s);
     s->recording = enable != 0;
@@ -1465,6 +1499,10 @@ int dem_b200_enable_recording(dem_b200_system* s, int enable, size_t max_pairs) 
 int dem_b200_get_forces(dem_b200_system* s, double* force3, double* torque3) {
     if (!s || !s->initialized || !s->B.recF)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     const size_t bytes = 3 * (size_t)s->P.N * sizeof(double);
     if (force3) CU(cudaMemcpyAsync(force3, s->B.recF, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -1496,6 +1534,10 @@ int dem_b200_get_pairs(dem_b200_system* s, uint64_t* pairs, size_t capacity, siz
 int dem_b200_get_bins(dem_b200_system* s, int32_t* gmin3, int32_t* gmax3) {
     if (!s || !s->initialized || !s->B.gmin)
         return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "not available on a slab engine (ids are global, buffers local): use dem_b200_export_owned / dem_b200_import_owned";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     CU(cudaStreamSynchronize(s->stream));
     const size_t bytes = 3 * (size_t)s->P.N * sizeof(int32_t);
@@ -1760,6 +1802,7 @@ int dem_b200_mgpu_finish_rebuild(dem_b200_system* s) {
     s->P.N = s->mg_n_local;
     drop_graph(s);
     s->mg_phase = 0;
+    s->slab_rebuilds++;
     s->mg_remap_pending = true;
     s->export_valid = false;
     return recompute_bbox(s);
@@ -1984,8 +2027,9 @@ int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, doubl
     }
     const unsigned N = s->P.N;
     unsigned* d_sid = reinterpret_cast<unsigned*>(s->B.rank);  // scratch of the rebuild, free between steps
+    unsigned* d_slot = reinterpret_cast<unsigned*>(s->B.cell);  // likewise: storage slot of every exported record
     CU(cudaMemsetAsync(s->d_count, 0, sizeof(unsigned), s->stream));
-    k_export_owned<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, s->d_count, (unsigned)std::min<size_t>(capacity, N), d_sid,
+    k_export_owned<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, s->d_count, (unsigned)std::min<size_t>(capacity, N), d_sid, d_slot,
                                                             s->d_pos3, s->d_vel3, s->d_om3);
     CU(cudaGetLastError());
     s->export_valid = false;
@@ -1996,11 +2040,59 @@ int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, doubl
     *n = c;
     if (c > capacity)
         return DEMB200_ECAPACITY;
+    s->owned_export_n = c;
+    s->owned_export_step = s->step_no;
+    s->owned_export_seq = s->p2p_rebuild_seq + s->slab_rebuilds;
     CU(cudaMemcpyAsync(sid, d_sid, c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     if (pos3) CU(cudaMemcpyAsync(pos3, s->d_pos3, 3 * (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (vel3) CU(cudaMemcpyAsync(vel3, s->d_vel3, 3 * (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (omega3) CU(cudaMemcpyAsync(omega3, s->d_om3, 3 * (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     return check_device_error(s);
+}
+
+// The inverse of dem_b200_export_owned for the slab-mode host round trip: the n records of the LAST export (same order), with
+// possibly changed values, go back into the spheres they came from.  Only valid while nothing (step, rebuild) has happened
+// since that export.  New positions invalidate the candidate lists and the ghost copies held by the neighbours: the caller
+// runs the slab rebuild protocol before the next step (chrono_b200/slab.py: SlabDriver.import_owned).
+int dem_b200_import_owned(dem_b200_system* s, size_t n, const double* pos3, const double* vel3, const double* omega3) {
+    if (!s || !s->initialized)
+        return DEMB200_EINVAL;
+    if (n != s->owned_export_n || s->owned_export_step != s->step_no || s->owned_export_seq != s->p2p_rebuild_seq + s->slab_rebuilds) {
+        s->err = "import_owned: must directly follow dem_b200_export_owned (same records, same order, no step or rebuild in between)";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    const size_t bytes = 3 * n * sizeof(double);
+    if (pos3) CU(cudaMemcpyAsync(s->d_pos3, pos3, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (vel3) CU(cudaMemcpyAsync(s->d_vel3, vel3, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (omega3) CU(cudaMemcpyAsync(s->d_om3, omega3, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (n) {
+        k_import_owned<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->B, (unsigned)n, reinterpret_cast<unsigned*>(s->B.cell),
+                                                                          pos3 ? s->d_pos3 : nullptr, vel3 ? s->d_vel3 : nullptr,
+                                                                          omega3 ? s->d_om3 : nullptr);
+        CU(cudaGetLastError());
+    }
+    s->export_valid = false;
+    s->accel_src_valid = s->accel_export_valid = false;
+    if (pos3 && !s->mgpu) {
+        const unsigned one = 1;
+        CU(cudaMemcpyAsync(&s->B.ctrl->need_rebuild, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
+        int rc = recompute_bbox(s);
+        if (rc)
+            return rc;
+    }
+    CU(cudaStreamSynchronize(s->stream));  // the host buffers may be reused by the caller
+    return 0;
+}
+
+int dem_b200_clear_error(dem_b200_system* s) {
+    if (!s || !s->initialized)
+        return DEMB200_EINVAL;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemsetAsync(&s->B.ctrl->err, 0, sizeof(unsigned), s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->err.clear();
+    return 0;
 }
 
 }  // extern "C"

@@ -210,7 +210,9 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
 // steps that rebuild (no empty launches of N / 256-block grids in the other ~97 % of the steps).
 __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned long long cond) {
     __shared__ Ctrl sC;
+    __shared__ unsigned s_err_in;
     static_assert(sizeof(Ctrl) % 8 == 0, "Ctrl is copied in 8-byte words");
+    static_assert(offsetof(Ctrl, err) % 8 == 0 && offsetof(Ctrl, nsteps) == offsetof(Ctrl, err) + 8, "err owns its 8-byte word");
     if (blockIdx.x != 0)
         return;
     unsigned long long* g = reinterpret_cast<unsigned long long*>(B.ctrl);
@@ -220,13 +222,20 @@ __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned
         l[i] = g[i];
     __syncthreads();
     if (threadIdx.x == 0) {
+        s_err_in = sC.err;
         step_begin_body(P, B, sC);
         if (cond)
             cudaGraphSetConditional((cudaGraphConditionalHandle)cond, sC.rebuild_now);
     }
     __syncthreads();
+    // the word that holds `err` is not written back: error bits may be set concurrently by kernels of another stream (halo
+    // overlap), and a plain store of the staged copy would lose them.  New bits of this kernel are OR-ed in instead.
+    constexpr unsigned kErrWord = offsetof(Ctrl, err) / 8;
     for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x)
-        g[i] = l[i];
+        if (i != kErrWord)
+            g[i] = l[i];
+    if (threadIdx.x == 0 && sC.err != s_err_in)
+        atomicOr(&B.ctrl->err, sC.err);
 }
 
 __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C) {
@@ -2450,7 +2459,7 @@ __global__ void k_p2p_vote(Params P, Buffers B, P2PDev X) {
 
 // compact export of the owned spheres (any order): sid, pos, vel, omega
 __global__ void __launch_bounds__(256) k_export_owned(Params P, Buffers B, unsigned* count, unsigned cap, unsigned* sid,
-                                                      double* pos3, double* vel3, double* om3) {
+                                                      unsigned* slot_of, double* pos3, double* vel3, double* om3) {
     const Ctrl& C = *B.ctrl;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     bool own = false;
@@ -2466,9 +2475,31 @@ __global__ void __launch_bounds__(256) k_export_owned(Params P, Buffers B, unsig
     if (!own || at >= cap)
         return;
     sid[at] = r.sid;
+    slot_of[at] = i;  // where record `at` of this export lives: dem_b200_import_owned hands the same records back
     if (pos3) { pos3[3 * (size_t)at] = p.x; pos3[3 * (size_t)at + 1] = p.y; pos3[3 * (size_t)at + 2] = p.z; }
     if (vel3) { vel3[3 * (size_t)at] = r.v.x; vel3[3 * (size_t)at + 1] = r.v.y; vel3[3 * (size_t)at + 2] = r.v.z; }
     if (om3) { om3[3 * (size_t)at] = r.w.x; om3[3 * (size_t)at + 1] = r.w.y; om3[3 * (size_t)at + 2] = r.w.z; }
+}
+
+// the inverse: records in the order of the last export -> their storage slots (no step in between: the order is unchanged)
+__global__ void __launch_bounds__(256) k_import_owned(Buffers B, unsigned n, const unsigned* slot_of, const double* pos3,
+                                                      const double* vel3, const double* om3) {
+    Ctrl& C = *B.ctrl;
+    const unsigned at = blockIdx.x * blockDim.x + threadIdx.x;
+    if (at >= n)
+        return;
+    const unsigned i = slot_of[at];
+    if (pos3) {
+        double4 p = B.pos[C.cur][i];
+        p.x = pos3[3 * (size_t)at]; p.y = pos3[3 * (size_t)at + 1]; p.z = pos3[3 * (size_t)at + 2];
+        B.pos[C.cur][i] = p;
+    }
+    if (vel3 || om3) {
+        VelVal r = load_vel(B.vel[C.cur], i);
+        if (vel3) r.v = mk(vel3[3 * (size_t)at], vel3[3 * (size_t)at + 1], vel3[3 * (size_t)at + 2]);
+        if (om3) r.w = mk(om3[3 * (size_t)at], om3[3 * (size_t)at + 1], om3[3 * (size_t)at + 2]);
+        store_vel(B.vel[C.cur], i, r.v, r.w, r.sid, r.meta, r.amask);
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -2492,10 +2523,18 @@ __global__ void __launch_bounds__(256) k_reduce(Params P, Buffers B, int which, 
                     0.5 * I * (vel[3] * vel[3] + vel[4] * vel[4] + vel[5] * vel[5]);
                 break;
             }
+            case 7: {  // translational part only: what Chrono::Dem's GetParticlesKineticEnergy sums (ChSystemDem_impl.cpp:1250-1264)
+                double m = sphere_mass(P, p.w);
+                v = 0.5 * m * (vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+                break;
+            }
             case 3: ext = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]); break;
             case 4: v = (p.z > arg) ? 1.0 : 0.0; break;
             case 5: v = (p.x > arg) ? 1.0 : 0.0; break;
-            case 6: v = (double)(__popcll(B.vel[C.cur][i].amask) + __popc((B.vel[C.cur][i].meta >> 8) & 0xFFFFu)); break;  // live contacts
+            case 6:  // live contacts of the spheres this engine owns (a ghost's contacts are counted by its owner)
+                v = (B.vel[C.cur][i].meta & FLAG_GHOST) ? 0.0
+                    : (double)(__popcll(B.vel[C.cur][i].amask) + __popc((B.vel[C.cur][i].meta >> 8) & 0xFFFFu));
+                break;
         }
     }
 #pragma unroll

@@ -21,6 +21,7 @@
 // sid = stable sphere id (= user index); shape id = shape_base + sid (Multicore numbering).
 // =============================================================================
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 namespace demb200 {
@@ -148,7 +149,8 @@ struct Ctrl {
     unsigned rebuild_now;   // this step rebuilds the search grid and the candidate lists
     unsigned need_rebuild;  // request (host: initialize / set_state)
     unsigned init_stage;    // first rebuild takes the contact history from Buffers::stage_init (checkpoint restart)
-    unsigned err;
+    unsigned err;           // sticky device error bits; alone in its 8-byte word (k_step_begin never overwrites it)
+    unsigned err_pad_;
     unsigned long long nsteps, nrebuilds;
     unsigned long long bbox[6];   // order-preserving encoded doubles: min xyz, max xyz of the sphere AABBs
     unsigned long long max_dx2;   // raw bits of max |x_new - x_old|^2 over the spheres, last step

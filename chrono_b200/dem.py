@@ -15,7 +15,7 @@ ADH_CONSTANT, ADH_DMT, ADH_PERKO = 0, 1, 2
 TANG_NONE, TANG_ONESTEP, TANG_MULTISTEP = 0, 1, 2
 FORWARD_EULER, CHUNG, CENTERED_DIFFERENCE, EXTENDED_TAYLOR = 0, 1, 2, 3
 MAT_SPHERE, MAT_WALL, MAT_MESH = 0, 1, 2
-RED_MAX_Z, RED_MIN_Z, RED_KE, RED_MAX_SPEED, RED_COUNT_ABOVE_Z, RED_COUNT_ABOVE_X, RED_NUM_CONTACTS = range(7)
+RED_MAX_Z, RED_MIN_Z, RED_KE, RED_MAX_SPEED, RED_COUNT_ABOVE_Z, RED_COUNT_ABOVE_X, RED_NUM_CONTACTS, RED_KE_TRANSLATIONAL = range(8)
 
 
 class Material(C.Structure):

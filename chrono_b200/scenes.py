@@ -10,6 +10,41 @@ import math
 
 import numpy as np
 
+RHO = 2000.0
+MASS_COEF = 4.0 / 3.0 * np.pi * RHO
+
+
+def settling_material(mu=0.4, cr=0.4, young=2e6, mu_roll=0.0, mu_spin=0.0, adhesion=0.0):
+    """btest_MCORE_settling.cpp:80-92"""
+    return dict(young=young, poisson=0.3, mu_s=mu, mu_roll=mu_roll, mu_spin=mu_spin, cr=cr, adhesion=adhesion)
+
+
+def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
+             integrator=None, history_slots=16, device=0, stream=None, **model):
+    """The scene in the CUDA engine, through its C ABI (chrono_b200/dem.py).  No CPU path: raises when the library is missing.
+    stream: raw cudaStream_t handle the engine runs on instead of its own stream (so that the caller's events time it)."""
+    from . import dem
+    mat = mat or settling_material()
+    cfg = dem.config(device=device, dt=dt, bins=scene["bins"], gravity=gravity, mat_sphere=dem.material(**mat),
+                     mat_wall=dem.material(**(wall_mat or mat)), mat_mesh=dem.material(**(mesh_mat or mat)),
+                     mass_coef=MASS_COEF, wall_mass=wall_mass,
+                     integrator=dem.CENTERED_DIFFERENCE if integrator is None else integrator,
+                     history_slots=history_slots, **model)
+    g = dem.DemSystem(cfg)
+    if stream is not None:
+        import ctypes
+        g._ck(g.L.dem_b200_set_stream(g.h, ctypes.c_void_p(stream)))
+    for p, h in scene["walls"]:
+        g.add_box_wall(p, h)
+    for c, rb in scene.get("balls", []):
+        g.add_sphere_wall(c, rb, spheres_outside=True)
+    for M in scene.get("meshes", []):
+        m = g.add_mesh(M["tri"], M.get("mass", 1.0))
+        g.set_mesh_motion(m, M.get("pos"), M.get("rot"), M.get("vel"), M.get("omega"))
+    g.set_spheres(scene["pos"], scene["radius"], vel=vel, omega=omega, fixed=scene.get("fixed"))
+    g.initialize()
+    return g
+
 
 def hcp_points(lo, hi, sep):
     """HCP lattice points p with lo <= p <= hi (ChHCPSampler, box volume).  Returned in the reference's
@@ -175,3 +210,112 @@ def cylinder_drum_mesh(radius, length, n_seg, axis=1, caps=True, n_ax=1):
         tri = tri[:, :, perm]
         tri = tri[:, [0, 2, 1], :]  # a coordinate swap mirrors the winding
     return np.ascontiguousarray(tri.reshape(-1, 9))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# large scenes generated per slab (BASELINE configs[4]): no rank ever holds the whole packing
+# ---------------------------------------------------------------------------------------------------------------------
+def _hash_uniform(gid, stream):
+    """Counter-based uniform numbers in [-1, 1): splitmix64 of (sphere id, stream).  The jitter of a sphere depends on its
+    global id only, so every partition of the lattice generates bit-identical spheres."""
+    z = gid.astype(np.uint64) * np.uint64(4) + np.uint64(stream) + np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
+
+def slab_lattice_scene(n_total, world=1, rank=0, radius=0.02, jitter=0.005, sep_factor=2.0, polydisperse=None,
+                       wall_thickness=0.2, bin_factor=2.0, headroom=1.25, cross_section_of=None):
+    """The settling_scene packing for `world` slabs along x, of which only slab `rank` is generated.
+
+    The box is `world` times as long (x) as the box of an n_total / world packing is wide, same width (y) and bed depth,
+    made of complete HCP layers (so the sphere count is n_actual ~ n_total, returned).  Slab faces lie between lattice
+    columns; global id = lattice index in generation order (z layers, y rows, x).  Returns dict(pos, radius, ids, lo, hi,
+    n_total, box_size, walls, bins) with pos / radius / ids of slab `rank` only."""
+    sep = sep_factor * radius * (1.2 if polydisperse else 1.0)
+    rmax = radius * (polydisperse[1] if polydisperse else 1.0)
+    site = sep ** 3 / math.sqrt(2.0)
+    n_one = cross_section_of or max(1, n_total // world)
+    L = (n_one * site / 0.26) ** (1.0 / 3.0)
+    dx, dy, dz = sep, sep * (math.sqrt(3.0) / 2), sep * math.sqrt(2.0 / 3.0)
+    nx1 = max(1, int((L - 2.02 * rmax) / dx))          # lattice columns per slab (the half-offset rows need dx / 2 more)
+    nx = nx1 * world
+    ny = max(1, int((L - 2.02 * rmax) / dy))
+    nz = max(1, int(round(n_total / float(nx * ny))))
+    Lx, Ly = nx * dx + dx / 2 + 2.02 * rmax, L
+    x0, y0, z0 = -Lx / 2 + 1.01 * rmax, -Ly / 2 + 1.01 * rmax, 1.01 * rmax
+    i0, i1 = rank * nx1, (rank + 1) * nx1
+    k = np.arange(nz, dtype=np.int64)[:, None, None]
+    j = np.arange(ny, dtype=np.int64)[None, :, None]
+    i = np.arange(i0, i1, dtype=np.int64)[None, None, :]
+    gid = ((k * ny + j) * nx + i).reshape(-1)
+    offy = np.where(k % 2 == 0, 0.0, dy / 3)
+    offx = np.where((j + k) % 2 == 0, 0.0, dx / 2)
+    shape = (nz, ny, i1 - i0)
+    pos = np.empty((gid.size, 3))
+    pos[:, 0] = np.broadcast_to(x0 + offx + i * dx, shape).reshape(-1)
+    pos[:, 1] = np.broadcast_to(y0 + offy + j * dy + 0.0 * i, shape).reshape(-1)
+    pos[:, 2] = np.broadcast_to(z0 + k * dz + 0.0 * j + 0.0 * i, shape).reshape(-1)
+    for c in range(3):
+        pos[:, c] += (jitter * radius) * _hash_uniform(gid, c)
+    if polydisperse:
+        u = 0.5 * (_hash_uniform(gid, 3) + 1.0)
+        rad = radius * (polydisperse[0] + (polydisperse[1] - polydisperse[0]) * u)
+    else:
+        rad = np.full(gid.size, radius)
+    ztop = z0 + (nz - 1) * dz + jitter * radius
+    Lz = max(ztop + 2 * rmax, 0.25 * Ly) * headroom
+    size = np.array([Lx, Ly, Lz])
+    walls = box_container(size, wall_thickness, center=(0.0, 0.0, Lz / 2), faces=(2, 2, -1))
+    wmin = np.min([p - h for p, h in walls], axis=0)
+    wmax = np.max([p + h for p, h in walls], axis=0)
+    bins = np.maximum(1, np.floor((wmax - wmin) * 1.002 / (bin_factor * rmax * 1.0001)).astype(np.int64))
+    # slab faces half-way between the last column of one slab and the first of the next (both row offsets considered)
+    face = lambda c: x0 + c * dx - dx / 4
+    lo = -np.inf if rank == 0 else face(i0)
+    hi = np.inf if rank == world - 1 else face(i1)
+    return dict(pos=pos, radius=rad, ids=gid.astype(np.uint32), lo=lo, hi=hi, n_total=int(nx) * int(ny) * int(nz), n=int(gid.size),
+                box_size=size, walls=walls, bins=tuple(int(b) for b in bins), rmax=float(rmax))
+
+
+def drum_scene(n_target, radius=0.02, seed=7, fill=0.35, facet_edge=4.0, jitter=0.005, sep_factor=2.0, aspect=4.0):
+    """BASELINE configs[3]: spheres resting in the lower part of a closed drum (triangle mesh, axis x) that rotates about
+    its axis.  The drum is long (length = aspect * diameter) so that slabs ALONG THE AXIS (x, the slab direction of the
+    engine) each own a stretch of drum wall; facets are about facet_edge sphere radii wide.
+    Returns a scene dict whose `meshes[0]` is the drum; the spheres start on an HCP lattice clipped to the drum interior
+    below the fill level, a hair above the wall, so that they are on the wall within a few hundred steps."""
+    rng = np.random.default_rng(seed)
+    sep = sep_factor * radius
+    site = sep ** 3 / math.sqrt(2.0)
+    # filled segment area fraction of a circle at relative fill height f (of the diameter)
+    th = 2 * math.acos(1 - 2 * fill)
+    seg_frac = (th - math.sin(th)) / (2 * math.pi)
+    # volume needed -> drum radius: n * site = seg_frac * pi Rd^2 * (aspect * 2 Rd)
+    Rd = (n_target * site / (seg_frac * math.pi * 2 * aspect)) ** (1.0 / 3.0) * 1.02
+    for _ in range(40):
+        Ld = 2 * aspect * Rd
+        lo = np.array([-Rd, -Ld / 2 + 1.2 * radius, -Rd])
+        hi = np.array([Rd, Ld / 2 - 1.2 * radius, -Rd + 2 * Rd * fill])
+        pts = hcp_points(lo, hi, sep)
+        rr = np.sqrt(pts[:, 0] ** 2 + pts[:, 2] ** 2)
+        pts = pts[rr < Rd - 1.3 * radius]
+        if len(pts) >= n_target:
+            break
+        Rd *= 1.02
+    else:
+        raise ValueError("drum_scene: could not place %d spheres" % n_target)
+    pts = pts[np.argsort(pts[:, 2], kind="stable")][:n_target]  # the lowest sites: a bed with a level surface
+    pts = pts + rng.uniform(-jitter * radius, jitter * radius, size=pts.shape)
+    n_seg = max(24, int(2 * math.pi * Rd / (facet_edge * radius)))
+    n_ax = max(1, int(round(Ld / (facet_edge * radius))))
+    tri = cylinder_drum_mesh(Rd, Ld, n_seg, axis=0, caps=False, n_ax=n_ax)  # the end caps are two box walls (fan facets would be metres long)
+    pts = np.ascontiguousarray(pts[:, [1, 0, 2]])  # the lattice was laid out along y: turn the drum axis to x
+    ext = np.array([Ld, 2 * Rd, 2 * Rd]) * 1.05
+    bins = np.maximum(1, np.floor(ext / (2.0 * radius * 1.0001)).astype(np.int64))
+    mesh = dict(tri=tri, pos=np.zeros(3), rot=np.array([1.0, 0, 0, 0]), vel=np.zeros(3), omega=np.zeros(3), mass=1000.0)
+    t = 0.2
+    walls = [(np.array([s_ * (Ld / 2 + t / 2), 0.0, 0.0]), np.array([t / 2, 1.05 * Rd, 1.05 * Rd])) for s_ in (-1.0, 1.0)]
+    return dict(pos=np.ascontiguousarray(pts), radius=np.full(n_target, radius), walls=walls, bins=tuple(int(b) for b in bins),
+                n=n_target, meshes=[mesh], drum_radius=Rd, drum_length=Ld, box_size=ext)

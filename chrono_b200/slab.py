@@ -186,6 +186,15 @@ class SlabDriver:
                     self._pending.clear()
                     self.rebuild()
 
+    def import_owned(self, pos=None, vel=None, omega=None):
+        """Host round trip of a slab engine: the records of the last export_owned() go back (same order), then the slab
+        is rebuilt (new positions invalidate the candidate lists and the neighbours' ghost copies).  Every rank calls it."""
+        self.b.import_owned(pos, vel, omega)
+        self._pending.clear()
+        self.rebuild()
+        if getattr(self, "p2p", False):
+            self.ignore_upto = self.b.step_count()
+
     def drain(self):
         """Act on the answers still in flight (call before reading results / at the end of a timed region)."""
         if getattr(self, "p2p", False):
@@ -309,6 +318,12 @@ class EngineBackend:
             return int(h[0])
         return wait
 
+    def import_owned(self, pos, vel, omega):
+        a = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None for x in (pos, vel, omega)]
+        n = next(len(x) for x in a if x is not None)
+        dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double)) if x is not None else None
+        self.g._ck(self.L.dem_b200_import_owned(self.h, C.c_size_t(n), dp(a[0]), dp(a[1]), dp(a[2])))
+
     def export_owned(self):
         cap = self.capacity
         sid = np.empty(cap, dtype=np.uint32)
@@ -319,6 +334,55 @@ class EngineBackend:
                                                 C.c_size_t(cap), C.byref(n)))
         k = n.value
         return sid[:k], pos[:k], vel[:k], om[:k]
+
+
+def slab_parity_check(rank, world, local, n=200000, steps=300, p2p=True, seed=77):
+    """A slab run of `n` spheres over `world` ranks against the same job on ONE GPU (every rank runs the whole scene on its
+    own device with the plain engine): positions, velocities and angular velocities of the owned spheres must be bit-identical
+    and the number of force-carrying contacts equal.  The spheres drift across the slab faces, so migration (with contact
+    history) and several list rebuilds are part of it.  Collective: every rank calls it; returns the same dict everywhere."""
+    from . import dem, scenes
+    scene = scenes.settling_scene(n, sep_factor=1.99, seed=seed)
+    rng = np.random.default_rng(5)
+    vel = rng.normal(size=(n, 3)) * 0.1
+    vel[:, 0] += np.where(scene["pos"][:, 0] < 0, 0.6, -0.6)  # both halves drift towards (and across) the middle
+    om = rng.normal(size=(n, 3)) * 2.0
+    kw = dict(dt=1e-4, force_model=dem.HERTZ, tangential_mode=dem.TANG_MULTISTEP)
+    ref = scenes.make_gpu(scene, vel=vel, omega=om, device=local, **kw)
+    ref.step(steps)
+    rp, rv, rw = ref.state()
+    contacts_ref = ref.reduce(dem.RED_NUM_CONTACTS)
+    ref.close()
+    x = scene["pos"][:, 0]
+    bounds = slab_bounds(x, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    mine = np.nonzero((x >= lo) & (x < hi))[0]
+    mat = scenes.settling_material()
+    cfg = dem.config(device=local, bins=scene["bins"], mat_sphere=dem.material(**mat), mat_wall=dem.material(**mat),
+                     mass_coef=scenes.MASS_COEF, wall_mass=1.0, integrator=dem.CENTERED_DIFFERENCE, history_slots=16, **kw)
+    g, backend = make_engine_slab(cfg, scene["walls"], scene["pos"][mine], scene["radius"][mine], mine, vel=vel[mine],
+                                  omega=om[mine], capacity=int(1.6 * len(mine)) + 4096, rmax_global=float(scene["radius"].max()))
+    drv = SlabDriver(backend, rank, world, lo, hi, lag=0)
+    drv.rebuild()
+    if p2p:
+        drv.enable_p2p(lag=2)
+    drv.step(steps)
+    drv.drain()
+    g.sync()
+    sid, p, v, w = backend.export_owned()
+    ok = bool(np.array_equal(p, rp[sid]) and np.array_equal(v, rv[sid]) and np.array_equal(w, rw[sid]))
+    worst = float(np.abs(p - rp[sid]).max()) if len(sid) else 0.0
+    t = torch.tensor([len(sid), int(ok), drv.stats["migrated"], g.reduce(dem.RED_NUM_CONTACTS), worst], dtype=torch.float64,
+                     device=backend.device)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    g.close()
+    tot = int(sum(float(a[0]) for a in allt))
+    contacts = int(sum(float(a[3]) for a in allt))
+    return dict(bit_identical=bool(all(int(a[1]) == 1 for a in allt)) and tot == n, worst_dp=max(float(a[4]) for a in allt),
+                spheres=n, timesteps=steps, owned_total=tot, migrated=int(sum(float(a[2]) for a in allt)),
+                rebuilds=int(drv.stats["rebuilds"]), contacts_slabs=contacts, contacts_single_gpu=int(contacts_ref),
+                contacts_equal=contacts == int(contacts_ref), transport="p2p" if p2p else "nccl")
 
 
 def make_engine_slab(cfg, scene_walls, pos, radius, ids, vel=None, omega=None, capacity=None, rmax_global=None, add_walls=None,

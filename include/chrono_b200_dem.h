@@ -176,7 +176,9 @@ double dem_b200_time(const dem_b200_system* s);
 /* ---- reductions -- GetMaxParticleZ, GetParticlesKineticEnergy, ... (ChSystemDem.h:246-262) ------------------ */
 enum { DEMB200_RED_MAX_Z = 0, DEMB200_RED_MIN_Z = 1, DEMB200_RED_KE = 2, DEMB200_RED_MAX_SPEED = 3,
        DEMB200_RED_COUNT_ABOVE_Z = 4, DEMB200_RED_COUNT_ABOVE_X = 5,
-       DEMB200_RED_NUM_CONTACTS = 6 /* sum over spheres of their force-carrying contacts (MultiStep only) */ };
+       DEMB200_RED_NUM_CONTACTS = 6, /* sum over the owned spheres of their force-carrying contacts (MultiStep only) */
+       DEMB200_RED_KE_TRANSLATIONAL = 7 /* sum of m v^2 / 2 only: what Chrono::Dem's GetParticlesKineticEnergy returns
+                                           (ChSystemDem_impl.cpp:1250-1264); DEMB200_RED_KE adds the rotational part */ };
 int dem_b200_reduce(dem_b200_system* s, int which, double arg, double* out);
 
 /* ---- parity / inspection (tests, smoke) ---------------------------------------------------------------------- */
@@ -246,6 +248,15 @@ unsigned long long dem_b200_step_count(const dem_b200_system* s); /* time steps 
 /* owned spheres (ghosts excluded) in arbitrary order: global id, pos, vel, omega to HOST buffers */
 int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, double* vel3, double* omega3, size_t capacity,
                           size_t* n);
+
+/* The inverse, for the host round trip of a slab engine (bench.py e2e at N > 1): the n records of the LAST
+ * dem_b200_export_owned, same order, values possibly changed by the caller, go back into their spheres.  Must directly
+ * follow that export (no step, no rebuild in between).  With new positions the candidate lists and the neighbours' ghost
+ * copies are stale: run the slab rebuild protocol before the next step. */
+int dem_b200_import_owned(dem_b200_system* s, size_t n, const double* pos3, const double* vel3, const double* omega3);
+/* Device error bits (history / neighbour overflow, skin exceeded, NaN ...) are sticky: every later sync point reports them.
+ * Once the cause is dealt with (set_config with more slots, set_state ...) this clears them. */
+int dem_b200_clear_error(dem_b200_system* s);
 
 #ifdef __cplusplus
 }

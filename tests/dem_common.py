@@ -3,19 +3,13 @@ import numpy as np
 
 from oracle import pyoracle as po
 
-RHO = 2000.0
-MASS_COEF = 4.0 / 3.0 * np.pi * RHO
+from chrono_b200.scenes import MASS_COEF, RHO, settling_material  # noqa: F401
 
 
 def sphere_mass(radius, mass_coef=MASS_COEF):
     """Same expression (and rounding sequence) as sphere_mass() in chrono_b200/csrc/dem_kernels.cuh."""
     r = np.asarray(radius, dtype=np.float64)
     return mass_coef * (r * r * r)
-
-
-def settling_material(mu=0.4, cr=0.4, young=2e6, mu_roll=0.0, mu_spin=0.0, adhesion=0.0):
-    """btest_MCORE_settling.cpp:80-92"""
-    return dict(young=young, poisson=0.3, mu_s=mu, mu_roll=mu_roll, mu_spin=mu_spin, cr=cr, adhesion=adhesion)
 
 
 def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
@@ -58,27 +52,7 @@ def make_oracle(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mas
     return o
 
 
-def make_gpu(scene, dt=1e-3, mat=None, wall_mat=None, mesh_mat=None, wall_mass=1.0, vel=None, omega=None, gravity=(0, 0, -9.81),
-             integrator=None, history_slots=16, device=0, **model):
-    from chrono_b200 import dem
-    mat = mat or settling_material()
-    kw = dict(model)
-    cfg = dem.config(device=device, dt=dt, bins=scene["bins"], gravity=gravity, mat_sphere=dem.material(**mat),
-                     mat_wall=dem.material(**(wall_mat or mat)), mat_mesh=dem.material(**(mesh_mat or mat)),
-                     mass_coef=MASS_COEF, wall_mass=wall_mass,
-                     integrator=dem.CENTERED_DIFFERENCE if integrator is None else integrator,
-                     history_slots=history_slots, **kw)
-    g = dem.DemSystem(cfg)
-    for p, h in scene["walls"]:
-        g.add_box_wall(p, h)
-    for c, rb in scene.get("balls", []):
-        g.add_sphere_wall(c, rb, spheres_outside=True)
-    for M in scene.get("meshes", []):
-        m = g.add_mesh(M["tri"], M.get("mass", 1.0))
-        g.set_mesh_motion(m, M.get("pos"), M.get("rot"), M.get("vel"), M.get("omega"))
-    g.set_spheres(scene["pos"], scene["radius"], vel=vel, omega=omega, fixed=scene.get("fixed"))
-    g.initialize()
-    return g
+from chrono_b200.scenes import make_gpu  # noqa: E402,F401  (the engine-side builder lives with the product; re-exported for the tests)
 
 
 def oracle_sphere_state(o):
