@@ -47,6 +47,7 @@ CONFIG_NAMES = {
 DEFAULT_SPHERES_TOTAL = {0: 10000, 1: 1000000, 2: 4000000, 3: 8000000}
 WEAK_PER_GPU = 32000000
 STRONG_TOTAL = 64000000
+BED_LAYERS = 44  # HCP layers of the 1 M-sphere bed of configs[1] (0.26 x as deep as wide); larger beds are wider, not deeper
 
 
 def peaks():
@@ -130,15 +131,16 @@ def build_scene(cfg_id, n):
         return scenes.settling_scene(n, radius=RADIUS, sep_factor=1.75, jitter=0.005, seed=12345 + 2, polydisperse=(0.8, 1.2))
     if cfg_id == 3:
         return scenes.drum_scene(n, radius=RADIUS)
-    if cfg_id == 4:
-        sc = scenes.slab_lattice_scene(n, world=1, rank=0, radius=RADIUS)
-        sc["n"] = sc["n_total"]
-        return sc
-    return scenes.settling_scene(n, radius=RADIUS, sep_factor=2.0, jitter=0.005, seed=12345 + 1)
+    if cfg_id == 0:
+        return scenes.settling_scene(n, radius=RADIUS, sep_factor=2.0, jitter=0.005, seed=12345 + 1)
+    # configs[1] / [4]: HCP bed of BED_LAYERS layers in static equilibrium under its own weight (it starts at rest)
+    sc = scenes.slab_lattice_scene(n, world=1, rank=0, radius=RADIUS, layers=BED_LAYERS if n >= 200000 else None, precompress=True)
+    sc["n"] = sc["n_total"]
+    return sc
 
 
 def workload_config(cfg_id, n_per_gpu, n_total, substeps, gpus, settle, extra=None):
-    d = {"workload": "%s -- %d spheres%s, jittered HCP packing at 2R spacing, settled %d time steps before the timed region; "
+    d = {"workload": "%s -- %d spheres%s, jittered HCP bed (2R in-plane spacing, layer heights in static equilibrium under gravity), settled %d time steps before the timed region; "
                      "R=0.02 rho=2000 Y=2e6 mu=0.4 cr=0.4 h=1e-4" % (CONFIG_NAMES[cfg_id], n_total,
                                                                      (" (%d per GPU)" % n_per_gpu) if gpus > 1 else "", settle),
          "config_id": cfg_id, "spheres_total": n_total, "spheres_per_gpu": n_per_gpu, "timesteps_per_step": substeps,
@@ -522,7 +524,7 @@ def slab_scene(cfg_id, n_total, world, rank):
     """(local pos, radius, ids, lo, hi, global scene dict) of rank's slab."""
     from chrono_b200 import scenes, slab
     if cfg_id in (1, 4):
-        sc = scenes.slab_lattice_scene(n_total, world=world, rank=rank, radius=RADIUS)
+        sc = scenes.slab_lattice_scene(n_total, world=world, rank=rank, radius=RADIUS, layers=BED_LAYERS, precompress=True)
         return sc["pos"], sc["radius"], sc["ids"], sc["lo"], sc["hi"], sc
     if cfg_id == 2:
         sc = scenes.slab_lattice_scene(n_total, world=world, rank=rank, radius=RADIUS, sep_factor=1.75, polydisperse=(0.8, 1.2))

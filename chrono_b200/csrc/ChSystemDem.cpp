@@ -37,6 +37,8 @@ struct BCInfo {
     double slope = 0, hmin = 0, hmax = 0;  // cone
     double vel[3] = {0, 0, 0};     // ball velocity (SetBCSphereVelocity)
     double mass = 0;               // ball: > 0 -> the ball is a free body driven by the spheres' reaction force and gravity
+    double rot_center[3] = {0, 0, 0}, rot_omega[3] = {0, 0, 0};  // plane: SetBCPlaneRotation
+    bool has_rotation = false;
     bool spheres_inside = true;
     bool track_forces = false;
     bool enabled = true;
@@ -271,7 +273,11 @@ void ChSystemDem::SetPsiFactors(unsigned int psi_T, unsigned int psi_L, float ps
 void ChSystemDem::SetPsiT(unsigned int psi_T) { m_sys->psi_T = psi_T; }
 void ChSystemDem::SetPsiL(unsigned int psi_L) { m_sys->psi_L = psi_L; }
 void ChSystemDem::SetPsiR(float psi_R) { m_sys->psi_R = psi_R; }
-void ChSystemDem::SetRecordingContactInfo(bool record) { m_sys->record_contacts = record; }
+void ChSystemDem::SetRecordingContactInfo(bool record) {
+    m_sys->record_contacts = record;
+    if (m_sys->initialized && m_sys->friction == CHDEM_FRICTION_MODE::MULTI_STEP)
+        m_sys->check(dem_b200_enable_contact_info(m_sys->h, record ? 1 : 0), "SetRecordingContactInfo");
+}
 void ChSystemDem::SetSimTime(float time) { m_sys->elapsed = time; }
 void ChSystemDem::SetVerbosity(CHDEM_VERBOSITY level) { m_sys->verbosity = level; }
 void ChSystemDem::SetParticleDensity(float density) { m_sys->density = density; }
@@ -368,8 +374,18 @@ ChVector3f ChSystemDem::GetBCSphereVelocity(size_t id) const {
     const BCInfo& bc = m_sys->bcs[id];
     return ChVector3f((float)bc.vel[0], (float)bc.vel[1], (float)bc.vel[2]);
 }
-// Declared by the reference, not provided by this engine (never called in-tree outside src/chrono_dem): fail loudly.
-void ChSystemDem::SetBCPlaneRotation(size_t, ChVector3d, ChVector3d) { fail("SetBCPlaneRotation is not supported"); }
+// Surface spin of a plane boundary (ChSystemDem_impl.cpp:993-1001; used by the force at ChDemBoundaryConditions.cuh:394): the
+// plane's material point at a contact moves with omega x (x - center); the plane itself stays where it is.
+void ChSystemDem::SetBCPlaneRotation(size_t plane_id, ChVector3d center, ChVector3d omega) {
+    ChSystemDem_impl& S = *m_sys;
+    if (plane_id >= S.bcs.size() || S.bcs[plane_id].kind != BCKind::PLANE)
+        fail("SetBCPlaneRotation: not a plane boundary");
+    BCInfo& bc = S.bcs[plane_id];
+    for (int k = 0; k < 3; k++) { bc.rot_center[k] = center[k]; bc.rot_omega[k] = omega[k]; }
+    bc.has_rotation = true;
+    if (S.initialized)
+        S.check(dem_b200_set_wall_rotation(S.h, bc.wall, bc.rot_center, bc.rot_omega), "SetBCPlaneRotation");
+}
 // acceleration of the last step, gravity included (the reference returns its sphere_acc array: ChSystemDem_impl.cpp:1290-1296)
 ChVector3f ChSystemDem::GetParticleLinAcc(int i) const {
     const ChSystemDem_impl& S = *m_sys;
@@ -379,12 +395,97 @@ ChVector3f ChSystemDem::GetParticleLinAcc(int i) const {
     S.check(dem_b200_get_sphere_accel(S.h, (size_t)i, a), "GetParticleLinAcc");
     return ChVector3f((float)a[0], (float)a[1], (float)a[2]);
 }
-void ChSystemDem::WriteContactInfoFile(const std::string&) const { fail("WriteContactInfoFile / SetRecordingContactInfo are not supported"); }
-ChVector3f ChSystemDem::getRollingFrictionTorque(unsigned int, unsigned int) { fail("getRollingFrictionTorque is not supported"); }
-ChVector3f ChSystemDem::getSlidingFrictionForce(unsigned int, unsigned int) { fail("getSlidingFrictionForce is not supported"); }
-ChVector3f ChSystemDem::getNormalForce(unsigned int, unsigned int) { fail("getNormalForce is not supported"); }
-ChVector3f ChSystemDem::getRollingVrot(unsigned int, unsigned int) { fail("getRollingVrot is not supported"); }
-float ChSystemDem::getRollingCharContactTime(unsigned int, unsigned int) { fail("getRollingCharContactTime is not supported"); }
+// ---- per-contact records (ChSystemDem_impl.cpp:443-635).  The engine keeps them per contact of the MULTI_STEP contact map;
+// like the reference, asking without SetRecordingContactInfo(true) is an error.
+namespace {
+// info13 of the contact between sphere i and label j (a sphere index, or nSpheres + BC_id + 1: ChDemBoundaryConditions.cuh:102);
+// the record is the one of sphere i (for two spheres the partner's is its mirror image)
+bool contact_info(const ChSystemDem_impl& S, unsigned int i, unsigned int j, double out[13], const char* what) {
+    if (!S.initialized || !S.record_contacts)
+        fail(std::string(what) + ": recording_contactInfo set to false (call SetRecordingContactInfo(true))");
+    if (S.friction != CHDEM_FRICTION_MODE::MULTI_STEP)
+        fail(std::string(what) + ": per-contact records need MULTI_STEP friction");
+    const size_t n = S.n();
+    if (i >= n && j < n)
+        std::swap(i, j);  // sphere-wall: the record sits with the sphere (ChSystemDem_impl.cpp:557-561)
+    if (i >= n)
+        return false;
+    uint32_t other;
+    if (j < n) {
+        other = (uint32_t)(S.bcs.size() + S.num_triangles() + j);
+    } else {
+        const size_t bc = (size_t)j - n - 1;
+        if (bc >= S.bcs.size() || S.bcs[bc].wall < 0)
+            return false;
+        other = (uint32_t)S.bcs[bc].wall;
+    }
+    int found = 0;
+    S.check(dem_b200_get_contact_info(S.h, i, other, out, &found), what);
+    return found != 0;
+}
+ChVector3f vec3f(const double* p) { return ChVector3f((float)p[0], (float)p[1], (float)p[2]); }
+}  // namespace
+
+ChVector3f ChSystemDem::getNormalForce(unsigned int i, unsigned int j) {
+    double c[13];
+    return contact_info(*m_sys, i, j, c, "getNormalForce") ? vec3f(c) : ChVector3f(0, 0, 0);
+}
+ChVector3f ChSystemDem::getSlidingFrictionForce(unsigned int i, unsigned int j) {
+    double c[13];
+    return contact_info(*m_sys, i, j, c, "getSlidingFrictionForce") ? vec3f(c + 3) : ChVector3f(0, 0, 0);
+}
+ChVector3f ChSystemDem::getRollingFrictionTorque(unsigned int i, unsigned int j) {
+    double c[13];
+    if (m_sys->rolling == CHDEM_ROLLING_MODE::NO_RESISTANCE)
+        return ChVector3f(0, 0, 0);  // ChSystemDem_impl.cpp:449-451
+    return contact_info(*m_sys, i, j, c, "getRollingFrictionTorque") ? vec3f(c + 6) : ChVector3f(0, 0, 0);
+}
+ChVector3f ChSystemDem::getRollingVrot(unsigned int i, unsigned int j) {
+    double c[13];
+    if (m_sys->rolling == CHDEM_ROLLING_MODE::NO_RESISTANCE)
+        return ChVector3f(0, 0, 0);
+    return contact_info(*m_sys, i, j, c, "getRollingVrot") ? vec3f(c + 9) : ChVector3f(0, 0, 0);
+}
+float ChSystemDem::getRollingCharContactTime(unsigned int i, unsigned int j) {
+    double c[13];
+    if (m_sys->rolling == CHDEM_ROLLING_MODE::NO_RESISTANCE)
+        return 0.f;
+    return contact_info(*m_sys, i, j, c, "getRollingCharContactTime") ? (float)c[12] : 0.f;
+}
+
+// "bi, bj, n_mag[, fx, fy, fz][, mx, my, mz]", one row per sphere-sphere contact with bi < bj (ChSystemDem_impl.cpp:588-635)
+void ChSystemDem::WriteContactInfoFile(const std::string& outfilename) const {
+    const ChSystemDem_impl& S = *m_sys;
+    if (!S.initialized || !S.record_contacts || S.friction == CHDEM_FRICTION_MODE::FRICTIONLESS)
+        fail("WriteContactInfoFile: you did not enable contact info recording or are using the frictionless model");
+    if (S.friction != CHDEM_FRICTION_MODE::MULTI_STEP)
+        fail("WriteContactInfoFile: per-contact records need MULTI_STEP friction");
+    size_t cnt = 0;
+    S.check(dem_b200_get_contact_infos(S.h, nullptr, nullptr, nullptr, 0, &cnt), "WriteContactInfoFile");
+    std::vector<uint32_t> bi(cnt + 1), bj(cnt + 1);
+    std::vector<double> info((cnt + 1) * 13);
+    if (cnt)
+        S.check(dem_b200_get_contact_infos(S.h, bi.data(), bj.data(), info.data(), cnt, &cnt), "WriteContactInfoFile");
+    std::vector<size_t> order(cnt);
+    for (size_t k = 0; k < cnt; k++) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return bi[a] != bi[b] ? bi[a] < bi[b] : bj[a] < bj[b]; });
+    const bool roll = S.rolling != CHDEM_ROLLING_MODE::NO_RESISTANCE;
+    std::ostringstream o;
+    o << "bi, bj, n_mag, fx, fy, fz";
+    if (roll)
+        o << ", mx, my, mz";
+    o << "\n";
+    for (size_t r = 0; r < cnt; r++) {
+        const size_t k = order[r];
+        const double* c = &info[13 * k];
+        o << bi[k] << ", " << bj[k] << ", " << std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) << ", " << c[3] << ", " << c[4] << ", " << c[5];
+        if (roll)
+            o << ", " << c[6] << ", " << c[7] << ", " << c[8];
+        o << "\n";
+    }
+    std::ofstream f(outfilename, std::ios::out);
+    f << o.str();
+}
 bool ChSystemDem::DisableBCbyID(size_t id) {
     if (id >= m_sys->bcs.size()) return false;
     m_sys->bcs[id].enabled = false;
@@ -447,7 +548,11 @@ void ChSystemDem::Initialize() {
             bc.wall = dem_b200_add_zcone_wall(S.h, bc.pos, bc.slope, bc.hmin, bc.hmax, bc.spheres_inside ? 1 : 0);
         else
             bc.wall = dem_b200_add_zcylinder_wall(S.h, bc.pos, bc.radius, bc.spheres_inside ? 1 : 0);
-        S.check(bc.wall, "CreateBC");
+        if (bc.wall < 0)
+            fail(std::string("CreateBC: ") + dem_b200_last_error(S.h) +
+                 " (the engine holds at most 16 boundary conditions, the six reserved box planes included)");
+        if (bc.has_rotation)
+            S.check(dem_b200_set_wall_rotation(S.h, bc.wall, bc.rot_center, bc.rot_omega), "SetBCPlaneRotation");
         if (!bc.enabled)
             S.check(dem_b200_enable_wall(S.h, bc.wall, 0), "DisableBCbyID");
         track |= bc.track_forces;
@@ -488,6 +593,8 @@ void ChSystemDem::Initialize() {
     }
     S.check(dem_b200_initialize(S.h), "Initialize");
     S.initialized = true;
+    if (S.record_contacts && S.friction == CHDEM_FRICTION_MODE::MULTI_STEP)
+        S.check(dem_b200_enable_contact_info(S.h, 1), "SetRecordingContactInfo");
     if (S.verbosity != CHDEM_VERBOSITY::QUIET)
         printf("ChSystemDem (B200 engine): %zu spheres, %zu boundary conditions, h = %g\n", n, S.bcs.size(), (double)S.step);
 }
@@ -806,13 +913,23 @@ void ChSystemDem::WriteHstHistory(std::ofstream& hf) const {
     const ChSystemDem_impl& S = *m_sys;
     const size_t n = S.n();
     const unsigned K = MAX_SPHERES_TOUCHED_BY_SPHERE;
+    // Layout of the reference writer (ChSystemDem.cpp:1450-1500): FRICTIONLESS writes nothing, SINGLE_STEP the partner map
+    // only ("partners 12"), MULTI_STEP the partner map and the displacement triples ("partners 12 history 12").
+    if (S.friction == CHDEM_FRICTION_MODE::FRICTIONLESS) {
+        printf("WARNING! Currently using FRICTIONLESS model. There is no contact history to write!\n");
+        return;
+    }
+    const bool with_hist = S.friction == CHDEM_FRICTION_MODE::MULTI_STEP;
     const PartnerRows rows = partner_rows(S);
     std::ostringstream o;
-    o << "partners " << K << " history " << K << "\n";
+    o << "partners " << K;
+    if (with_hist)
+        o << " history " << K;
+    o << "\n";
     for (size_t i = 0; i < n; i++) {
         for (unsigned k = 0; k < K; k++)
             o << (k < rows[i].size() ? rows[i][k].first : (uint32_t)NULL_CHDEM_ID) << " ";
-        for (unsigned k = 0; k < K; k++) {
+        for (unsigned k = 0; with_hist && k < K; k++) {
             if (k < rows[i].size())
                 o << rows[i][k].second[0] << " " << rows[i][k].second[1] << " " << rows[i][k].second[2] << " ";
             else
@@ -970,20 +1087,37 @@ void ChSystemDem::ReadCsvParticles(std::ifstream& ifile, unsigned int totRow) {
 void ChSystemDem::ReadHstHistory(std::ifstream& ifile, unsigned int totItem) {
     ChSystemDem_impl& S = *m_sys;
     std::string line, w1, w2;
-    if (!std::getline(ifile, line))
-        fail("history: missing header");
+    auto blank = [](const std::string& l) { return l.find_first_not_of(" \r\t") == std::string::npos; };
+    // header as the reference parses it (quarryHistoryFormat, ChSystemDem.cpp:690-706): "partners N", optionally followed by
+    // "history N" (SINGLE_STEP checkpoints carry the partner map only); blank lines in front of it are skipped (:793-795)
+    do {
+        if (!std::getline(ifile, line))
+            fail("history: missing header");
+    } while (blank(line));
     unsigned np = 0, nh = 0;
+    bool with_hist = false;
     {
         std::istringstream h(line);
-        h >> w1 >> np >> w2 >> nh;
-        if (w1 != "partners" || w2 != "history" || np == 0 || np != nh)
-            fail("history: header must read \"partners N history N\"");
+        h >> w1 >> np;
+        if (w1 != "partners" || np == 0)
+            fail("history: header must read \"partners N [history N]\"");
+        if (h >> w2 >> nh) {
+            if (w2 != "history" || nh != np)
+                fail("history: header must read \"partners N [history N]\"");
+            with_hist = true;
+        }
     }
     const size_t n = S.n();
     S.hist.clear();
-    for (size_t i = 0; i < n && i < totItem; i++) {
+    for (size_t i = 0; i < n && i < totItem;) {
         if (!std::getline(ifile, line))
             break;
+        if (blank(line))
+            continue;  // as the reference (:815-817)
+        i++;
+        if (!with_hist)
+            continue;  // partner map only: nothing to restore, contact pairs are found again by the first step
+        const size_t row_i = i - 1;
         std::istringstream r(line);
         std::vector<uint32_t> partner(np);
         for (auto& p : partner) r >> p;
@@ -994,12 +1128,12 @@ void ChSystemDem::ReadHstHistory(std::ifstream& ifile, unsigned int totItem) {
             if (p == (uint32_t)NULL_CHDEM_ID)
                 continue;
             ChSystemDem_impl::HistRow row;
-            row.sphere = (uint32_t)i;
+            row.sphere = (uint32_t)row_i;
             if (p > n) {  // boundary label nSpheres + BC_id + 1 (ChDemBoundaryConditions.cuh:102)
                 row.is_bc = true;
                 row.partner = p - (uint32_t)n - 1;
             } else {
-                if (p > i)
+                if (p > row_i)
                     continue;  // the higher-id partner's copy is the one we keep (both are present in the file)
                 row.is_bc = false;
                 row.partner = p;

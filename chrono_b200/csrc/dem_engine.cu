@@ -55,6 +55,9 @@ struct dem_b200_system {
     unsigned ntiles = 0;               // scan tiles covering the search-cell capacity
     cudaGraphExec_t graph1 = nullptr;  // one step
     bool recording = false;
+    bool user_recording = false;       // dem_b200_enable_recording asked for by the caller (contact info piggybacks on the same kernels)
+    bool contact_info = false;
+    double* d_cinfo_out = nullptr;
     size_t max_pairs = 0;
     bool use_hrel = false;
     bool track_wall_forces = false;
@@ -521,7 +524,14 @@ int recompute_bbox(dem_b200_system* s) {
         init[k] = s->W.has_bb ? enc_ord_h(s->W.bb_min[k]) : enc_ord_h(INFINITY);
         init[3 + k] = s->W.has_bb ? enc_ord_h(s->W.bb_max[k]) : enc_ord_h(-INFINITY);
     }
+    unsigned long long sinit[6];
+    for (int k = 0; k < 3; k++) {
+        sinit[k] = enc_ord_h(INFINITY);
+        sinit[3 + k] = enc_ord_h(-INFINITY);
+    }
     CU(cudaMemcpyAsync(s->B.ctrl->bbox, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->B.ctrl->sbox, sinit, sizeof(sinit), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(&s->B.ctrl->sbox_pending, 0, sizeof(unsigned), s->stream));
     CU(cudaStreamSynchronize(s->stream));  // init[] is on the stack
     k_bbox_reduce<<<(s->P.N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B);
     CU(cudaGetLastError());
@@ -1013,9 +1023,9 @@ int dem_b200_initialize(dem_b200_system* s) {
     // spreads beyond that, k_step_begin coarsens the cells instead of overflowing
     {
         double mn[3], mx[3];
-        for (int k = 0; k < 3; k++) {
-            mn[k] = s->W.has_bb ? s->W.bb_min[k] : INFINITY;
-            mx[k] = s->W.has_bb ? s->W.bb_max[k] : -INFINITY;
+        for (int k = 0; k < 3; k++) {  // the search grid covers the spheres and the meshes, not the walls
+            mn[k] = INFINITY;
+            mx[k] = -INFINITY;
         }
         for (size_t i = 0; i < n; i++)
             for (int k = 0; k < 3; k++) {
@@ -1475,7 +1485,8 @@ int dem_b200_enable_recording(dem_b200_system* s, int enable, size_t max_pairs) 
     }
     CU(cudaSetDevice(s->cfg.device));
     drop_graph(s);
-    s->recording = enable != 0;
+    s->user_recording = enable != 0;
+    s->recording = enable != 0 || s->contact_info;
     if (!enable)
         return 0;
     const size_t n = s->P.N;
@@ -2083,6 +2094,125 @@ int dem_b200_import_owned(dem_b200_system* s, size_t n, const double* pos3, cons
     }
     CU(cudaStreamSynchronize(s->stream));  // the host buffers may be reused by the caller
     return 0;
+}
+
+// ---- per-contact records: Chrono::Dem SetRecordingContactInfo / getNormalForce ... / WriteContactInfoFile -----------------
+int dem_b200_enable_contact_info(dem_b200_system* s, int enable) {
+    if (!s || !s->initialized)
+        return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "contact info recording is not available on a slab engine";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaStreamSynchronize(s->stream));
+    if (!enable) {
+        s->contact_info = false;
+        if (!s->user_recording)
+            return dem_b200_enable_recording(s, 0, 0);
+        return 0;
+    }
+    const bool keep_user = s->user_recording;
+    int rc = dem_b200_enable_recording(s, 1, s->max_pairs);  // the recording instantiations of the force kernel write the records
+    s->user_recording = keep_user;
+    if (rc)
+        return rc;
+    if (!s->B.cinfo) {
+        const size_t rows = (size_t)s->P.Kn + (size_t)s->P.nW;
+        rc = dev_alloc(s, &s->B.cinfo, rows * s->P.Np * kCInfo);
+        if (rc)
+            return rc;
+        CU(cudaMemset(s->B.cinfo, 0, rows * s->P.Np * kCInfo * sizeof(double)));
+    }
+    s->contact_info = true;
+    return 0;
+}
+
+int dem_b200_get_contact_info(dem_b200_system* s, size_t sphere, uint32_t other_shape, double info13[13], int* found) {
+    if (!s || !s->initialized || !info13 || !found || sphere >= s->P.N)
+        return DEMB200_EINVAL;
+    if (!s->contact_info || !s->B.cinfo) {
+        s->err = "get_contact_info: call dem_b200_enable_contact_info(s, 1) first";
+        return DEMB200_EINVAL;
+    }
+    if (s->P.tang_mode != DEMB200_TANG_MULTISTEP) {
+        s->err = "contact info needs the MultiStep contact map";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    double* d_out = nullptr;
+    if (!s->d_cinfo_out) {
+        int rc = dev_alloc(s, &s->d_cinfo_out, 16);
+        if (rc)
+            return rc;
+    }
+    d_out = s->d_cinfo_out;
+    CU(cudaMemsetAsync(d_out, 0, 16 * sizeof(double), s->stream));
+    k_find_contact<<<(s->P.N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, (unsigned)sphere, other_shape, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->h_pin, d_out, 14 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    *found = s->h_pin[0] != 0.0;
+    for (int c = 0; c < kCInfo; c++)
+        info13[c] = *found ? s->h_pin[1 + c] : 0.0;
+    return 0;
+}
+
+int dem_b200_get_contact_infos(dem_b200_system* s, uint32_t* bi, uint32_t* bj, double* info13, size_t capacity, size_t* n) {
+    if (!s || !s->initialized || !n)
+        return DEMB200_EINVAL;
+    if (!s->contact_info || !s->B.cinfo || s->P.tang_mode != DEMB200_TANG_MULTISTEP) {
+        s->err = "get_contact_infos: needs dem_b200_enable_contact_info(s, 1) and MultiStep friction";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    if (!s->d_count) {
+        int rc = dev_alloc(s, &s->d_count, 4);
+        if (rc)
+            return rc;
+    }
+    unsigned *d_bi = nullptr, *d_bj = nullptr;
+    double* d_info = nullptr;
+    const size_t cap = (bi && bj && info13) ? capacity : 0;
+    if (cap) {
+        CU(cudaMalloc((void**)&d_bi, cap * sizeof(unsigned)));
+        CU(cudaMalloc((void**)&d_bj, cap * sizeof(unsigned)));
+        CU(cudaMalloc((void**)&d_info, cap * kCInfo * sizeof(double)));
+    }
+    CU(cudaMemsetAsync(s->d_count, 0, sizeof(unsigned), s->stream));
+    k_export_contacts<<<(s->P.N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B, s->d_count, (unsigned)std::min<size_t>(cap, 0xFFFFFFFFull),
+                                                                    d_bi, d_bj, d_info);
+    cudaError_t e = cudaGetLastError();
+    unsigned c = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->h_pin, s->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(s->stream);
+    memcpy(&c, s->h_pin, sizeof(unsigned));
+    *n = c;
+    if (e == cudaSuccess && cap && c <= cap && c) {
+        cudaMemcpy(bi, d_bi, c * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        cudaMemcpy(bj, d_bj, c * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(info13, d_info, (size_t)c * kCInfo * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_bi); cudaFree(d_bj); cudaFree(d_info);
+    if (e != cudaSuccess) {
+        s->err = std::string("get_contact_infos: ") + cudaGetErrorString(e);
+        return DEMB200_ECUDA;
+    }
+    return (cap && c > cap) ? DEMB200_ECAPACITY : 0;
+}
+
+// Chrono::Dem SetBCPlaneRotation (ChSystemDem_impl.cpp:993-1001): the wall's surface moves with vel + omega x (x - center) at
+// the contact point (ChDemBoundaryConditions.cuh:394); the wall geometry stays put.
+int dem_b200_set_wall_rotation(dem_b200_system* s, int w, const double center[3], const double omega[3]) {
+    if (!s || w < 0 || w >= s->P.nW || !center || !omega)
+        return DEMB200_EINVAL;
+    for (int k = 0; k < 3; k++) {
+        s->W.w[w].rc[k] = center[k];
+        s->W.w[w].omg[k] = omega[k];
+    }
+    return s->initialized ? upload_walls(s) : 0;
 }
 
 int dem_b200_clear_error(dem_b200_system* s) {

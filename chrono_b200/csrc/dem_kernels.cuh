@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(256) k_bbox_reduce(Params P, Buffers B) {
         mxx = p.x + p.w; mxy = p.y + p.w; mxz = p.z + p.w;
     }
     block_bbox_commit(mnx, mny, mnz, mxx, mxy, mxz, C.bbox);
+    block_bbox_commit(mnx, mny, mnz, mxx, mxy, mxz, C.sbox);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -240,6 +241,11 @@ __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned
 
 __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C) {
     const WallSet& WS = *B.walls;
+    if (C.sbox_pending) {  // the last rebuild measured the spheres' own box while binning them
+        for (int k = 0; k < 6; k++)
+            C.sbox[k] = C.sbox_next[k];
+        C.sbox_pending = 0u;
+    }
     // ---- Verlet bookkeeping: every sphere moved at most `travel` since the lists were built ----
     const double dx = sqrt(__longlong_as_double((long long)C.max_dx2));
     C.max_dx2 = 0ull;
@@ -310,8 +316,25 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
     if (err)
         atomicOr(&C.err, err);
 
-    // ---- search grid for the rebuild: cells no smaller than the candidate cut-off 2 rmax + skin ----
+    // ---- search grid for the rebuild: cells no smaller than the candidate cut-off 2 rmax + skin, over the box of the spheres
+    //      (as measured at the last rebuild, grown by what they can have moved since) and of the meshes -- not of the walls:
+    //      positions outside the grid are clamped into its boundary cells, which is still exact, only crowded
     if (rebuild) {
+        for (int k = 0; k < 3; k++) {
+            mn[k] = dec_ord(C.sbox[k]) - C.travel;
+            mx[k] = dec_ord(C.sbox[3 + k]) + C.travel;
+        }
+        if (P.nT) {
+            const MeshSet& MS = *B.meshes;
+            for (int m = 0; m < MS.n; m++)
+                for (int k = 0; k < 3; k++) {
+                    mn[k] = fmin(mn[k], dec_ord(MS.bb[m][k]));
+                    mx[k] = fmax(mx[k], dec_ord(MS.bb[m][3 + k]));
+                }
+        }
+        for (int k = 0; k < 3; k++)
+            if (!(mx[k] >= mn[k]) || !isfinite(mn[k]) || !isfinite(mx[k]))
+                mn[k] = mx[k] = 0.0;  // no spheres (cannot happen after initialize): a one-cell grid
         double e = (2.0 * P.rmax + C.skin) * (1.0 + 1e-9);
         double ext[3];
         for (int k = 0; k < 3; k++) {
@@ -344,6 +367,11 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
             C.s_dim[k] = dim[k];
         }
         C.s_ncell = (unsigned)tot;
+        for (int k = 0; k < 3; k++) {
+            C.sbox_next[k] = enc_ord(CUDART_INF);
+            C.sbox_next[3 + k] = enc_ord(-CUDART_INF);
+        }
+        C.sbox_pending = 1u;
         C.travel = 0.0;
         C.travel_mesh = 0.0;
         C.nrebuilds++;
@@ -412,12 +440,20 @@ __device__ __forceinline__ int cell_coord(double x, double org, double inv, int 
 }
 
 __global__ void __launch_bounds__(256) k_bin_count(Params P, Buffers B) {
-    const Ctrl& C = *B.ctrl;
+    Ctrl& C = *B.ctrl;
     if (!C.rebuild_now)
         return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < P.N;
     unsigned h = 0xFFFFFFFFu;
+    {   // the spheres' own bounding box, for the search grid of the NEXT rebuild (warp reduction, atomics only when it grows)
+        double4 p = make_double4(0, 0, 0, 0);
+        if (valid)
+            p = B.pos[C.rb_src][i];
+        const double inf = CUDART_INF;
+        block_bbox_commit(valid ? p.x - p.w : inf, valid ? p.y - p.w : inf, valid ? p.z - p.w : inf, valid ? p.x + p.w : -inf,
+                          valid ? p.y + p.w : -inf, valid ? p.z + p.w : -inf, C.sbox_next);
+    }
     if (valid) {
         const double4 p = B.pos[C.rb_src][i];
         const int cx = cell_coord(p.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
@@ -971,10 +1007,21 @@ struct Hist {
     double dur, relvel0;
     bool isnew;
 };
+// what SetRecordingContactInfo keeps of a contact, seen from body 2 of the evaluation (generic law) / from the evaluating
+// sphere (fast law): normal and tangential part of the force on it, rolling + spinning resistance torque on it (tr1: on
+// body 1), v_rot, characteristic collision time
+struct CInfoOut {
+    V3 fn, ft, tr, tr1, vrot;
+    double tc;
+};
+__device__ __forceinline__ void store_cinfo(double* dst, V3 fn, V3 ft, V3 tr, V3 vrot, double tc) {
+    dst[0] = fn.x; dst[1] = fn.y; dst[2] = fn.z; dst[3] = ft.x; dst[4] = ft.y; dst[5] = ft.z;
+    dst[6] = tr.x; dst[7] = tr.y; dst[8] = tr.z; dst[9] = vrot.x; dst[10] = vrot.y; dst[11] = vrot.z; dst[12] = tc;
+}
 
 template <bool HIST, bool ROLL>
 __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, const Body& b1, const Body& b2,
-                                           const Geom& g, Hist& h, V3& F, V3& T1, V3& T2) {
+                                           const Geom& g, Hist& h, V3& F, V3& T1, V3& T2, CInfoOut* info = nullptr) {
     const double kPI = 3.141592653589793238462643383279;
     const double eps = 2.220446049250313e-16;
     const V3 pt1_loc = g.pt1 - b1.pos;
@@ -1119,12 +1166,21 @@ __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, cons
 
     V3 tq1 = -cross(pt1_loc, force);
     V3 tq2 = cross(pt2_loc, force);
+    if (info) {
+        info->fn = forceN_mag * g.n;
+        info->ft = force - info->fn;
+        info->tr = mk(0, 0, 0); info->tr1 = mk(0, 0, 0); info->vrot = mk(0, 0, 0);
+        info->tc = 0.0;
+    }
+    const V3 tq1_f = tq1, tq2_f = tq2;
 
     if (ROLL) {
         double muRoll = cm.mu_roll, muSpin = cm.mu_spin;
         double d_coeff = gn_simple / (2.0 * m_eff * sqrt(kn_simple / m_eff));
         if (d_coeff < 1.0) {
             double t_collision = kPI * sqrt(m_eff / (kn_simple * (1 - d_coeff * d_coeff)));
+            if (info)
+                info->tc = t_collision;
             if (t_contact <= t_collision) {
                 muRoll = 0.0;
                 muSpin = 0.0;
@@ -1132,6 +1188,8 @@ __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, cons
         }
         V3 v_rot = cross(b2.w, pt2_loc) - cross(b1.w, pt1_loc);
         V3 rel_o = b2.w - b1.w;
+        if (info)
+            info->vrot = v_rot;
         double lv = len(v_rot);
         if (lv > P.min_roll && muRoll > eps) {
             tq1 = tq1 + muRoll * cross(forceN_mag * pt1_loc, v_rot) / lv;
@@ -1147,12 +1205,18 @@ __device__ __noinline__ void contact_force(const Params& P, const Comp& cm, cons
             tq1 = tq1 + ms;
             tq2 = tq2 - ms;
         }
+        if (info) {
+            info->tr = tq2 - tq2_f;
+            info->tr1 = tq1 - tq1_f;
+        }
     }
     switch (P.adhesion_model) {
         case 0: force = force - cm.adh * g.n; break;
         case 1: force = force - cm.adh_dmt * sqrt(g.erad) * g.n; break;
         default: force = force - cm.adh_perko * g.erad * g.n; break;
     }
+    if (info)
+        info->fn = force - info->ft;  // adhesion acts along the normal
     F = force;
     T1 = tq1;
     T2 = tq2;
@@ -1171,7 +1235,7 @@ template <bool HIST, bool ROLL, bool MATPROPS>
 __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp& cm, V3 n, double dist, double ra,
                                                     double rb, V3 va, V3 wa, V3 vb, V3 wb, double ma, double mb,
                                                     bool a_is_body1, V3& disp, double& steps, bool isnew, V3& F_me,
-                                                    V3& T_me) {
+                                                    V3& T_me, CInfoOut* info = nullptr) {
     const double eps = 2.220446049250313e-16;
     const double radSum = __dadd_rn(ra, rb);
     const double delta_n = radSum - dist;
@@ -1248,6 +1312,12 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     // force on b = fN n - fT; on a (me) the opposite.  Torque on a: -(n ra) x (fN n - fT) = ra (n x fT)
     V3 Fb = fN * n - fT;
     V3 Ta = ra * cross(n, fT);
+    const V3 Ta_f = Ta;
+    if (info) {
+        info->ft = fT;
+        info->vrot = mk(0, 0, 0);
+        info->tc = 0.0;
+    }
 
     if (ROLL) {
         const double kPI = 3.141592653589793238462643383279;
@@ -1263,6 +1333,8 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
         const double d_coeff = 0.5 * gn_simple * inv_m * fast_rsqrt(kn_simple * inv_m);
         if (d_coeff < 1.0) {
             const double t_collision = kPI * fast_rsqrt(kn_simple * (1 - d_coeff * d_coeff) * inv_m);
+            if (info)
+                info->tc = t_collision;
             const double t_contact = HIST ? steps * P.dt : 0.0;
             if (t_contact <= t_collision) {
                 muRoll = 0.0;
@@ -1271,6 +1343,8 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
         }
         // v_rot = wb x (-n rb) - wa x (n ra) = -(wsum x n)
         const V3 v_rot = -wxn;
+        if (info)
+            info->vrot = v_rot;
         const V3 rel_o = wb - wa;
         const double lv2 = dot(v_rot, v_rot);
         if (lv2 > P.min_roll * P.min_roll && muRoll > eps)
@@ -1288,6 +1362,10 @@ __device__ __forceinline__ void sphere_contact_fast(const Params& P, const Comp&
     Fb = Fb - cm.adh * n;
     F_me = -Fb;
     T_me = Ta;
+    if (info) {
+        info->fn = (cm.adh - fN) * n;
+        info->tr = Ta - Ta_f;
+    }
 }
 
 // box_sphere: ChNarrowphasePRIMS.cpp:269-313 with snap_to_box (ChCollisionUtils.h:546-563); rounding pinned.
@@ -1527,7 +1605,11 @@ __device__ __noinline__ void mesh_contacts(const Params& P, const Buffers& B, un
         Body b1{mk(M.pos[0], M.pos[1], M.pos[2]), mk(M.vel[0], M.vel[1], M.vel[2]), mk(M.omg[0], M.omg[1], M.omg[2]), M.mass};
         Body b2{mpos, v, w, my_mass};
         V3 F, T1, T2;
-        contact_force<HIST, ROLL>(P, P.comp[2], b1, b2, g, h, F, T1, T2);
+        CInfoOut ci;
+        const bool want_ci = REC && B.cinfo != nullptr;
+        contact_force<HIST, ROLL>(P, P.comp[2], b1, b2, g, h, F, T1, T2, want_ci ? &ci : nullptr);
+        if (want_ci)
+            store_cinfo(B.cinfo + (hi + s) * kCInfo, ci.fn, ci.ft, ci.tr, ci.vrot, ci.tc);
         out.F = out.F + F;
         out.T = out.T + T2;
         if (HIST) {
@@ -1737,9 +1819,18 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 steps += 1.0;
             }
             Body b1{mk(0, 0, 0), mk(W.vel[0], W.vel[1], W.vel[2]), mk(0, 0, 0), P.wall_mass};
+            if (W.omg[0] != 0.0 || W.omg[1] != 0.0 || W.omg[2] != 0.0) {
+                // SetBCPlaneRotation: the wall's material point at the contact moves with vel + omg x (pt1 - rc)
+                b1.pos = mk(W.rc[0], W.rc[1], W.rc[2]);
+                b1.w = mk(W.omg[0], W.omg[1], W.omg[2]);
+            }
             Body b2{mpos, mv.v, mv.w, my_mass};
             V3 F, T1, T2;
-            contact_force<HIST, ROLL>(P, P.comp[1], b1, b2, g, h, F, T1, T2);
+            CInfoOut ci;
+            const bool want_ci = REC && B.cinfo != nullptr;
+            contact_force<HIST, ROLL>(P, P.comp[1], b1, b2, g, h, F, T1, T2, want_ci ? &ci : nullptr);
+            if (want_ci)
+                store_cinfo(B.cinfo + (hi + s) * kCInfo, ci.fn, ci.ft, ci.tr, ci.vrot, ci.tc);
             Fsum = Fsum + F;
             Tsum = Tsum + T2;
             if (P.track_wall_forces) {
@@ -1834,8 +1925,12 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             if (had && !me1)
                 disp = -disp;  // canonical (body 1 -> body 2) to my frame
             V3 F, T;
+            CInfoOut ci;
+            const bool want_ci = REC && B.cinfo != nullptr;
             sphere_contact_fast<HIST, ROLL, FAST == 1>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass,
-                                            sphere_mass(P, pj.w), me1, disp, steps, !had, F, T);
+                                            sphere_mass(P, pj.w), me1, disp, steps, !had, F, T, want_ci ? &ci : nullptr);
+            if (want_ci)
+                store_cinfo(B.cinfo + (hi + s) * kCInfo, ci.fn, ci.ft, ci.tr, ci.vrot, ci.tc);
             Fsum = Fsum + F;
             Tsum = Tsum + T;
             if (HIST) {
@@ -1883,7 +1978,15 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 steps += 1.0;
             }
             V3 F, T1, T2;
-            contact_force<HIST, ROLL>(P, P.comp[0], b1, b2, g, h, F, T1, T2);
+            CInfoOut ci;
+            const bool want_ci = REC && B.cinfo != nullptr;
+            contact_force<HIST, ROLL>(P, P.comp[0], b1, b2, g, h, F, T1, T2, want_ci ? &ci : nullptr);
+            if (want_ci) {  // the generic law reports body 2's view
+                if (me1)
+                    store_cinfo(B.cinfo + (hi + s) * kCInfo, -ci.fn, -ci.ft, ci.tr1, ci.vrot, ci.tc);
+                else
+                    store_cinfo(B.cinfo + (hi + s) * kCInfo, ci.fn, ci.ft, ci.tr, ci.vrot, ci.tc);
+            }
             if (me1) {
                 Fsum = Fsum - F;
                 Tsum = Tsum + T1;
@@ -2499,6 +2602,64 @@ __global__ void __launch_bounds__(256) k_import_owned(Buffers B, unsigned n, con
         if (vel3) r.v = mk(vel3[3 * (size_t)at], vel3[3 * (size_t)at + 1], vel3[3 * (size_t)at + 2]);
         if (om3) r.w = mk(om3[3 * (size_t)at], om3[3 * (size_t)at + 1], om3[3 * (size_t)at + 2]);
         store_vel(B.vel[C.cur], i, r.v, r.w, r.sid, r.meta, r.amask);
+    }
+}
+
+// ---- per-contact records (SetRecordingContactInfo): one pair, or all sphere-sphere contacts with bi < bj
+// other_shape: shape id of the partner (wall w -> w, facet t -> nW + t, sphere j -> shape_base + j)
+__global__ void __launch_bounds__(256) k_find_contact(Params P, Buffers B, unsigned sid_i, unsigned other_shape, double* out) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.N)
+        return;
+    const VelRec* vel = B.vel[C.cur];
+    if (vel[s].sid != sid_i || (vel[s].meta & FLAG_GHOST))
+        return;
+    int slot = -1;
+    if (other_shape < (unsigned)P.nW) {
+        if ((vel[s].meta >> (8 + other_shape)) & 1u)
+            slot = P.Kn + (int)other_shape;
+    } else {
+        const unsigned nc = B.ncnt[s] & 0xFFu, tc = B.ncnt[s] >> 24;
+        for (unsigned k = 0; k < nc + tc; k++) {
+            if (!((vel[s].amask >> k) & 1ull))
+                continue;
+            const unsigned e = B.nl[(size_t)k * P.Np + s] & ~kHiFlag;
+            const unsigned key = (e & kTriFlag) ? (unsigned)P.nW + (e & ~kTriFlag) : P.shape_base + vel[e].sid;
+            if (key == other_shape)
+                slot = (int)k;
+        }
+    }
+    if (slot < 0)
+        return;
+    const double* src = B.cinfo + ((size_t)slot * P.Np + s) * kCInfo;
+    for (int c = 0; c < kCInfo; c++)
+        out[1 + c] = src[c];
+    out[0] = 1.0;
+}
+
+__global__ void __launch_bounds__(256) k_export_contacts(Params P, Buffers B, unsigned* count, unsigned cap, unsigned* bi,
+                                                         unsigned* bj, double* info) {
+    const Ctrl& C = *B.ctrl;
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.N)
+        return;
+    const VelRec* vel = B.vel[C.cur];
+    if (vel[s].meta & FLAG_GHOST)
+        return;
+    const unsigned nc = B.ncnt[s] & 0xFFu;
+    for (unsigned k = 0; k < nc; k++) {
+        const unsigned e = B.nl[(size_t)k * P.Np + s];
+        if (!(e & kHiFlag) || !((vel[s].amask >> k) & 1ull))
+            continue;  // each pair once, from the lower id's side
+        const unsigned at = atomicAdd(count, 1u);
+        if (at >= cap)
+            continue;
+        bi[at] = vel[s].sid;
+        bj[at] = vel[e & ~kHiFlag].sid;
+        const double* src = B.cinfo + ((size_t)k * P.Np + s) * kCInfo;
+        for (int c = 0; c < kCInfo; c++)
+            info[(size_t)at * kCInfo + c] = src[c];
     }
 }
 

@@ -35,6 +35,7 @@ constexpr unsigned kTriFlag = 0x80000000u;  // candidate-list entry = triangle (
 constexpr unsigned kHiFlag = 0x40000000u;   // sphere entry: the partner's stable id is higher than the owner's, i.e. the owner is body 1 of
                                             // the canonical (lower id, higher id) orientation -- decided once per list build so that the
                                             // force kernel does not have to gather the partner's id for it
+constexpr int kCInfo = 13;                  // doubles per recorded contact (Buffers::cinfo)
 constexpr unsigned kSlotHi = 0x80u;         // the same bit in the force kernel's shared-memory contact list (slot byte: slot < 64)
 
 // device error bits (dem_b200 error codes are derived from these at sync points)
@@ -67,6 +68,8 @@ struct Wall {
                        // (ball radius, +1 obstacle | -1 cavity, -) / cone (slope dz/dr, hmin, hmax), rot[0] = +1 spheres above
                        // the cone surface (inside a hopper) | -1 below it
     double vel[3];     // velocity of the wall body (moving boundaries)
+    double omg[3];     // surface spin of a plane (Chrono::Dem SetBCPlaneRotation, ChSystemDem_impl.cpp:993-1001): the wall's material
+    double rc[3];      // point at x moves with vel + omg x (x - rc); the geometry itself stays where it is
     double amin[3], amax[3];  // world AABB (ChCollisionSystemMulticore.cpp:395-406); boxes only
 };
 
@@ -153,6 +156,9 @@ struct Ctrl {
     unsigned err_pad_;
     unsigned long long nsteps, nrebuilds;
     unsigned long long bbox[6];   // order-preserving encoded doubles: min xyz, max xyz of the sphere AABBs
+    unsigned long long sbox[6];   // same encoding: AABB of the spheres alone (local ones and ghosts) at the last list rebuild -- the
+    unsigned long long sbox_next[6];  // search grid covers this box (+ the meshes), not the walls: a slab of a long box must not
+    unsigned sbox_pending, sbox_pad_; // bin the whole box.  sbox_next is gathered by k_bin_count while it reads every position anyway.
     unsigned long long max_dx2;   // raw bits of max |x_new - x_old|^2 over the spheres, last step
     double travel;                // sum of per-step max displacements since the last rebuild
     double last_dx;               // max displacement of the step before the last one (growth estimate of the slab vote)
@@ -239,6 +245,10 @@ struct Buffers {
     double* recF; double* recT;      // by sid, 3 each
     unsigned long long* pairs; unsigned long long pair_cap;
     int* gmin; int* gmax;            // by sid, 3 each: Multicore HashMin / HashMax of the sphere AABB
+    // per-contact records (Chrono::Dem SetRecordingContactInfo, ChSystemDem_impl.cpp:443-635): kCInfo doubles per history
+    // slot, [(slot * Np + s) * kCInfo + c] = force on the sphere: normal part xyz, tangential part xyz; rolling + spinning
+    // resistance torque xyz; v_rot xyz; characteristic collision time.  Null unless dem_b200_enable_contact_info.
+    double* cinfo;
     // triangle meshes: soup in the body frame and in the world frame (9 doubles per triangle: A, B, C), owner mesh,
     // and the CSR "triangles reaching search cell c" of the last rebuild
     MeshSet* meshes;

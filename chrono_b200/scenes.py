@@ -226,25 +226,56 @@ def _hash_uniform(gid, stream):
     return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
 
 
+def hcp_layer_heights(nz, radius, sep, young=2e6, poisson=0.3, g=9.81):
+    """Centre heights of nz HCP layers (in-plane spacing sep, laterally confined) in STATIC EQUILIBRIUM under gravity with the
+    Hertz law of the engine (ChIterativeSolverMulticoreSMC.cpp:277-290: F = kn delta, kn = 4/3 E* sqrt(R* delta)): every sphere
+    rests on three spheres of the layer below (horizontal offset sep / sqrt(3)), the bottom layer on the floor at z = 0.
+    A bed generated at these heights starts at rest instead of collapsing by several per cent of its depth."""
+    E = 1.0 / (2.0 * (1.0 - poisson * poisson) / young)        # composite of two equal materials (make_comp, float there)
+    m = MASS_COEF * radius ** 3
+    h = sep / math.sqrt(3.0)
+    dz0 = sep * math.sqrt(2.0 / 3.0)
+    n_above = np.arange(nz - 1, 0, -1, dtype=np.float64)       # layers resting on interface q = 0 .. nz-2
+    kH = 4.0 / 3.0 * E * math.sqrt(0.5 * radius)
+    lo, hi = np.zeros(nz - 1), np.full(nz - 1, dz0)
+    for _ in range(80):                                          # bisection on the layer spacing: the support grows as dz shrinks
+        dz = 0.5 * (lo + hi)
+        dist = np.sqrt(h * h + dz * dz)
+        delta = np.maximum(2.0 * radius - dist, 0.0)
+        support = 3.0 * kH * delta ** 1.5 * dz / dist
+        too_low = support > n_above * m * g
+        lo = np.where(too_low, dz, lo)
+        hi = np.where(too_low, hi, dz)
+    dz = 0.5 * (lo + hi)
+    dw = (nz * m * g / (4.0 / 3.0 * E * math.sqrt(radius))) ** (2.0 / 3.0)  # floor contact: face of a box, R* = R
+    return np.concatenate([[radius - dw], radius - dw + np.cumsum(dz)])
+
+
 def slab_lattice_scene(n_total, world=1, rank=0, radius=0.02, jitter=0.005, sep_factor=2.0, polydisperse=None,
-                       wall_thickness=0.2, bin_factor=2.0, headroom=1.25, cross_section_of=None):
+                       wall_thickness=0.2, bin_factor=2.0, headroom=1.25, cross_section_of=None, layers=None, precompress=False):
     """The settling_scene packing for `world` slabs along x, of which only slab `rank` is generated.
 
     The box is `world` times as long (x) as the box of an n_total / world packing is wide, same width (y) and bed depth,
     made of complete HCP layers (so the sphere count is n_actual ~ n_total, returned).  Slab faces lie between lattice
-    columns; global id = lattice index in generation order (z layers, y rows, x).  Returns dict(pos, radius, ids, lo, hi,
-    n_total, box_size, walls, bins) with pos / radius / ids of slab `rank` only."""
+    columns; global id = lattice index in generation order (z layers, y rows, x).  layers: fixed bed depth in HCP layers (the
+    box widens instead of deepening as n_total grows: equal work per sphere at every size); precompress: layer heights in
+    static equilibrium (hcp_layer_heights; monodisperse only).  Returns dict(pos, radius, ids, lo, hi, n_total, box_size,
+    walls, bins) with pos / radius / ids of slab `rank` only."""
     sep = sep_factor * radius * (1.2 if polydisperse else 1.0)
     rmax = radius * (polydisperse[1] if polydisperse else 1.0)
     site = sep ** 3 / math.sqrt(2.0)
     n_one = cross_section_of or max(1, n_total // world)
-    L = (n_one * site / 0.26) ** (1.0 / 3.0)
     dx, dy, dz = sep, sep * (math.sqrt(3.0) / 2), sep * math.sqrt(2.0 / 3.0)
-    nx1 = max(1, int((L - 2.02 * rmax) / dx))          # lattice columns per slab (the half-offset rows need dx / 2 more)
+    if layers:
+        L = math.sqrt(n_one * dx * dy / layers) + 2.02 * rmax   # square footprint holding n_one / layers sites
+    else:
+        L = (n_one * site / 0.26) ** (1.0 / 3.0)
+    nx1 = max(1, int(round((L - 2.02 * rmax) / dx)))   # lattice columns per slab
     nx = nx1 * world
-    ny = max(1, int((L - 2.02 * rmax) / dy))
-    nz = max(1, int(round(n_total / float(nx * ny))))
-    Lx, Ly = nx * dx + dx / 2 + 2.02 * rmax, L
+    ny = max(1, int(round((L - 2.02 * rmax) / dy)))
+    nz = int(layers) if layers else max(1, int(round(n_total / float(nx * ny))))
+    # the box holds the lattice exactly: odd rows are shifted by dx / 2, odd layers by dy / 3
+    Lx, Ly = (nx - 1) * dx + dx / 2 + 2.02 * rmax, (ny - 1) * dy + dy / 3 + 2.02 * rmax
     x0, y0, z0 = -Lx / 2 + 1.01 * rmax, -Ly / 2 + 1.01 * rmax, 1.01 * rmax
     i0, i1 = rank * nx1, (rank + 1) * nx1
     k = np.arange(nz, dtype=np.int64)[:, None, None]
@@ -257,7 +288,11 @@ def slab_lattice_scene(n_total, world=1, rank=0, radius=0.02, jitter=0.005, sep_
     pos = np.empty((gid.size, 3))
     pos[:, 0] = np.broadcast_to(x0 + offx + i * dx, shape).reshape(-1)
     pos[:, 1] = np.broadcast_to(y0 + offy + j * dy + 0.0 * i, shape).reshape(-1)
-    pos[:, 2] = np.broadcast_to(z0 + k * dz + 0.0 * j + 0.0 * i, shape).reshape(-1)
+    if precompress and not polydisperse:
+        zk = hcp_layer_heights(nz, radius, sep)
+    else:
+        zk = z0 + np.arange(nz) * dz
+    pos[:, 2] = np.broadcast_to(zk[:, None, None] + 0.0 * j + 0.0 * i, shape).reshape(-1)
     for c in range(3):
         pos[:, c] += (jitter * radius) * _hash_uniform(gid, c)
     if polydisperse:
@@ -265,7 +300,7 @@ def slab_lattice_scene(n_total, world=1, rank=0, radius=0.02, jitter=0.005, sep_
         rad = radius * (polydisperse[0] + (polydisperse[1] - polydisperse[0]) * u)
     else:
         rad = np.full(gid.size, radius)
-    ztop = z0 + (nz - 1) * dz + jitter * radius
+    ztop = zk[-1] + jitter * radius
     Lz = max(ztop + 2 * rmax, 0.25 * Ly) * headroom
     size = np.array([Lx, Ly, Lz])
     walls = box_container(size, wall_thickness, center=(0.0, 0.0, Lz / 2), faces=(2, 2, -1))

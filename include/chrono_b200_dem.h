@@ -254,6 +254,22 @@ int dem_b200_export_owned(dem_b200_system* s, uint32_t* sid, double* pos3, doubl
  * follow that export (no step, no rebuild in between).  With new positions the candidate lists and the neighbours' ghost
  * copies are stale: run the slab rebuild protocol before the next step. */
 int dem_b200_import_owned(dem_b200_system* s, size_t n, const double* pos3, const double* vel3, const double* omega3);
+/* ---- per-contact records -- SetRecordingContactInfo / getNormalForce ... / WriteContactInfoFile
+ * (src/chrono_dem/physics/ChSystemDem.h:180,326-338; ChSystemDem_impl.cpp:443-635).  While enabled every step also keeps,
+ * for each force-carrying contact of each sphere, 13 doubles: the force on that sphere split into its normal (xyz) and
+ * tangential (xyz) part, the rolling + spinning resistance torque on it (xyz), v_rot (xyz) and the characteristic collision
+ * time.  Needs MultiStep friction (the contact map); steps run un-graphed through the recording kernels. */
+int dem_b200_enable_contact_info(dem_b200_system* s, int enable);
+/* One contact of sphere `sphere` (user index): other_shape = shape id of the partner (wall k -> k, facet t -> num_walls + t,
+ * sphere j -> num_walls + num_triangles + j).  *found = 0 and zeros when the two do not touch. */
+int dem_b200_get_contact_info(dem_b200_system* s, size_t sphere, uint32_t other_shape, double info13[13], int* found);
+/* All sphere-sphere contacts, each once (bi < bj, the record is the one of sphere bi), any order.  Pass NULL arrays to get
+ * the count. */
+int dem_b200_get_contact_infos(dem_b200_system* s, uint32_t* bi, uint32_t* bj, double* info13, size_t capacity, size_t* n);
+/* Surface spin of a wall -- SetBCPlaneRotation (ChSystemDem.h:238, ChSystemDem_impl.cpp:993-1001): the wall's material point
+ * at a contact moves with vel + omega x (x - center); the geometry does not move.  Legal at any time. */
+int dem_b200_set_wall_rotation(dem_b200_system* s, int wall, const double center[3], const double omega[3]);
+
 /* Device error bits (history / neighbour overflow, skin exceeded, NaN ...) are sticky: every later sync point reports them.
  * Once the cause is dealt with (set_config with more slots, set_state ...) this clears them. */
 int dem_b200_clear_error(dem_b200_system* s);

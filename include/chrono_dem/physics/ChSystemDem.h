@@ -104,7 +104,7 @@ class CH_DEM_API ChSystemDem {
     bool SetBCOffsetFunction(size_t BC_id, const GranPositionFunction& offset_function);
     void SetBCSpherePosition(size_t sphere_bc_id, const ChVector3f& pos);
     void SetBCSphereVelocity(size_t sphere_bc_id, const ChVector3f& velo);
-    void SetBCPlaneRotation(size_t plane_id, ChVector3d center, ChVector3d omega);  ///< declared for source compatibility; throws
+    void SetBCPlaneRotation(size_t plane_id, ChVector3d center, ChVector3d omega);
     ChVector3f GetBCSpherePosition(size_t sphere_id) const;
     ChVector3f GetBCSphereVelocity(size_t sphere_id) const;
     void setBDWallsMotionFunction(const GranPositionFunction& pos_fn);

@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "cpp", "_bin")
-PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling", "utest_utils", "utest_DEM_bcsphere"]
+PROGRAMS = ["utest_DEM_stack", "utest_DEM_frictionrolling", "utest_DEM_pyramid", "utest_DEM_api", "utest_DEM_meshrolling", "utest_utils", "utest_DEM_bcsphere", "utest_DEM_contactinfo"]
 
 
 def build_program(name):
@@ -80,4 +80,11 @@ def test_dem_bc_ball_with_mass_and_cone_hopper():
 @pytest.mark.gpu
 def test_dem_api_io_roundtrip(tmp_path):
     out = run("utest_DEM_api", str(tmp_path))
+    assert "PASSED" in out
+
+
+@pytest.mark.gpu
+def test_dem_contact_info_plane_rotation_single_step_checkpoint(tmp_path):
+    """SetRecordingContactInfo + per-pair getters + WriteContactInfoFile, SetBCPlaneRotation, SINGLE_STEP checkpoint layout."""
+    out = run("utest_DEM_contactinfo", str(tmp_path))
     assert "PASSED" in out
