@@ -34,9 +34,9 @@ sys.path.insert(0, ROOT)
 
 RADIUS = 0.02
 DT = 1e-4
-COND_GRAPH = os.environ.get("DEMB200_COND_GRAPH", "")[:1] == "1"  # opt-in: see build_graph() in csrc/dem_engine.cu
+COND_GRAPH = os.environ.get("DEMB200_COND_GRAPH", "1")[:1] != "0"  # default: see build_graph() in csrc/dem_engine.cu
 KERNELS_PER_TIMESTEP = 9   # launches of our own kernels per DEM time step (7 of them return at once unless the step rebuilds)
-KERNELS_PER_TIMESTEP_SLAB = 14  # + 2 x halo pack, 2 x halo unpack, vote
+KERNELS_PER_TIMESTEP_SLAB = 15  # + second pass of the force kernel (spheres that touch a ghost), 2 x halo unpack, 2 x halo pack, vote
 CONFIG_NAMES = {
     0: "BASELINE configs[0]: 10k monodisperse spheres Hertz SMC settling in a box, 1000 time steps, GPU vs the CPU port full length",
     1: "BASELINE configs[1]: 1M spheres Hertz-Mindlin with MultiStep tangential history settling in a 5-wall box",
@@ -146,8 +146,8 @@ def workload_config(cfg_id, n_per_gpu, n_total, substeps, gpus, settle, extra=No
          "config_id": cfg_id, "spheres_total": n_total, "spheres_per_gpu": n_per_gpu, "timesteps_per_step": substeps,
          "settle_timesteps": settle,
          "l2_policy": "working set (>= 900 B/sphere-step of DRAM traffic x %d spheres) exceeds the 126 MB L2; no explicit flush" % n_per_gpu,
-         "step_graph": ("conditional rebuild node (DEMB200_COND_GRAPH=1; its kernels are invisible to ncu)"
-                        if gpus == 1 and COND_GRAPH else "flat capture, every launch profilable"),
+         "step_graph": ("conditional rebuild node: a step that does not rebuild launches 2 kernels (DEMB200_COND_GRAPH=0 -> flat capture "
+                        "of all 9, the form ncu can profile)" if gpus == 1 and COND_GRAPH else "flat capture, every launch profilable"),
          "parallelism": "1 process per GPU" if gpus == 1 else
          "slab domain decomposition along x, %d ranks, ghost halo by NVLink peer stores, spheres migrate at list rebuilds" % gpus}
     if extra:

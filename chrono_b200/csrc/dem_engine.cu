@@ -26,6 +26,9 @@ using namespace demb200;
 #ifndef DEMB200_COND_GRAPH
 #define DEMB200_COND_GRAPH 1
 #endif
+#ifndef DEMB200_TILE_DEFAULT
+#define DEMB200_TILE_DEFAULT 0
+#endif
 
 namespace {
 thread_local std::string g_create_error;
@@ -249,19 +252,50 @@ bool fast_path(const dem_b200_system* s) {
     return s->P.force_model == DEMB200_HERTZ && s->P.adhesion_model == DEMB200_ADH_CONSTANT;
 }
 
+// The tile kernel (shared-memory staging of the neighbour bins): Hertz fast paths, no meshes, no recording.
+template <bool H, bool R, int F>
+void launch_tile(dem_b200_system* s, const Buffers& B, unsigned pass) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_force_tile<H, R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+        attr_set = true;
+    }
+    const unsigned tiles = s->P.cell_cap / (unsigned)kTileCells + 1u;  // upper bound of the tile count; surplus blocks leave at once
+    k_force_tile<H, R, F><<<tiles, kTileThreads, kTileSmemBytes, s->stream>>>(s->P, B, pass);
+}
+
+bool use_tile_kernel(const dem_b200_system* s) {
+    return s->P.tiled && !s->P.nT && fast_path(s) && !s->recording;
+}
+
+// pass 0: all spheres; 1 / 2: the spheres without / with a ghost among their candidates (slab mode, direct halo: see enqueue_post)
 template <bool REC>
-void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks) {
+void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks, unsigned pass = 0u) {
     const Params& P = s->P;
     const bool hist = (P.tang_mode == DEMB200_TANG_MULTISTEP);
     const bool roll = need_roll(s);
     const int fast = fast_path(s) ? (P.use_mat_props ? 1 : 2) : 0;
+    if (!REC && use_tile_kernel(s)) {
+        const int tsel = (hist ? 4 : 0) + (roll ? 2 : 0) + (fast - 1);
+        switch (tsel) {
+            case 0: launch_tile<false, false, 1>(s, B, pass); break;
+            case 1: launch_tile<false, false, 2>(s, B, pass); break;
+            case 2: launch_tile<false, true, 1>(s, B, pass); break;
+            case 3: launch_tile<false, true, 2>(s, B, pass); break;
+            case 4: launch_tile<true, false, 1>(s, B, pass); break;
+            case 5: launch_tile<true, false, 2>(s, B, pass); break;
+            case 6: launch_tile<true, true, 1>(s, B, pass); break;
+            default: launch_tile<true, true, 2>(s, B, pass); break;
+        }
+        return;
+    }
     const int sel = (hist ? 6 : 0) + (roll ? 3 : 0) + fast;
 #define LF(H, R, F)                                                                                  \
     do {                                                                                             \
         if (P.nT)                                                                                    \
-            k_force_integrate<H, R, F, REC, true><<<blocks, kForceThreads, 0, s->stream>>>(P, B);    \
+            k_force_integrate<H, R, F, REC, true><<<blocks, kForceThreads, 0, s->stream>>>(P, B, pass);    \
         else                                                                                         \
-            k_force_integrate<H, R, F, REC, false><<<blocks, kForceThreads, 0, s->stream>>>(P, B);   \
+            k_force_integrate<H, R, F, REC, false><<<blocks, kForceThreads, 0, s->stream>>>(P, B, pass);   \
     } while (0)
     switch (sel) {
         case 0: LF(false, false, 0); break;
@@ -289,20 +323,18 @@ const char* kKernelNames[kNumKernels] = {"k_step_begin", "k_bin_count", "k_scan_
 // One step = halo + control kernel | rebuild kernels (they return at once unless k_step_begin said "rebuild") | force kernel.
 // The three parts are separate so that the step graph can put the middle one into a conditional node.
 void enqueue_pre(dem_b200_system* s, cudaStream_t st, unsigned long long cond) {
-    const Params& P = s->P;
-    Buffers& B = s->B;
-    if (s->p2p && !s->mg_remap_pending) {
-        // ghost halo of this step: my boundary spheres go straight into the neighbours' landing buffers (NVLink stores),
-        // theirs are picked up as soon as their step number shows up.  (Skipped right after a rebuild: the ghosts that
-        // were just exchanged are current.)
-        for (int d = 0; d < 2; d++)
-            if (s->mg_ns[d])
-                k_p2p_pack<<<(s->mg_ns[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ns[d]);
-        for (int d = 0; d < 2; d++)
-            if (s->mg_ng[d])
-                k_p2p_unpack<<<(s->mg_ng[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ng[d]);
-    }
-    k_step_begin<<<1, 32, 0, st>>>(P, B, cond);
+    k_step_begin<<<1, 32, 0, st>>>(s->P, s->B, cond);
+}
+
+// Direct halo of slab mode (dem_b200_p2p_*): at the END of a step the boundary spheres' new state goes straight into the
+// neighbours' landing buffers (NVLink stores, tagged with the number of the step that will consume it) and the rebuild vote is
+// cast; the consumer picks the data up BETWEEN the two passes of its force kernel (enqueue_post), i.e. a whole interior pass
+// after it was sent, so nobody waits for a neighbour unless it lags by most of a step.
+void enqueue_halo_send(dem_b200_system* s, cudaStream_t st) {
+    for (int d = 0; d < 2; d++)
+        if (s->mg_ns[d])
+            k_p2p_pack<<<(s->mg_ns[d] + 255) / 256, 256, 0, st>>>(s->B, s->X, d, s->mg_ns[d]);
+    k_p2p_vote<<<1, 32, 0, st>>>(s->P, s->B, s->X);
 }
 
 // ev: optional events recorded after each of the seven rebuild kernels (profiling), starting at ev[*k]
@@ -349,12 +381,24 @@ void enqueue_post(dem_b200_system* s, cudaStream_t st) {
     if (s->recording) {
         k_record_bins<<<(N + 255) / 256, 256, 0, st>>>(P, B);
         launch_force<true>(s, B, fb);
+    } else if (s->p2p && !s->mg_remap_pending) {
+        // interior first (needs no ghost), then the halo that was sent at the end of the neighbours' previous step, then the
+        // spheres that touch a ghost: at most the ghost senders (a sphere with a ghost candidate lies within the ghost cut of
+        // its slab face), hence the grid of the second pass
+        launch_force<false>(s, B, fb, 1u);
+        for (int d = 0; d < 2; d++)
+            if (s->mg_ng[d])
+                k_p2p_unpack<<<(s->mg_ng[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ng[d], 1);
+        const unsigned nb = s->mg_ns[0] + s->mg_ns[1];
+        if (nb)
+            launch_force<false>(s, B, (nb + kForceThreads - 1) / kForceThreads, 2u);
+        enqueue_halo_send(s, st);
     } else {
+        // (slab mode right after a rebuild: the ghosts that were just exchanged are current, one pass; run_steps sends the halo
+        // once the sorted slots of the senders are known)
         launch_force<false>(s, B, fb);
     }
     s->stream = keep;
-    if (s->p2p)
-        k_p2p_vote<<<1, 32, 0, st>>>(P, B, s->X);
 }
 
 // Enqueue one step.  ev: optional kNumKernels+1 events recorded around each launch (profiling).
@@ -456,9 +500,15 @@ int build_graph(dem_b200_system* s) {
     // nodes of a graph that holds a conditional node, so the default is the flat capture whose launches are all profilable.
     // Slab mode re-captures the graph after every slab rebuild (the local sphere count changes): there the flat capture,
     // which is cheaper to build, wins anyway (2 x B200: 36.2 vs 37.3 ms per 100 steps).
+    // The conditional step graph is the default outside slab mode (DEMB200_COND_GRAPH=0 in the environment selects the flat
+    // capture): a step that does not rebuild launches k_step_begin and the force kernel only, instead of seven more kernels that
+    // return at once (3 - 5 % of a 1 M-sphere step).  ncu cannot see the kernel nodes of a graph that holds a conditional node:
+    // profile with DEMB200_COND_GRAPH=0 or through direct launches (scripts/profile_kernels.py does).
+    // Slab mode re-captures the graph after every slab rebuild (the local sphere count changes): there the flat capture,
+    // which is cheaper to build, wins anyway (2 x B200: 36.2 vs 37.3 ms per 100 steps).
     static const bool want_cond = [] {
         const char* e = getenv("DEMB200_COND_GRAPH");
-        return e && e[0] == '1';
+        return !(e && e[0] == '0');
     }();
     if (want_cond && !s->mgpu && build_graph_conditional(s, &g) == 0) {
         cudaError_t ei = cudaGraphInstantiate(&s->graph1, g, 0);
@@ -587,8 +637,10 @@ int run_steps(dem_b200_system* s, int nsteps) {
             k_mgpu_invert_perm<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B);
             if (m)
                 k_mgpu_remap<<<(m + 255) / 256, 256, 0, s->stream>>>(s->B, s->mg_n_own, s->mg_ns[0], s->mg_ns[1], s->mg_ng[0], s->mg_ng[1]);
-            CU(cudaGetLastError());
             s->mg_remap_pending = false;
+            if (s->p2p)
+                enqueue_halo_send(s, s->stream);  // the first step after a slab rebuild: its result feeds the neighbours' next step
+            CU(cudaGetLastError());
         }
     }
     return 0;
@@ -1019,6 +1071,13 @@ int dem_b200_initialize(dem_b200_system* s) {
         s->err = "bad radius / verlet_skin";
         return DEMB200_EINVAL;
     }
+    // Tiled search grid + tile force kernel (shared-memory staging of the neighbour bins): on by default where the tile kernel
+    // applies (Hertz fast paths, no meshes); DEMB200_TILE=0 in the environment keeps the plain grid and k_force_integrate.
+    {
+        const char* e = getenv("DEMB200_TILE");
+        const bool want = e ? (e[0] != '0') : (DEMB200_TILE_DEFAULT != 0);
+        P.tiled = (want && !P.nT && fast_path(s)) ? 1 : 0;
+    }
     // capacity of the search grid: twice the cells of the initial bounding box (spheres + walls); if the bed ever
     // spreads beyond that, k_step_begin coarsens the cells instead of overflowing
     {
@@ -1041,6 +1100,11 @@ int dem_b200_initialize(dem_b200_system* s) {
         double cells = 1.0;
         for (int k = 0; k < 3; k++)
             cells *= std::max(1.0, std::floor((mx[k] - mn[k]) / e) + 1.0);
+        if (P.tiled) {  // border tiles are only partly inside the box: count whole tiles
+            cells = 1.0;
+            for (int k = 0; k < 3; k++)
+                cells *= (std::floor((std::max(1.0, std::floor((mx[k] - mn[k]) / e) + 1.0) + kTile - 1) / kTile) + 1.0) * kTile;
+        }
         cells = std::min(std::max(2.0 * cells, 4096.0), std::max(4096.0, 16.0 * (double)(s->mgpu ? s->mg_cap : n)));
         P.cell_cap = (unsigned)cells;
     }
@@ -1072,6 +1136,8 @@ int dem_b200_initialize(dem_b200_system* s) {
     rc |= dev_alloc(s, &B.cell_count, (size_t)P.cell_cap + 8); rc |= dev_alloc(s, &B.cell_start, (size_t)P.cell_cap + 8);
     rc |= dev_alloc(s, &B.block_sums, (size_t)s->ntiles + 8);
     rc |= dev_alloc(s, &B.nl, (size_t)P.Kn * Np); rc |= dev_alloc(s, &B.ncnt, Np);
+    if (P.tiled)
+        rc |= dev_alloc(s, &B.nl16, (size_t)P.Kn * Np);
     rc |= dev_alloc(s, &s->d_pos3, 3 * Np); rc |= dev_alloc(s, &s->d_vel3, 3 * Np); rc |= dev_alloc(s, &s->d_om3, 3 * Np);
     rc |= dev_alloc(s, &s->d_red, 4);
     if (P.nT) {
@@ -1103,6 +1169,7 @@ int dem_b200_initialize(dem_b200_system* s) {
     if (s->mgpu) {
         rc |= dev_alloc(s, &B.slab, 1);
         rc |= dev_alloc(s, &B.inv_perm, Np);
+        rc |= dev_alloc(s, &B.bnd_list, Np);
         rc |= dev_alloc(s, &s->d_count, 4);
         for (int d = 0; d < 2; d++) {
             rc |= dev_alloc(s, &B.send_pre[d], Np); rc |= dev_alloc(s, &B.send_slot[d], Np); rc |= dev_alloc(s, &B.ghost_slot[d], Np);
@@ -1890,6 +1957,11 @@ int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64) 
 int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* handles, int steps_ahead) {
     if (!s || !s->p2p_region || !handles || world < 2 || world > kMaxRanks || rank < 0 || rank >= world || steps_ahead < 1)
         return DEMB200_EINVAL;
+    if (!s->mg_remap_pending) {
+        s->err = "p2p_import: switch to the direct halo right after a slab rebuild, before the next step (the first direct step "
+                 "must not wait for a halo that nobody sent)";
+        return DEMB200_EINVAL;
+    }
     CU(cudaSetDevice(s->cfg.device));
     P2PDev& X = s->X;
     memset(&X, 0, sizeof(X));

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <type_traits>
 #include "dem_types.h"
 
 namespace demb200 {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) k_bbox_reduce(Params P, Buffers B) {
 // --------------------------------------------------------------------------------------------
 // step control: runs as one thread at the head of every step
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C);
+__device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C, const WallSet& WS);
 
 // The control block is staged through shared memory by the whole warp: the serial part then works at shared-memory
 // latency instead of paying a global round trip for every field it touches.
@@ -211,6 +212,7 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
 // steps that rebuild (no empty launches of N / 256-block grids in the other ~97 % of the steps).
 __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned long long cond) {
     __shared__ Ctrl sC;
+    __shared__ WallSet sW;  // read-only copy: the serial part below touches every wall, one global round trip each otherwise
     __shared__ unsigned s_err_in;
     static_assert(sizeof(Ctrl) % 8 == 0, "Ctrl is copied in 8-byte words");
     static_assert(offsetof(Ctrl, err) % 8 == 0 && offsetof(Ctrl, nsteps) == offsetof(Ctrl, err) + 8, "err owns its 8-byte word");
@@ -221,10 +223,17 @@ __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned
     constexpr unsigned kWords = sizeof(Ctrl) / 8;
     for (unsigned i = threadIdx.x; i < kWords; i += blockDim.x)
         l[i] = g[i];
+    {
+        static_assert(sizeof(WallSet) % 8 == 0, "WallSet is copied in 8-byte words");
+        const unsigned long long* gw = reinterpret_cast<const unsigned long long*>(B.walls);
+        unsigned long long* lw = reinterpret_cast<unsigned long long*>(&sW);
+        for (unsigned i = threadIdx.x; i < sizeof(WallSet) / 8; i += blockDim.x)
+            lw[i] = gw[i];
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         s_err_in = sC.err;
-        step_begin_body(P, B, sC);
+        step_begin_body(P, B, sC, sW);
         if (cond)
             cudaGraphSetConditional((cudaGraphConditionalHandle)cond, sC.rebuild_now);
     }
@@ -239,8 +248,7 @@ __global__ void __launch_bounds__(32) k_step_begin(Params P, Buffers B, unsigned
         atomicOr(&B.ctrl->err, sC.err);
 }
 
-__device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C) {
-    const WallSet& WS = *B.walls;
+__device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& B, Ctrl& C, const WallSet& WS) {
     if (C.sbox_pending) {  // the last rebuild measured the spheres' own box while binning them
         for (int k = 0; k < 6; k++)
             C.sbox[k] = C.sbox_next[k];
@@ -263,8 +271,10 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
         else if (C.since_rebuild > 60u)
             C.skin = fmax(C.skin / 1.3, P.skin);
     }
-    if (rebuild)
+    if (rebuild) {
         C.max_cand = 0u;
+        C.n_bnd = 0u;
+    }
     C.since_rebuild = rebuild ? 0u : C.since_rebuild + 1u;
     if (C.nrebuilds >= 1)
         C.init_stage = 0u;  // the checkpoint history was consumed by the first rebuild
@@ -342,7 +352,7 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
             if (!(ext[k] >= e))
                 ext[k] = e;
         }
-        int dim[3];
+        int dim[3], tdim[3];
         for (int it = 0; it < 400; it++) {
             double tot = 1.0;
             for (int k = 0; k < 3; k++) {
@@ -350,21 +360,25 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
                 d = (d < 1.0) ? 1.0 : d;
                 d = (d > 2097152.0) ? 2097152.0 : d;
                 dim[k] = (int)d;
-                tot *= d;
+                tdim[k] = (dim[k] + kTile - 1) / kTile;
+                tot *= P.tiled ? (double)(tdim[k] * kTile) : d;  // tiled: the cells of the partly filled border tiles count too
             }
             if (tot <= (double)P.cell_cap)
                 break;
             e *= 1.05;
         }
-        unsigned long long tot = (unsigned long long)dim[0] * dim[1] * dim[2];
+        unsigned long long tot = P.tiled ? (unsigned long long)tdim[0] * tdim[1] * tdim[2] * (unsigned long long)kTileCells
+                                         : (unsigned long long)dim[0] * dim[1] * dim[2];
         if (tot > P.cell_cap) {  // not reachable (400 x 5 % growth), but never index out of bounds
             dim[0] = dim[1] = dim[2] = 1;
-            tot = 1;
+            tdim[0] = tdim[1] = tdim[2] = 1;
+            tot = P.tiled ? (unsigned long long)kTileCells : 1ull;
         }
         for (int k = 0; k < 3; k++) {
             C.s_org[k] = mn[k] - 1e-6 * e;
             C.s_inv[k] = (double)dim[k] / ext[k];
             C.s_dim[k] = dim[k];
+            C.t_dim[k] = tdim[k];
         }
         C.s_ncell = (unsigned)tot;
         for (int k = 0; k < 3; k++) {
@@ -438,6 +452,15 @@ __device__ __forceinline__ int cell_coord(double x, double org, double inv, int 
     int c = (int)floor((x - org) * inv);
     return min(max(c, 0), dim - 1);
 }
+// Number of a search cell.  Plain grid: x fastest.  Tiled grid (Params::tiled): tiles of kTile^3 cells, tile by tile (x fastest
+// over the tiles), x fastest inside a tile -- the spheres of one tile are then one contiguous run of the storage order.
+__device__ __forceinline__ unsigned cell_index(const Params& P, const Ctrl& C, int cx, int cy, int cz) {
+    if (!P.tiled)
+        return (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
+    const int tx = cx / kTile, ty = cy / kTile, tz = cz / kTile;
+    const unsigned tile = (unsigned)((tz * C.t_dim[1] + ty) * C.t_dim[0] + tx);
+    return tile * (unsigned)kTileCells + (unsigned)((((cz % kTile) * kTile) + (cy % kTile)) * kTile + (cx % kTile));
+}
 
 __global__ void __launch_bounds__(256) k_bin_count(Params P, Buffers B) {
     Ctrl& C = *B.ctrl;
@@ -459,7 +482,7 @@ __global__ void __launch_bounds__(256) k_bin_count(Params P, Buffers B) {
         const int cx = cell_coord(p.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
         const int cy = cell_coord(p.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
         const int cz = cell_coord(p.z, C.s_org[2], C.s_inv[2], C.s_dim[2]);
-        h = (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
+        h = cell_index(P, C, cx, cy, cz);
         B.cell[i] = h;
     }
     // warp-aggregated histogram update: lanes that fall in the same cell elect a leader that issues one atomic;
@@ -644,7 +667,7 @@ __global__ void __launch_bounds__(256) k_mesh_transform(Buffers B, int m) {
 
 // cells reached by triangle t: AABB inflated by `reach`, culled by the distance of the cell centre to the triangle's plane
 template <class Visit>
-__device__ __forceinline__ void tri_cells(const Ctrl& C, const double* w, double reach, Visit visit) {
+__device__ __forceinline__ void tri_cells(const Params& P, const Ctrl& C, const double* w, double reach, Visit visit) {
     const V3 A = mk(w[0], w[1], w[2]), Bv = mk(w[3], w[4], w[5]), Cv = mk(w[6], w[7], w[8]);
     int lo[3], hi[3];
     const double mn[3] = {fmin(A.x, fmin(Bv.x, Cv.x)) - reach, fmin(A.y, fmin(Bv.y, Cv.y)) - reach, fmin(A.z, fmin(Bv.z, Cv.z)) - reach};
@@ -670,7 +693,7 @@ __device__ __forceinline__ void tri_cells(const Ctrl& C, const double* w, double
                     if (fabs(dot(c - A, n)) > slack)
                         continue;
                 }
-                visit((unsigned)((z * C.s_dim[1] + y) * C.s_dim[0] + x));
+                visit(cell_index(P, C, x, y, z));
             }
 }
 
@@ -682,7 +705,7 @@ __global__ void __launch_bounds__(256) k_tri_count(Params P, Buffers B) {
     if (t >= P.nT)
         return;
     const double reach = (P.rmax + 0.5 * P.skin_tri) * (1.0 + 1e-9);
-    tri_cells(C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) { atomicAdd(&B.tcell_count[cell], 1u); });
+    tri_cells(P, C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) { atomicAdd(&B.tcell_count[cell], 1u); });
 }
 
 __global__ void __launch_bounds__(256) k_tri_fill(Params P, Buffers B) {
@@ -693,7 +716,7 @@ __global__ void __launch_bounds__(256) k_tri_fill(Params P, Buffers B) {
     if (t >= P.nT)
         return;
     const double reach = (P.rmax + 0.5 * P.skin_tri) * (1.0 + 1e-9);
-    tri_cells(C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) {
+    tri_cells(P, C, B.tri_w + 9 * (size_t)t, reach, [&](unsigned cell) {
         // counts back down to zero: the histogram is clean again for the next rebuild
         const unsigned at = B.tcell_start[cell] + atomicSub(&B.tcell_count[cell], 1u) - 1u;
         if (at < P.tri_cap)
@@ -836,8 +859,10 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     const int cz = cell_coord(me.z, C.s_org[2], C.s_inv[2], C.s_dim[2]);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, C.s_dim[0] - 1);
     unsigned tj[kMaxNeighbors], ts[kMaxNeighbors];
+    unsigned short tc[kMaxNeighbors];  // tiled grid: (box cell, rank in cell) of the candidate, relative to this sphere's tile
+    const int tx0 = (cx / kTile) * kTile, ty0 = (cy / kTile) * kTile, tz0 = (cz / kTile) * kTile;
     int cnt = 0;
-    bool overflow = false;
+    bool overflow = false, has_ghost = false;
     for (int dz = -1; dz <= 1; dz++) {
         const int z = cz + dz;
         if (z < 0 || z >= C.s_dim[2])
@@ -846,25 +871,39 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
             const int y = cy + dy;
             if (y < 0 || y >= C.s_dim[1])
                 continue;
-            const unsigned row = (unsigned)((z * C.s_dim[1] + y) * C.s_dim[0]);
-            const unsigned jb = B.cell_start[row + x0], je = B.cell_start[row + x1 + 1];
-            for (unsigned j = jb; j < je; j++) {
-                if (j == s)
-                    continue;
-                const double4 pj = pos[j];
-                const double dx = pj.x - me.x, dy2 = pj.y - me.y, dz2 = pj.z - me.z;
-                const double d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
-                const double rs = me.w + pj.w + C.skin;
-                if (d2 > rs * rs * (1.0 + 1e-12))
-                    continue;
-                if (me_fixed && (vel[j].meta & FLAG_FIXED))
-                    continue;
-                if (cnt < P.Kn) {
-                    tj[cnt] = j;
-                    ts[cnt] = vel[j].sid;
-                    cnt++;
+            // plain grid: the three cells of a row are one run of the storage order; tiled grid: cell by cell
+            for (int x = x0; x <= x1; x += P.tiled ? 1 : 3) {
+                unsigned jb, je, box = 0u;
+                if (P.tiled) {
+                    const unsigned ci = cell_index(P, C, x, y, z);
+                    jb = B.cell_start[ci];
+                    je = B.cell_start[ci + 1];
+                    box = (unsigned)(((z - tz0 + 1) * kBox + (y - ty0 + 1)) * kBox + (x - tx0 + 1));
                 } else {
-                    overflow = true;
+                    const unsigned row = (unsigned)((z * C.s_dim[1] + y) * C.s_dim[0]);
+                    jb = B.cell_start[row + x0];
+                    je = B.cell_start[row + x1 + 1];
+                }
+                for (unsigned j = jb; j < je; j++) {
+                    if (j == s)
+                        continue;
+                    const double4 pj = pos[j];
+                    const double dx = pj.x - me.x, dy2 = pj.y - me.y, dz2 = pj.z - me.z;
+                    const double d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
+                    const double rs = me.w + pj.w + C.skin;
+                    if (d2 > rs * rs * (1.0 + 1e-12))
+                        continue;
+                    if (me_fixed && (vel[j].meta & FLAG_FIXED))
+                        continue;
+                    if (cnt < P.Kn) {
+                        tj[cnt] = j;
+                        ts[cnt] = vel[j].sid;
+                        tc[cnt] = (unsigned short)((box << kCodeRankBits) | min(j - jb, kCodeNoRank));
+                        has_ghost |= (vel[j].meta & FLAG_GHOST) != 0;
+                        cnt++;
+                    } else {
+                        overflow = true;
+                    }
                 }
             }
         }
@@ -875,20 +914,23 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     // independent of the storage order
     for (int a = 1; a < cnt; a++) {
         const unsigned kj = tj[a], ks = ts[a];
+        const unsigned short kc = tc[a];
         int b = a - 1;
         while (b >= 0 && ts[b] > ks) {
             tj[b + 1] = tj[b];
             ts[b + 1] = ts[b];
+            tc[b + 1] = tc[b];
             b--;
         }
         tj[b + 1] = kj;
         ts[b + 1] = ks;
+        tc[b + 1] = kc;
     }
     // mesh triangles within reach (r + skin/2; the mesh's own motion uses up skin like a wall's), ascending triangle
     // index, behind the sphere candidates.  ts[] keeps the staging key (shape id - shape_base, wrapping for triangles).
     int tcnt = 0;
     if (P.nT && B.meshes->enabled && !me_fixed) {
-        const unsigned cell = (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
+        const unsigned cell = cell_index(P, C, cx, cy, cz);
         const unsigned tb = B.tcell_start[cell], te = min(B.tcell_start[cell + 1], P.tri_cap);
         const double reach = me.w + 0.5 * P.skin_tri + 1e-9 * (me.w + fabs(me.x) + fabs(me.y) + fabs(me.z));
         const V3 c = mk(me.x, me.y, me.z);
@@ -921,6 +963,9 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         const unsigned my_sid = vel[s].sid;
         for (int k = 0; k < cnt + tcnt; k++)
             B.nl[(size_t)k * P.Np + s] = tj[k] | ((k < cnt && ts[k] > my_sid) ? kHiFlag : 0u);
+        if (P.tiled)
+            for (int k = 0; k < cnt; k++)
+                B.nl16[(size_t)k * P.Np + s] = (unsigned short)(tc[k] | (ts[k] > my_sid ? kCodeHi : 0u));
     }
     if ((unsigned)(cnt + tcnt) > C.max_cand)
         atomicMax(&C.max_cand, (unsigned)(cnt + tcnt));
@@ -954,7 +999,9 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                 wc |= 1u << w;
         }
     }
-    B.ncnt[s] = (unsigned)cnt | (wc << 8) | ((unsigned)tcnt << 24);
+    B.ncnt[s] = (unsigned)cnt | (has_ghost ? kBndFlag : 0u) | (wc << 8) | ((unsigned)tcnt << 24);
+    if (has_ghost && B.bnd_list)  // slab mode: the forces of these spheres wait for the halo, everybody else's do not
+        B.bnd_list[atomicAdd(&C.n_bnd, 1u)] = s;
     // staged history -> slots of the new list (a record whose partner is no longer a candidate is dropped: that
     // contact has broken)
     if (B.hist) {
@@ -1670,7 +1717,7 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 // FAST: 0 = generic law (contact_force), 1 = Hertz with material properties, 2 = Hertz with user coefficients
 template <bool HIST, bool ROLL, int FAST, bool REC, bool MESH>
 __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS : DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
-                                                                      const __grid_constant__ Buffers B) {
+                                                                      const __grid_constant__ Buffers B, const unsigned pass) {
     __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
     __shared__ unsigned char cslot[kMaxSlots * kForceThreads];  // its index in the candidate list (= history slot)
     Ctrl& C = *B.ctrl;
@@ -1678,8 +1725,14 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
     const double4* __restrict__ pos_in = B.pos[src];
     const VelRec* __restrict__ vel_in = B.vel[src];
     const unsigned tid = threadIdx.x;
-    const unsigned s = blockIdx.x * kForceThreads + tid;
-    const bool valid = s < P.N;
+    // pass 0: every sphere.  Slab mode with the direct halo splits the step in two: pass 1 = every sphere without a ghost among
+    // its candidates (runs while the halo is still in flight), pass 2 = the others (Buffers::bnd_list), after the halo has landed.
+    unsigned s = blockIdx.x * kForceThreads + tid;
+    if (pass == 2u)
+        s = (s < C.n_bnd) ? B.bnd_list[s] : P.N;
+    bool valid = s < P.N;
+    if (pass == 1u && valid && (B.ncnt[s] & kBndFlag))
+        valid = false;
     const GridDev& G = C.mc;
 
     double4 me = make_double4(0, 0, 0, 1.0);
@@ -1703,7 +1756,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             }
         }
         const unsigned ncw = B.ncnt[s];
-        const unsigned nc = ncw & 0xFFu;
+        const unsigned nc = ncw & 0x7Fu;
         wcand = (ncw >> 8) & 0xFFFFu;
         if (MESH) {
             tfirst = nc;
@@ -1760,12 +1813,12 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
     const unsigned long long amask_old = mv.amask;
     unsigned wmask_new = 0u;
     unsigned long long amask_new = 0ull;
-    const double my_mass = sphere_mass(P, me.w);
+    const double my_mass0 = sphere_mass(P, me.w);
     V3 Fsum = mk(0, 0, 0), Tsum = mk(0, 0, 0);
     unsigned ncontacts = 0;
     double4* const hcol = HIST ? B.hist + s : nullptr;            // my column of history records
     double* const rcol = (HIST && B.hrel) ? B.hrel + s : nullptr;
-    const V3 mpos = mk(me.x, me.y, me.z);
+    const V3 mpos0 = mk(me.x, me.y, me.z);
 
     if (valid && !ghost) {
         // ---- walls first: body 1 = wall body (lower id), body 2 = this sphere
@@ -1781,19 +1834,19 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             Geom g;
             bool hit;
             if (W.type == WALL_ZCYL) {
-                hit = zcyl_sphere_dev(W, mpos, me.w, g);
+                hit = zcyl_sphere_dev(W, mpos0, me.w, g);
             } else if (W.type == WALL_SPHERE) {
-                hit = ball_sphere_dev(W, mpos, me.w, g);
+                hit = ball_sphere_dev(W, mpos0, me.w, g);
             } else if (W.type == WALL_ZCONE) {
-                hit = zcone_sphere_dev(W, mpos, me.w, g);
+                hit = zcone_sphere_dev(W, mpos0, me.w, g);
             } else if (W.type == WALL_BOX) {
                 // broadphase AABB overlap on origin-offset boxes (ChCollisionUtils.h:83-87)
                 if (!(amin[0] <= G.wmax[w][0] && G.wmin[w][0] <= amax[0] && amin[1] <= G.wmax[w][1] &&
                       G.wmin[w][1] <= amax[1] && amin[2] <= G.wmax[w][2] && G.wmin[w][2] <= amax[2]))
                     continue;
-                hit = box_sphere_dev(W, mpos, me.w, g);
+                hit = box_sphere_dev(W, mpos0, me.w, g);
             } else {
-                hit = plane_sphere_dev(W, mpos, me.w, g);
+                hit = plane_sphere_dev(W, mpos0, me.w, g);
             }
             if (!hit)
                 continue;
@@ -1824,7 +1877,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 b1.pos = mk(W.rc[0], W.rc[1], W.rc[2]);
                 b1.w = mk(W.omg[0], W.omg[1], W.omg[2]);
             }
-            Body b2{mpos, mv.v, mv.w, my_mass};
+            Body b2{mpos0, mv.v, mv.w, my_mass0};
             V3 F, T1, T2;
             CInfoOut ci;
             const bool want_ci = REC && B.cinfo != nullptr;
@@ -1849,7 +1902,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
 
     if (MESH && tcand && !ghost) {
         MeshOut mo;
-        mesh_contacts<HIST, ROLL, REC>(P, B, s, sid, me, mv.v, mv.w, my_mass, tfirst, tcand, amask_old, mo);
+        mesh_contacts<HIST, ROLL, REC>(P, B, s, sid, me, mv.v, mv.w, my_mass0, tfirst, tcand, amask_old, mo);
         Fsum = Fsum + mo.F;
         Tsum = Tsum + mo.T;
         amask_new |= mo.mask;
@@ -1927,7 +1980,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             V3 F, T;
             CInfoOut ci;
             const bool want_ci = REC && B.cinfo != nullptr;
-            sphere_contact_fast<HIST, ROLL, FAST == 1>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass,
+            sphere_contact_fast<HIST, ROLL, FAST == 1>(P, P.comp[0], n, dist, me.w, pj.w, mv.v, mv.w, ov.v, ov.w, my_mass0,
                                             sphere_mass(P, pj.w), me1, disp, steps, !had, F, T, want_ci ? &ci : nullptr);
             if (want_ci)
                 store_cinfo(B.cinfo + (hi + s) * kCInfo, ci.fn, ci.ft, ci.tr, ci.vrot, ci.tc);
@@ -1943,7 +1996,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             Body b1, b2;
             double r1, r2;
             {
-                Body bm{mpos, mv.v, mv.w, my_mass};
+                Body bm{mpos0, mv.v, mv.w, my_mass0};
                 Body bo{mk(pj.x, pj.y, pj.z), ov.v, ov.w, sphere_mass(P, pj.w)};
                 b1 = me1 ? bm : bo;
                 b2 = me1 ? bo : bm;
@@ -2016,6 +2069,10 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
 
         // ---- time integration ----
         const bool fixed = (flags & (FLAG_FIXED | FLAG_GHOST)) != 0;
+        // own state re-derived from `me` here (the lean phase 2 parks it in shared memory and reloads it: nothing of it stays
+        // live in registers across the contact loop)
+        const V3 mpos = mk(me.x, me.y, me.z);
+        const double my_mass = sphere_mass(P, me.w);
         const double hdt = P.dt;
         const double inv_m = 1.0 / my_mass;
         const double inv_I = 1.0 / (0.4 * my_mass * me.w * me.w);
@@ -2086,6 +2143,465 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         if (e > C.max_dx2)
             atomicMax(&C.max_dx2, e);
     }
+}
+
+// --------------------------------------------------------------------------------------------
+// Tile force kernel: the same step as k_force_integrate, with the neighbour bins staged in shared memory.
+//
+// One block per tile of the tiled search grid (kTile^3 cells, Params::tiled).  The spheres of the tile are a contiguous run
+// of the storage order; every candidate of every one of them lies in the tile's box (the tile plus a one-cell halo,
+// kBox^3 cells).  The block copies position, radius, velocity and angular velocity of all spheres of the box into shared
+// memory once (coalesced runs, 80 bytes per sphere); after that the exact narrowphase on the candidates (phase 1) and the
+// partner state of every contact (phase 2) are shared-memory reads addressed by the 16-bit candidate code written at list
+// build time (box cell, rank in cell), instead of three divergent global gathers per contact.  Only the history rows (own
+// column, read and written once) and the sphere's own record still go to global memory.  Arithmetic, contact order and
+// therefore every bit of the result are those of k_force_integrate (checked by the parity tests, which run both).
+// Restrictions: Hertz fast paths (FAST 1 / 2), no meshes, no recording -- everything else runs k_force_integrate.
+// --------------------------------------------------------------------------------------------
+#ifndef DEMB200_TILE_THREADS
+#define DEMB200_TILE_THREADS 160
+#endif
+#ifndef DEMB200_TILE_CAP
+#define DEMB200_TILE_CAP 640  /* sphere records staged per block; a box holds ~430 - 600 of them in a dense bed */
+#endif
+#ifndef DEMB200_TILE_MINBLOCKS
+#define DEMB200_TILE_MINBLOCKS 3
+#endif
+constexpr int kTileThreads = DEMB200_TILE_THREADS;
+constexpr int kTileCap = DEMB200_TILE_CAP;
+struct __align__(16) TileRec {
+    double x, y, z, r, vx, vy, vz, wx, wy, wz;
+};
+constexpr size_t kTileSmemBytes = (size_t)kTileCap * sizeof(TileRec) + (size_t)kMaxSlots * kTileThreads * 3;
+
+// walls of one sphere: body 1 = wall body (lower id), body 2 = the sphere (same code path as in k_force_integrate)
+template <bool HIST, bool ROLL>
+__device__ __forceinline__ void wall_contacts(const Params& P, const Buffers& B, Ctrl& C, const double4 me, const V3 v, const V3 w,
+                                              unsigned wcand, const unsigned wmask_old, double4* const hcol, double* const rcol,
+                                              const double my_mass, V3& Fsum, V3& Tsum, unsigned& wmask_new) {
+    const GridDev& G = C.mc;
+    const V3 mpos = mk(me.x, me.y, me.z);
+    double amin[3], amax[3];
+    if (wcand)
+        sphere_aabb_offset(me, G.origin, amin, amax);
+    while (wcand) {
+        const int wi = __ffs(wcand) - 1;
+        wcand &= wcand - 1;
+        const Wall& W = B.walls->w[wi];
+        if (!W.enabled)
+            continue;
+        Geom g;
+        bool hit;
+        if (W.type == WALL_ZCYL) {
+            hit = zcyl_sphere_dev(W, mpos, me.w, g);
+        } else if (W.type == WALL_SPHERE) {
+            hit = ball_sphere_dev(W, mpos, me.w, g);
+        } else if (W.type == WALL_ZCONE) {
+            hit = zcone_sphere_dev(W, mpos, me.w, g);
+        } else if (W.type == WALL_BOX) {
+            if (!(amin[0] <= G.wmax[wi][0] && G.wmin[wi][0] <= amax[0] && amin[1] <= G.wmax[wi][1] &&
+                  G.wmin[wi][1] <= amax[1] && amin[2] <= G.wmax[wi][2] && G.wmin[wi][2] <= amax[2]))
+                continue;
+            hit = box_sphere_dev(W, mpos, me.w, g);
+        } else {
+            hit = plane_sphere_dev(W, mpos, me.w, g);
+        }
+        if (!hit || g.depth >= 0)
+            continue;
+        Hist h{mk(0, 0, 0), 0.0, 0.0, true};
+        double steps = 0.0;
+        const size_t hi = (size_t)(P.Kn + wi) * P.Np;
+        if (HIST && ((wmask_old >> wi) & 1u)) {
+            const double4 r = ld256v(hcol + hi);
+            h.disp = mk(r.x, r.y, r.z);
+            steps = r.w;
+            h.dur = steps * P.dt;
+            if (rcol)
+                h.relvel0 = rcol[hi];
+            h.isnew = false;
+            steps += 1.0;
+        }
+        Body b1{mk(0, 0, 0), mk(W.vel[0], W.vel[1], W.vel[2]), mk(0, 0, 0), P.wall_mass};
+        if (W.omg[0] != 0.0 || W.omg[1] != 0.0 || W.omg[2] != 0.0) {
+            b1.pos = mk(W.rc[0], W.rc[1], W.rc[2]);
+            b1.w = mk(W.omg[0], W.omg[1], W.omg[2]);
+        }
+        Body b2{mpos, v, w, my_mass};
+        V3 F, T1, T2;
+        contact_force<HIST, ROLL>(P, P.comp[1], b1, b2, g, h, F, T1, T2);
+        Fsum = Fsum + F;
+        Tsum = Tsum + T2;
+        if (P.track_wall_forces) {
+            atomicAdd(&C.wall_force[wi][0], -F.x);
+            atomicAdd(&C.wall_force[wi][1], -F.y);
+            atomicAdd(&C.wall_force[wi][2], -F.z);
+        }
+        if (HIST) {
+            st256(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
+            if (rcol)
+                rcol[hi] = h.relvel0;
+            wmask_new |= 1u << wi;
+        }
+    }
+}
+
+// time integration of one sphere and the store of its new record (same arithmetic as the tail of k_force_integrate)
+__device__ __forceinline__ V3 integrate_store(const Params& P, const Buffers& B, Ctrl& C, unsigned src, unsigned dst, unsigned s,
+                                              const double4 me, const V3 v0, const V3 w0, unsigned sid, unsigned flags, const V3 Fsum,
+                                              const V3 Tsum, unsigned wmask_new, unsigned long long amask_new) {
+    const V3 mpos = mk(me.x, me.y, me.z);
+    const double my_mass = sphere_mass(P, me.w);
+    const bool fixed = (flags & (FLAG_FIXED | FLAG_GHOST)) != 0;
+    const double hdt = P.dt;
+    const double inv_m = 1.0 / my_mass;
+    const double inv_I = 1.0 / (0.4 * my_mass * me.w * me.w);
+    const V3 gv = mk(P.g[0], P.g[1], P.g[2]);
+    V3 x = mpos;
+    V3 vn = v0, wn = w0;
+    if (!fixed) {
+        if (P.integrator == 2) {
+            V3 hf = hdt * (gv * my_mass) + hdt * Fsum;
+            vn = v0 + inv_m * hf;
+            wn = w0 + inv_I * (hdt * Tsum);
+            x = x + vn * hdt;
+        } else {
+            const V3 acc = gv + inv_m * Fsum;
+            const V3 alp = inv_I * Tsum;
+            if (P.integrator == 3) {
+                x = x + hdt * (v0 + 0.5 * hdt * acc);
+                vn = v0 + hdt * acc;
+                wn = w0 + hdt * alp;
+            } else if (P.integrator == 0) {
+                x = x + hdt * v0;
+                vn = v0 + hdt * acc;
+                wn = w0 + hdt * alp;
+            } else {
+                const double2* ap = reinterpret_cast<const double2*>(B.acc[src] + 6 * (size_t)s);
+                const double2 o0 = ap[0], o1 = ap[1], o2 = ap[2];
+                const V3 ao = mk(o0.x, o0.y, o1.x), lo = mk(o1.y, o2.x, o2.y);
+                const double beta = 28.0 / 27.0;
+                x = x + hdt * (v0 + hdt * (beta * acc + (0.5 - beta) * ao));
+                vn = v0 + hdt * (1.5 * acc - 0.5 * ao);
+                wn = w0 + hdt * (1.5 * alp - 0.5 * lo);
+                double2* aw = reinterpret_cast<double2*>(B.acc[dst] + 6 * (size_t)s);
+                aw[0] = make_double2(acc.x, acc.y);
+                aw[1] = make_double2(acc.z, alp.x);
+                aw[2] = make_double2(alp.y, alp.z);
+            }
+        }
+    } else if (P.integrator == 1) {
+        double2* aw = reinterpret_cast<double2*>(B.acc[dst] + 6 * (size_t)s);
+        aw[0] = aw[1] = aw[2] = make_double2(0.0, 0.0);
+    }
+    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z)))
+        atomicOr(&C.err, ERR_NAN);
+    st256(B.pos[dst] + s, make_double4(x.x, x.y, x.z, me.w));
+    store_vel(B.vel[dst], s, vn, wn, sid, flags | (wmask_new << 8), amask_new);
+    return x;
+}
+
+template <bool HIST, bool ROLL, int FAST>
+__global__ void __launch_bounds__(kTileThreads, DEMB200_TILE_MINBLOCKS) k_force_tile(const __grid_constant__ Params P,
+                                                                                   const __grid_constant__ Buffers B, const unsigned pass) {
+    static_assert(FAST == 1 || FAST == 2, "the tile kernel carries the Hertz fast paths only");
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    TileRec* const s_rec = reinterpret_cast<TileRec*>(tile_smem);
+    unsigned short* const clist = reinterpret_cast<unsigned short*>(s_rec + kTileCap);           // [kMaxSlots][kTileThreads] code of the k-th touching candidate
+    unsigned char* const cslot = reinterpret_cast<unsigned char*>(clist + kMaxSlots * kTileThreads);  // its candidate slot (= history slot)
+    __shared__ unsigned s_off[kBoxCells + 1];   // first staged record of every box cell
+    __shared__ unsigned s_gstart[kBoxCells];    // its first sphere in the storage order
+    Ctrl& C = *B.ctrl;
+    const unsigned tid = threadIdx.x;
+    const unsigned ntiles = (unsigned)(C.t_dim[0] * C.t_dim[1] * C.t_dim[2]);
+    const unsigned tile = blockIdx.x;
+    if (tile >= ntiles)
+        return;
+    const unsigned t_begin = B.cell_start[(size_t)tile * kTileCells], t_end = B.cell_start[(size_t)(tile + 1) * kTileCells];
+    if (t_end <= t_begin)
+        return;  // empty tile (the whole block leaves)
+    if (pass == 2u) {  // only the tiles that hold a sphere with a ghost candidate have work in the second pass
+        bool any = false;
+        for (unsigned i = t_begin + threadIdx.x; i < t_end; i += kTileThreads)
+            any |= (B.ncnt[i] & kBndFlag) != 0u;
+        if (!__syncthreads_or(any))
+            return;
+    }
+    const unsigned src = C.f_src, dst = src ^ 1u;
+    const double4* __restrict__ pos_in = B.pos[src];
+    const VelRec* __restrict__ vel_in = B.vel[src];
+
+    // ---- stage the box: cell ranges, exclusive scan, records
+    {
+        const int tx = (int)(tile % (unsigned)C.t_dim[0]), ty = (int)((tile / (unsigned)C.t_dim[0]) % (unsigned)C.t_dim[1]),
+                  tz = (int)(tile / (unsigned)(C.t_dim[0] * C.t_dim[1]));
+        for (unsigned c = tid; c < (unsigned)kBoxCells; c += kTileThreads) {
+            const int x = tx * kTile - 1 + (int)(c % kBox), y = ty * kTile - 1 + (int)((c / kBox) % kBox),
+                      z = tz * kTile - 1 + (int)(c / (kBox * kBox));
+            unsigned gs = 0u, n = 0u;
+            if (x >= 0 && y >= 0 && z >= 0 && x < C.s_dim[0] && y < C.s_dim[1] && z < C.s_dim[2]) {
+                const unsigned ci = cell_index(P, C, x, y, z);
+                gs = B.cell_start[ci];
+                n = B.cell_start[ci + 1] - gs;
+            }
+            s_gstart[c] = gs;
+            s_off[c + 1] = n;
+        }
+        if (tid == 0)
+            s_off[0] = 0u;
+        __syncthreads();
+        if (tid < 32) {  // inclusive scan of s_off[1 .. kBoxCells] by one warp, kBoxCells / 32 (rounded up) entries per lane
+            constexpr unsigned per = (kBoxCells + 31) / 32;
+            unsigned sum = 0u;
+            for (unsigned q = 0; q < per; q++) {
+                const unsigned i = tid * per + q;
+                if (i < (unsigned)kBoxCells)
+                    sum += s_off[i + 1];
+            }
+            unsigned inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= (unsigned)o)
+                    inc += t;
+            }
+            unsigned run = inc - sum;
+            for (unsigned q = 0; q < per; q++) {
+                const unsigned i = tid * per + q;
+                if (i < (unsigned)kBoxCells) {
+                    run += s_off[i + 1];
+                    s_off[i + 1] = run;
+                }
+            }
+        }
+        __syncthreads();
+        for (unsigned c = tid; c < (unsigned)kBoxCells; c += kTileThreads) {
+            const unsigned o = s_off[c], gs = s_gstart[c];
+            const unsigned n = min(s_off[c + 1] - o, (unsigned)kTileCap > o ? (unsigned)kTileCap - o : 0u);
+            constexpr unsigned kS = 4;  // records of one cell in flight together (a cell holds ~2 spheres)
+            for (unsigned r0 = 0; r0 < n; r0 += kS) {
+                double4 p[kS], q0[kS];
+                double2 q1[kS];
+#pragma unroll
+                for (unsigned u = 0; u < kS; u++)
+                    if (r0 + u < n) {
+                        p[u] = ld256(pos_in + gs + r0 + u);
+                        q0[u] = ld256(vel_in + gs + r0 + u);
+                        q1[u] = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(vel_in + gs + r0 + u) + 32);
+                    }
+#pragma unroll
+                for (unsigned u = 0; u < kS; u++)
+                    if (r0 + u < n) {
+                        // TileRec = (x y z r | vx vy vz wx | wy wz): 80 bytes, five 16-byte shared stores
+                        double2* d = reinterpret_cast<double2*>(s_rec + o + r0 + u);
+                        d[0] = make_double2(p[u].x, p[u].y);
+                        d[1] = make_double2(p[u].z, p[u].w);
+                        d[2] = make_double2(q0[u].x, q0[u].y);
+                        d[3] = make_double2(q0[u].z, q0[u].w);
+                        d[4] = q1[u];
+                    }
+            }
+        }
+    }
+    // A box that does not fit the staging buffer, or a cell too crowded for the 6-bit rank of the candidate code, sends the
+    // whole block through the instantiation that can fall back to the global arrays.  (Kept out of the common instantiation:
+    // a never-taken global load at the head of the contact loop would share its scoreboard with the history prefetch.)
+    bool crowded = false;
+    for (unsigned c = tid; c < (unsigned)kBoxCells; c += kTileThreads)
+        crowded |= (s_off[c + 1] - s_off[c]) >= kCodeNoRank;
+    const bool slow_block = __syncthreads_or(crowded || s_off[kBoxCells] > (unsigned)kTileCap) != 0;  // also the barrier after staging
+
+    const unsigned nt = t_end - t_begin;
+    auto rounds = [&](auto slow_tag) {
+    constexpr bool SLOW = decltype(slow_tag)::value;
+    for (unsigned base = 0; base < nt; base += kTileThreads) {
+        if (base + (tid & ~31u) >= nt)
+            break;  // this warp has no sphere in this round (warp-uniform)
+        const unsigned s = t_begin + base + tid;
+        bool valid = base + tid < nt;
+        if (pass != 0u && valid && (((B.ncnt[s] & kBndFlag) != 0u) != (pass == 2u)))
+            valid = false;  // pass 1: spheres without a ghost candidate; pass 2: the others (see k_force_integrate)
+        double4 me = make_double4(0, 0, 0, 1.0);
+        VelVal mv;
+        mv.v = mk(0, 0, 0); mv.w = mk(0, 0, 0); mv.sid = 0; mv.meta = 0; mv.amask = 0ull;
+        int cnt = 0;
+        unsigned wcand = 0;
+        // partner record of a candidate code: staged copy, or (box overflow / rank not encodable) the global arrays
+        auto partner_index = [&](unsigned code, unsigned slot, unsigned& idx) -> bool {
+            const unsigned c = (code >> kCodeRankBits) & 0xFFu, r = code & kCodeNoRank;
+            idx = s_off[c] + r;
+            if constexpr (!SLOW) {
+                return true;
+            } else {
+                if (r != kCodeNoRank && idx < (unsigned)kTileCap)
+                    return true;
+                idx = (r != kCodeNoRank) ? s_gstart[c] + r : (B.nl[(size_t)slot * P.Np + s] & ~(kHiFlag | kTriFlag));
+                return false;
+            }
+        };
+        if (valid) {
+            me = ld256(pos_in + s);
+            mv = load_vel(vel_in, s);
+            const unsigned ncw = B.ncnt[s];
+            const unsigned nc = ncw & 0x7Fu;
+            wcand = (ncw >> 8) & 0xFFFFu;
+            const unsigned short* __restrict__ nl16 = B.nl16 + s;
+            // ---- phase 1: exact sphere_sphere test (ChNarrowphasePRIMS.cpp:50-59) on the candidates, positions from the box.
+            //      The candidate codes are a coalesced global stream: batches of kP1 of them are in flight together.
+            constexpr int kP1 = 8;
+            for (unsigned k0 = 0; k0 < nc; k0 += kP1) {
+                unsigned codes[kP1];
+#pragma unroll
+                for (int u = 0; u < kP1; u++)
+                    codes[u] = (k0 + u < nc) ? (unsigned)nl16[(size_t)(k0 + u) * P.Np] : 0xFFFFFFFFu;
+#pragma unroll
+                for (int u = 0; u < kP1; u++) {
+                    const unsigned code = codes[u];
+                    if (code == 0xFFFFFFFFu)
+                        continue;
+                    const unsigned k = k0 + u;
+                    unsigned idx;
+                    double4 pp;
+                    if (partner_index(code, k, idx)) {
+                        const double2* q = reinterpret_cast<const double2*>(s_rec + idx);
+                        const double2 a = q[0], b = q[1];
+                        pp = make_double4(a.x, a.y, b.x, b.y);
+                    } else {
+                        pp = ld256(pos_in + idx);
+                    }
+                    const V3 d = mk(__dsub_rn(pp.x, me.x), __dsub_rn(pp.y, me.y), __dsub_rn(pp.z, me.z));
+                    const double dist2 = dot_rn(d, d);
+                    const double rs = __dadd_rn(me.w, pp.w);
+                    if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
+                        continue;
+                    if (cnt < kMaxSlots) {
+                        clist[cnt * kTileThreads + tid] = (unsigned short)code;
+                        cslot[cnt * kTileThreads + tid] = (unsigned char)k;
+                    }
+                    cnt++;
+                }
+            }
+            if (cnt > kMaxSlots) {
+                atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
+                cnt = kMaxSlots;
+            }
+        }
+        const unsigned sid = mv.sid;
+        const unsigned flags = mv.meta & 0xFFu;
+        const bool ghost = (flags & FLAG_GHOST) != 0;
+        if (ghost)
+            cnt = 0;
+        const unsigned wmask_old = (mv.meta >> 8) & 0xFFFFu;
+        const unsigned long long amask_old = mv.amask;
+        unsigned wmask_new = 0u;
+        unsigned long long amask_new = 0ull;
+        V3 Fsum = mk(0, 0, 0), Tsum = mk(0, 0, 0);
+        double4* const hcol = HIST ? B.hist + s : nullptr;
+        double* const rcol = (HIST && B.hrel) ? B.hrel + s : nullptr;
+        if (valid && !ghost && wcand)
+            wall_contacts<HIST, ROLL>(P, B, C, me, mv.v, mv.w, wcand, wmask_old, hcol, rcol, sphere_mass(P, me.w), Fsum, Tsum, wmask_new);
+
+        // ---- phase 2: all lanes evaluate their k-th sphere contact together (stable-id order); only the history record of the
+        //      next contact is prefetched -- the partner state is a shared-memory read
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        double4 hr_next = make_double4(0, 0, 0, 0);
+        if (HIST && cnt > 0) {
+            const unsigned s0 = cslot[tid];
+            if ((amask_old >> s0) & 1ull)
+                hr_next = ld256v(hcol + (size_t)s0 * P.Np);
+        }
+        const double my_mass = sphere_mass(P, me.w);
+        for (int k = 0; k < maxc; k++) {
+            if (k >= cnt)
+                continue;
+            const unsigned code = clist[k * kTileThreads + tid];
+            const unsigned slot = cslot[k * kTileThreads + tid];
+            const bool me1 = (code & kCodeHi) != 0;
+            double4 hr = hr_next;
+            if (HIST && k + 1 < cnt) {
+                const unsigned sn = cslot[(k + 1) * kTileThreads + tid];
+                if ((amask_old >> sn) & 1ull)
+                    hr_next = ld256v(hcol + (size_t)sn * P.Np);
+            }
+            unsigned idx;
+            double px, py, pz, pr;
+            V3 vb, wb;
+            if (partner_index(code, slot, idx)) {
+                const double2* q = reinterpret_cast<const double2*>(s_rec + idx);
+                const double2 a = q[0], b = q[1], c2 = q[2], d2_ = q[3], e2 = q[4];
+                px = a.x; py = a.y; pz = b.x; pr = b.y;
+                vb = mk(c2.x, c2.y, d2_.x);
+                wb = mk(d2_.y, e2.x, e2.y);
+            } else {
+                const double4 pj = ld256(pos_in + idx);
+                const double4 q0 = ld256(vel_in + idx);
+                const double2 q1 = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(vel_in + idx) + 32);
+                px = pj.x; py = pj.y; pz = pj.z; pr = pj.w;
+                vb = mk(q0.x, q0.y, q0.z);
+                wb = mk(q0.w, q1.x, q1.y);
+            }
+            const bool had = HIST && ((amask_old >> slot) & 1ull);
+            const size_t hi = (size_t)slot * P.Np;
+            const V3 delta = mk(__dsub_rn(px, me.x), __dsub_rn(py, me.y), __dsub_rn(pz, me.z));
+            const double d2 = dot_rn(delta, delta);
+            const double inv_d = fast_rsqrt(d2);
+            const double dist = d2 * inv_d;
+            if (dist - __dadd_rn(me.w, pr) >= 0)
+                continue;
+            const V3 n = delta * inv_d;
+            V3 disp = mk(hr.x, hr.y, hr.z);
+            double steps = hr.w;
+            if (!had) {
+                disp = mk(0, 0, 0);
+                steps = 0.0;
+            } else if (!me1) {
+                disp = -disp;  // canonical (body 1 -> body 2) to my frame
+            }
+            V3 F, T;
+            sphere_contact_fast<HIST, ROLL, FAST == 1>(P, P.comp[0], n, dist, me.w, pr, mv.v, mv.w, vb, wb, my_mass, sphere_mass(P, pr), me1,
+                                                       disp, steps, !had, F, T);
+            Fsum = Fsum + F;
+            Tsum = Tsum + T;
+            if (HIST) {
+                if (!me1)
+                    disp = -disp;
+                st256(hcol + hi, make_double4(disp.x, disp.y, disp.z, steps));
+                amask_new |= 1ull << slot;
+            }
+        }
+
+        double nmnx = CUDART_INF, nmny = CUDART_INF, nmnz = CUDART_INF, nmxx = -CUDART_INF, nmxy = -CUDART_INF, nmxz = -CUDART_INF;
+        double dx2 = 0.0;
+        if (valid) {
+            if (HIST && __popcll(amask_new) + __popc(wmask_new) > P.K)
+                atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
+            const V3 x = integrate_store(P, B, C, src, dst, s, me, mv.v, mv.w, sid, flags, Fsum, Tsum, wmask_new, amask_new);
+            if (!ghost) {
+                nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
+                nmxx = x.x + me.w; nmxy = x.y + me.w; nmxz = x.z + me.w;
+            }
+            const V3 dxv = x - mk(me.x, me.y, me.z);
+            dx2 = dot(dxv, dxv);
+        }
+        {
+            const bool grows = nmnx < dec_ord(C.bbox[0]) || nmny < dec_ord(C.bbox[1]) || nmnz < dec_ord(C.bbox[2]) ||
+                               nmxx > dec_ord(C.bbox[3]) || nmxy > dec_ord(C.bbox[4]) || nmxz > dec_ord(C.bbox[5]);
+            if (__any_sync(0xffffffffu, grows))
+                block_bbox_commit(nmnx, nmny, nmnz, nmxx, nmxy, nmxz, C.bbox);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            dx2 = fmax(dx2, __shfl_xor_sync(0xffffffffu, dx2, o));
+        if ((tid & 31) == 0) {
+            const unsigned long long e = (unsigned long long)__double_as_longlong(dx2);
+            if (e > C.max_dx2)
+                atomicMax(&C.max_dx2, e);
+        }
+    }
+    };  // rounds
+    if (slow_block)
+        rounds(std::true_type{});
+    else
+        rounds(std::false_type{});
 }
 
 // --------------------------------------------------------------------------------------------
@@ -2435,9 +2951,13 @@ __global__ void __launch_bounds__(256) k_p2p_pack(Buffers B, P2PDev X, int dir, 
 }
 
 // side 0: data from my left neighbour -> my ghost slots of side 0; side 1: from the right.
-__global__ void __launch_bounds__(256) k_p2p_unpack(Buffers B, P2PDev X, int side, unsigned n) {
+// after_begin = 0: runs in front of k_step_begin (the data belongs to the step about to begin, the live buffer is Ctrl::cur);
+// 1: runs behind it, between the two passes of the force kernel (the step has begun: its number is Ctrl::nsteps, its input
+// buffer Ctrl::f_src).
+__global__ void __launch_bounds__(256) k_p2p_unpack(Buffers B, P2PDev X, int side, unsigned n, int after_begin) {
     const Ctrl& C = *B.ctrl;
-    const unsigned long long step = C.nsteps + 1ull;
+    const unsigned long long step = C.nsteps + (after_begin ? 0ull : 1ull);
+    const unsigned buf = after_begin ? C.f_src : C.cur;
     if (threadIdx.x == 0) {
         const unsigned long long* f = &X.self->arrive[side][step & 1ull];
         while (ld_acquire_sys(f) < step)
@@ -2449,10 +2969,10 @@ __global__ void __launch_bounds__(256) k_p2p_unpack(Buffers B, P2PDev X, int sid
         return;
     const double* o = X.land[side][step & 1ull] + (size_t)i * kHaloDoubles;
     const unsigned s = B.ghost_slot[side][i];
-    double4 p = B.pos[C.cur][s];
+    double4 p = B.pos[buf][s];
     p.x = __ldcv(o + 0); p.y = __ldcv(o + 1); p.z = __ldcv(o + 2);
-    B.pos[C.cur][s] = p;
-    double2* q = reinterpret_cast<double2*>(B.vel[C.cur] + s);
+    B.pos[buf][s] = p;
+    double2* q = reinterpret_cast<double2*>(B.vel[buf] + s);
     q[0] = make_double2(__ldcv(o + 3), __ldcv(o + 4));
     q[1] = make_double2(__ldcv(o + 5), __ldcv(o + 6));
     q[2] = make_double2(__ldcv(o + 7), __ldcv(o + 8));
@@ -2620,7 +3140,7 @@ __global__ void __launch_bounds__(256) k_find_contact(Params P, Buffers B, unsig
         if ((vel[s].meta >> (8 + other_shape)) & 1u)
             slot = P.Kn + (int)other_shape;
     } else {
-        const unsigned nc = B.ncnt[s] & 0xFFu, tc = B.ncnt[s] >> 24;
+        const unsigned nc = B.ncnt[s] & 0x7Fu, tc = B.ncnt[s] >> 24;
         for (unsigned k = 0; k < nc + tc; k++) {
             if (!((vel[s].amask >> k) & 1ull))
                 continue;
@@ -2647,7 +3167,7 @@ __global__ void __launch_bounds__(256) k_export_contacts(Params P, Buffers B, un
     const VelRec* vel = B.vel[C.cur];
     if (vel[s].meta & FLAG_GHOST)
         return;
-    const unsigned nc = B.ncnt[s] & 0xFFu;
+    const unsigned nc = B.ncnt[s] & 0x7Fu;
     for (unsigned k = 0; k < nc; k++) {
         const unsigned e = B.nl[(size_t)k * P.Np + s];
         if (!(e & kHiFlag) || !((vel[s].amask >> k) & 1ull))

@@ -35,7 +35,18 @@ constexpr unsigned kTriFlag = 0x80000000u;  // candidate-list entry = triangle (
 constexpr unsigned kHiFlag = 0x40000000u;   // sphere entry: the partner's stable id is higher than the owner's, i.e. the owner is body 1 of
                                             // the canonical (lower id, higher id) orientation -- decided once per list build so that the
                                             // force kernel does not have to gather the partner's id for it
+// Tiled search grid (force kernel with shared-memory staging of the neighbour bins): search cells are numbered tile by tile,
+// kTile x kTile x kTile cells per tile, x fastest inside a tile, so that the spheres of a tile are one contiguous run of the
+// storage order and a tile plus its one-cell halo ("box", (kTile+2)^3 cells) holds every candidate of every sphere of the tile.
+constexpr int kTile = 4;
+constexpr int kTileCells = kTile * kTile * kTile;
+constexpr int kBox = kTile + 2;
+constexpr int kBoxCells = kBox * kBox * kBox;
+constexpr unsigned kCodeHi = 0x8000u;     // nl16 entry: owner is body 1 (same meaning as kHiFlag)
+constexpr unsigned kCodeRankBits = 6;     // nl16 entry = hi << 15 | box cell << 6 | rank in that cell; rank 63 = "not encodable"
+constexpr unsigned kCodeNoRank = 63u;
 constexpr int kCInfo = 13;                  // doubles per recorded contact (Buffers::cinfo)
+constexpr unsigned kBndFlag = 0x80u;        // Buffers::ncnt bit 7: a candidate of this sphere is a ghost (slab mode) -> its forces wait for the halo
 constexpr unsigned kSlotHi = 0x80u;         // the same bit in the force kernel's shared-memory contact list (slot byte: slot < 64)
 
 // device error bits (dem_b200 error codes are derived from these at sync points)
@@ -121,6 +132,7 @@ struct Params {
                             // result depends on the skin (summation order is by stable id), so this only moves cost around.
     double skin_tri;        // skin of the sphere-facet candidates (>= skin): a moving mesh (drum, mixer) sweeps much faster
                             // than the bed creeps, and only the spheres next to it pay for the longer facet lists
+    int tiled;              // search cells numbered tile by tile + nl16 written: the tile force kernel can run
     unsigned nT;            // mesh triangles (shape ids nW .. nW + nT - 1; spheres follow: shape_base = nW + nT)
     unsigned tri_cap;       // capacity of the (search cell, triangle) pair list
 };
@@ -165,11 +177,14 @@ struct Ctrl {
     double skin;                  // Verlet skin the current lists were built with (Params::skin unless adaptive)
     unsigned since_rebuild;       // steps since the lists were built
     unsigned max_cand;            // longest candidate list of the last rebuild (the adaptive skin backs off near Kn)
+    unsigned n_bnd;               // slab mode: owned spheres with a ghost among their candidates (Buffers::bnd_list), last rebuild
+    unsigned n_bnd_pad_;
     double travel_mesh;           // how far mesh vertices moved since the last rebuild (ApplyMeshMotion); counts against the
                                   // facet candidates' own, larger skin (Params::skin_tri) on top of `travel`
     // search grid (cells >= 2 rmax + skin), x fastest
     double s_org[3], s_inv[3];
     int s_dim[3];
+    int t_dim[3];           // tiles per axis (Params::tiled): ceil(s_dim / kTile); s_ncell then counts the padded cells
     unsigned s_ncell;
     GridDev mc;
     unsigned long long n_contacts, pair_count;
@@ -227,6 +242,7 @@ struct Buffers {
     uint32_t* send_slot[2];  // its storage slot after the sort (per-step pack list)
     uint32_t* ghost_slot[2]; // storage slot of the i-th ghost received from the left / right neighbour
     uint32_t* inv_perm;      // scratch: pre-sort index -> storage slot
+    uint32_t* bnd_list;      // storage slots of the spheres whose candidate list holds a ghost (any order), Ctrl::n_bnd of them
     // state, ping-pong
     double4* pos[2];
     VelRec* vel[2];
@@ -240,6 +256,7 @@ struct Buffers {
     uint32_t* cell; uint32_t* rank; uint32_t* perm;
     uint32_t* cell_count; uint32_t* cell_start; uint32_t* block_sums;
     uint32_t* nl;         // [Kn][Np]
+    uint16_t* nl16;       // [Kn][Np] (Params::tiled) the sphere candidates again, as (box cell, rank in cell) relative to the owner's tile
     uint32_t* ncnt;       // [Np]
     // recording (parity tests / smoke)
     double* recF; double* recT;      // by sid, 3 each

@@ -12,6 +12,8 @@ import sys
 import numpy as np
 import torch
 
+os.environ.setdefault("DEMB200_COND_GRAPH", "0")  # ncu cannot see the kernel nodes of a graph with a conditional node
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402

@@ -24,6 +24,15 @@ from test_gpu_bc import one_sphere, hertz_speed, R  # noqa: E402
 def test_moving_walls_match_the_oracle(tang):
     n = 3000
     scene = scenes.settling_scene(n, sep_factor=1.985, seed=61)
+    # the lattice starts 0.01 R clear of the container: push every wall 0.03 R inwards so that the outer spheres touch it
+    centre = np.array([0.0, 0.0, scene["box_size"][2] / 2])
+    walls = []
+    for p, h in scene["walls"]:
+        a = int(np.argmin(h))
+        p = np.array(p, dtype=np.float64)
+        p[a] -= np.sign(p[a] - centre[a]) * 0.03 * R
+        walls.append((p, h))
+    scene["walls"] = walls
     vel, om = kinematics(n, 17)
     wall_v = np.array([0.35, -0.2, 0.15])
     kw = dict(dt=1e-4, force_model=po.HERTZ, tangential_mode=tang)
