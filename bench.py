@@ -311,6 +311,8 @@ def measure_single(cfg_id, n, args, local=0, with_profile=True, tag=None):
     scene = build_scene(cfg_id, n)
     n = scene["n"]
     kw = physics(cfg_id)
+    if args.skin > 0:
+        kw["verlet_skin"] = args.skin * RADIUS  # fixed (non-adaptive) Verlet skin, as slab mode uses
     motion = None
     if cfg_id == 3:  # per-step host calls (ApplyMeshMotion): run the engine on torch's stream so that torch events time it
         kw["stream"] = torch.cuda.current_stream().cuda_stream
@@ -540,6 +542,13 @@ def slab_scene(cfg_id, n_total, world, rank):
 
 
 def measure_slabs(cfg_id, n_total, args, rank, world, local, dist, torch):
+    # the engine runs on the stream that is current when it is created: give it a stream of its own instead of the legacy
+    # default stream (graph launches into stream 0 serialise with every other blocking stream of the process)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        return _measure_slabs(cfg_id, n_total, args, rank, world, local, dist, torch)
+
+
+def _measure_slabs(cfg_id, n_total, args, rank, world, local, dist, torch):
     from chrono_b200 import dem, scenes, slab
     S = args.substeps
     pos, rad, ids, lo, hi, sc = slab_scene(cfg_id, n_total, world, rank)
@@ -757,7 +766,7 @@ def main():
     ap.add_argument("--parity-steps", type=int, default=300)
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: NCCL send/recv halo + all-reduce vote instead of P2P stores")
     ap.add_argument("--slab-lag", type=int, default=3, help="N > 1: steps between casting the rebuild vote and acting on it")
-    ap.add_argument("--skin", type=float, default=0.0, help="N > 1: Verlet skin in sphere radii (0 = engine default)")
+    ap.add_argument("--skin", type=float, default=0.0, help="fixed Verlet skin in sphere radii (0 = engine default: adaptive 0.25 - 0.5 on one GPU, 0.35 on slabs)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.config < 0:

@@ -55,6 +55,8 @@ struct dem_b200_system {
     cudaStream_t stream = nullptr;
     cudaStream_t cap_stream = nullptr;  // graph capture only
     cudaStream_t cap_stream2 = nullptr; // body of the conditional node
+    cudaStream_t side_stream = nullptr; // slab mode: halo pick-up + second force pass next to the first pass
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned ntiles = 0;               // scan tiles covering the search-cell capacity
     cudaGraphExec_t graph1 = nullptr;  // one step
     bool recording = false;
@@ -86,6 +88,7 @@ struct dem_b200_system {
     unsigned long long step_no = 0;      // host mirror of Ctrl::nsteps (steps enqueued so far)
     unsigned long long p2p_rebuild_seq = 0;
     unsigned long long slab_rebuilds = 0;  // host-driven slab rebuilds (dem_b200_mgpu_finish_rebuild)
+    unsigned long long mg_last_rebuild_step = 0, mg_last_interval = 0;  // time steps between the last two slab rebuilds
     size_t owned_export_n = (size_t)-1;    // dem_b200_export_owned bookkeeping for dem_b200_import_owned
     unsigned long long owned_export_step = ~0ull, owned_export_seq = ~0ull;
     int one_step_calls = 0;
@@ -328,14 +331,13 @@ void enqueue_pre(dem_b200_system* s, cudaStream_t st, unsigned long long cond) {
 
 // Direct halo of slab mode (dem_b200_p2p_*): at the END of a step the boundary spheres' new state goes straight into the
 // neighbours' landing buffers (NVLink stores, tagged with the number of the step that will consume it) and the rebuild vote is
-// cast; the consumer picks the data up BETWEEN the two passes of its force kernel (enqueue_post), i.e. a whole interior pass
-// after it was sent, so nobody waits for a neighbour unless it lags by most of a step.
-void enqueue_halo_send(dem_b200_system* s, cudaStream_t st) {
+// cast; the consumer picks the data up on a side stream next to the first pass of its force kernel (enqueue_post).
+void enqueue_halo_pack(dem_b200_system* s, cudaStream_t st) {
     for (int d = 0; d < 2; d++)
         if (s->mg_ns[d])
             k_p2p_pack<<<(s->mg_ns[d] + 255) / 256, 256, 0, st>>>(s->B, s->X, d, s->mg_ns[d]);
-    k_p2p_vote<<<1, 32, 0, st>>>(s->P, s->B, s->X);
 }
+void enqueue_vote(dem_b200_system* s, cudaStream_t st) { k_p2p_vote<<<1, 32, 0, st>>>(s->P, s->B, s->X); }
 
 // ev: optional events recorded after each of the seven rebuild kernels (profiling), starting at ev[*k]
 void enqueue_rebuild(dem_b200_system* s, cudaStream_t st, cudaEvent_t* ev, int* k) {
@@ -382,17 +384,31 @@ void enqueue_post(dem_b200_system* s, cudaStream_t st) {
         k_record_bins<<<(N + 255) / 256, 256, 0, st>>>(P, B);
         launch_force<true>(s, B, fb);
     } else if (s->p2p && !s->mg_remap_pending) {
-        // interior first (needs no ghost), then the halo that was sent at the end of the neighbours' previous step, then the
-        // spheres that touch a ghost: at most the ghost senders (a sphere with a ghost candidate lies within the ghost cut of
-        // its slab face), hence the grid of the second pass
+        // Two passes.  Pass 2 = the ghost senders (every owned sphere within the ghost cut of a slab face: they include every
+        // sphere that has a ghost among its candidates), pass 1 = everybody else: 95 % of a 1 M-sphere slab, needs no halo.
+        // Side stream, next to pass 1 (a fork / join of the step graph): pick up the halo the neighbours sent during THEIR
+        // previous step -> pass 2 -> send the new state of the senders for the neighbours' next step.  Main stream: pass 1, then
+        // the rebuild vote (it needs the displacement of every sphere).  Critical path: step control -> pass 1 -> vote.
+        if (!s->side_stream) {
+            cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+        }
+        cudaEventRecord(s->ev_fork, st);
+        cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
         launch_force<false>(s, B, fb, 1u);
+        s->stream = s->side_stream;
         for (int d = 0; d < 2; d++)
             if (s->mg_ng[d])
-                k_p2p_unpack<<<(s->mg_ng[d] + 255) / 256, 256, 0, st>>>(B, s->X, d, s->mg_ng[d], 1);
+                k_p2p_unpack<<<(s->mg_ng[d] + 255) / 256, 256, 0, s->side_stream>>>(B, s->X, d, s->mg_ng[d], 1);
         const unsigned nb = s->mg_ns[0] + s->mg_ns[1];
         if (nb)
             launch_force<false>(s, B, (nb + kForceThreads - 1) / kForceThreads, 2u);
-        enqueue_halo_send(s, st);
+        enqueue_halo_pack(s, s->side_stream);
+        cudaEventRecord(s->ev_join, s->side_stream);
+        cudaStreamWaitEvent(st, s->ev_join, 0);
+        s->stream = st;
+        enqueue_vote(s, st);
     } else {
         // (slab mode right after a rebuild: the ghosts that were just exchanged are current, one pass; run_steps sends the halo
         // once the sorted slots of the senders are known)
@@ -510,7 +526,9 @@ int build_graph(dem_b200_system* s) {
         const char* e = getenv("DEMB200_COND_GRAPH");
         return !(e && e[0] == '0');
     }();
-    if (want_cond && !s->mgpu && build_graph_conditional(s, &g) == 0) {
+    // slab mode re-captures the graph after every slab rebuild: the conditional form (dearer to build, cheaper to run) only when
+    // the rebuilds have been coming more than 150 steps apart (a settled bed), the flat one while the bed flows
+    if (want_cond && (!s->mgpu || s->mg_last_interval >= 150ull) && build_graph_conditional(s, &g) == 0) {
         cudaError_t ei = cudaGraphInstantiate(&s->graph1, g, 0);
         cudaGraphDestroy(g);
         if (ei == cudaSuccess)
@@ -609,7 +627,13 @@ int run_steps(dem_b200_system* s, int nsteps) {
     // their third call on
     if (nsteps == 1 && s->one_step_calls < 3)
         s->one_step_calls++;
-    if (!s->recording && ((!s->mgpu && (nsteps >= 2 || (nsteps == 1 && s->one_step_calls >= 3))) || (s->mgpu && !s->mg_remap_pending))) {
+    // DEMB200_NO_GRAPH=1: every step as direct launches (profiling: ncu lists the kernels of a step one by one, also where it
+    // cannot look into the step graph)
+    static const bool no_graph = [] {
+        const char* e = getenv("DEMB200_NO_GRAPH");
+        return e && e[0] == '1';
+    }();
+    if (!no_graph && !s->recording && ((!s->mgpu && (nsteps >= 2 || (nsteps == 1 && s->one_step_calls >= 3))) || (s->mgpu && !s->mg_remap_pending))) {
         if (!s->graph1) {
             int rc = build_graph(s);
             if (rc)
@@ -637,9 +661,12 @@ int run_steps(dem_b200_system* s, int nsteps) {
             k_mgpu_invert_perm<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B);
             if (m)
                 k_mgpu_remap<<<(m + 255) / 256, 256, 0, s->stream>>>(s->B, s->mg_n_own, s->mg_ns[0], s->mg_ns[1], s->mg_ng[0], s->mg_ng[1]);
+            k_mgpu_bnd_list<<<(N + 255) / 256, 256, 0, s->stream>>>(s->P, s->B);
             s->mg_remap_pending = false;
-            if (s->p2p)
-                enqueue_halo_send(s, s->stream);  // the first step after a slab rebuild: its result feeds the neighbours' next step
+            if (s->p2p) {  // the first step after a slab rebuild: its result feeds the neighbours' next step
+                enqueue_halo_pack(s, s->stream);
+                enqueue_vote(s, s->stream);
+            }
             CU(cudaGetLastError());
         }
     }
@@ -710,6 +737,11 @@ void dem_b200_destroy(dem_b200_system* s) {
         cudaStreamDestroy(s->cap_stream);
     if (s->cap_stream2)
         cudaStreamDestroy(s->cap_stream2);
+    if (s->side_stream) {
+        cudaStreamDestroy(s->side_stream);
+        cudaEventDestroy(s->ev_fork);
+        cudaEventDestroy(s->ev_join);
+    }
     delete s;
 }
 
@@ -1881,6 +1913,8 @@ int dem_b200_mgpu_finish_rebuild(dem_b200_system* s) {
     drop_graph(s);
     s->mg_phase = 0;
     s->slab_rebuilds++;
+    s->mg_last_interval = s->step_no - s->mg_last_rebuild_step;
+    s->mg_last_rebuild_step = s->step_no;
     s->mg_remap_pending = true;
     s->export_valid = false;
     return recompute_bbox(s);
@@ -2031,6 +2065,8 @@ int dem_b200_p2p_rebuild(dem_b200_system* s, double lo, double hi, size_t counts
         return DEMB200_EINVAL;
     CU(cudaSetDevice(s->cfg.device));
     const unsigned long long seq = ++s->p2p_rebuild_seq;
+    s->mg_last_interval = s->step_no - s->mg_last_rebuild_step;
+    s->mg_last_rebuild_step = s->step_no;
     cudaStream_t st = s->stream;
     const P2PDev& X = s->X;
     CU(cudaMemsetAsync(s->B.slab, 0, sizeof(SlabDev), st));

@@ -381,6 +381,10 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
             C.t_dim[k] = tdim[k];
         }
         C.s_ncell = (unsigned)tot;
+        // slab mode: x (the slab axis) varies slowest, y fastest
+        C.s_perm[0] = P.external_rebuild ? 1 : 0;
+        C.s_perm[1] = P.external_rebuild ? 2 : 1;
+        C.s_perm[2] = P.external_rebuild ? 0 : 2;
         for (int k = 0; k < 3; k++) {
             C.sbox_next[k] = enc_ord(CUDART_INF);
             C.sbox_next[3 + k] = enc_ord(-CUDART_INF);
@@ -455,8 +459,11 @@ __device__ __forceinline__ int cell_coord(double x, double org, double inv, int 
 // Number of a search cell.  Plain grid: x fastest.  Tiled grid (Params::tiled): tiles of kTile^3 cells, tile by tile (x fastest
 // over the tiles), x fastest inside a tile -- the spheres of one tile are then one contiguous run of the storage order.
 __device__ __forceinline__ unsigned cell_index(const Params& P, const Ctrl& C, int cx, int cy, int cz) {
-    if (!P.tiled)
-        return (unsigned)((cz * C.s_dim[1] + cy) * C.s_dim[0] + cx);
+    if (!P.tiled) {
+        const int c[3] = {cx, cy, cz};
+        const int p0 = C.s_perm[0], p1 = C.s_perm[1], p2 = C.s_perm[2];
+        return (unsigned)((c[p2] * C.s_dim[p1] + c[p1]) * C.s_dim[p0] + c[p0]);
+    }
     const int tx = cx / kTile, ty = cy / kTile, tz = cz / kTile;
     const unsigned tile = (unsigned)((tz * C.t_dim[1] + ty) * C.t_dim[0] + tx);
     return tile * (unsigned)kTileCells + (unsigned)((((cz % kTile) * kTile) + (cy % kTile)) * kTile + (cx % kTile));
@@ -857,32 +864,37 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     const int cx = cell_coord(me.x, C.s_org[0], C.s_inv[0], C.s_dim[0]);
     const int cy = cell_coord(me.y, C.s_org[1], C.s_inv[1], C.s_dim[1]);
     const int cz = cell_coord(me.z, C.s_org[2], C.s_inv[2], C.s_dim[2]);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, C.s_dim[0] - 1);
     unsigned tj[kMaxNeighbors], ts[kMaxNeighbors];
     unsigned short tc[kMaxNeighbors];  // tiled grid: (box cell, rank in cell) of the candidate, relative to this sphere's tile
     const int tx0 = (cx / kTile) * kTile, ty0 = (cy / kTile) * kTile, tz0 = (cz / kTile) * kTile;
+    // axes in the order of the cell numbering: a0 runs fastest (the three cells c0-1 .. c0+1 of a row are one run of the storage
+    // order on the plain grid), a2 slowest
+    const int a0 = P.tiled ? 0 : C.s_perm[0], a1 = P.tiled ? 1 : C.s_perm[1], a2 = P.tiled ? 2 : C.s_perm[2];
+    const int cc[3] = {cx, cy, cz};
+    const int lo0 = max(cc[a0] - 1, 0), hi0 = min(cc[a0] + 1, C.s_dim[a0] - 1);
     int cnt = 0;
     bool overflow = false, has_ghost = false;
-    for (int dz = -1; dz <= 1; dz++) {
-        const int z = cz + dz;
-        if (z < 0 || z >= C.s_dim[2])
+    for (int e2 = -1; e2 <= 1; e2++) {
+        const int v2 = cc[a2] + e2;
+        if (v2 < 0 || v2 >= C.s_dim[a2])
             continue;
-        for (int dy = -1; dy <= 1; dy++) {
-            const int y = cy + dy;
-            if (y < 0 || y >= C.s_dim[1])
+        for (int e1 = -1; e1 <= 1; e1++) {
+            const int v1 = cc[a1] + e1;
+            if (v1 < 0 || v1 >= C.s_dim[a1])
                 continue;
             // plain grid: the three cells of a row are one run of the storage order; tiled grid: cell by cell
-            for (int x = x0; x <= x1; x += P.tiled ? 1 : 3) {
+            for (int v0 = lo0; v0 <= hi0; v0 += P.tiled ? 1 : 3) {
                 unsigned jb, je, box = 0u;
                 if (P.tiled) {
+                    const int x = v0, y = v1, z = v2;  // tiled: a0, a1, a2 = x, y, z
                     const unsigned ci = cell_index(P, C, x, y, z);
                     jb = B.cell_start[ci];
                     je = B.cell_start[ci + 1];
                     box = (unsigned)(((z - tz0 + 1) * kBox + (y - ty0 + 1)) * kBox + (x - tx0 + 1));
                 } else {
-                    const unsigned row = (unsigned)((z * C.s_dim[1] + y) * C.s_dim[0]);
-                    jb = B.cell_start[row + x0];
-                    je = B.cell_start[row + x1 + 1];
+                    const unsigned row = (unsigned)((v2 * C.s_dim[a1] + v1) * C.s_dim[a0]);
+                    jb = B.cell_start[row + lo0];
+                    je = B.cell_start[row + hi0 + 1];
                 }
                 for (unsigned j = jb; j < je; j++) {
                     if (j == s)
@@ -999,9 +1011,9 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                 wc |= 1u << w;
         }
     }
+    // (a sphere with a ghost among its candidates lies within the ghost cut of a slab face: it is one of the ghost SENDERS, which
+    // k_mgpu_remap flags as the second-pass set of the direct halo; the flag set here only matters until that kernel has run)
     B.ncnt[s] = (unsigned)cnt | (has_ghost ? kBndFlag : 0u) | (wc << 8) | ((unsigned)tcnt << 24);
-    if (has_ghost && B.bnd_list)  // slab mode: the forces of these spheres wait for the halo, everybody else's do not
-        B.bnd_list[atomicAdd(&C.n_bnd, 1u)] = s;
     // staged history -> slots of the new list (a record whose partner is no longer a candidate is dropped: that
     // contact has broken)
     if (B.hist) {
@@ -2058,7 +2070,8 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
 
     double nmnx = CUDART_INF, nmny = CUDART_INF, nmnz = CUDART_INF, nmxx = -CUDART_INF, nmxy = -CUDART_INF, nmxz = -CUDART_INF;
     double dx2 = 0.0;
-    if (valid) {
+    // pass 1 runs next to the halo pick-up (side stream), which rewrites the ghost records of BOTH buffers itself: ghosts sit out
+    if (valid && !(pass == 1u && ghost)) {
         if (HIST && __popcll(amask_new) + __popc(wmask_new) > P.K)
             atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
         if (REC) {
@@ -2571,7 +2584,7 @@ __global__ void __launch_bounds__(kTileThreads, DEMB200_TILE_MINBLOCKS) k_force_
 
         double nmnx = CUDART_INF, nmny = CUDART_INF, nmnz = CUDART_INF, nmxx = -CUDART_INF, nmxy = -CUDART_INF, nmxz = -CUDART_INF;
         double dx2 = 0.0;
-        if (valid) {
+        if (valid && !(pass == 1u && ghost)) {  // (ghosts sit out pass 1: see k_force_integrate)
             if (HIST && __popcll(amask_new) + __popc(wmask_new) > P.K)
                 atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
             const V3 x = integrate_store(P, B, C, src, dst, s, me, mv.v, mv.w, sid, flags, Fsum, Tsum, wmask_new, amask_new);
@@ -2844,10 +2857,30 @@ __global__ void __launch_bounds__(256) k_mgpu_invert_perm(Params P, Buffers B) {
 __global__ void __launch_bounds__(256) k_mgpu_remap(Buffers B, unsigned n_own, unsigned ns0, unsigned ns1, unsigned ng0,
                                                     unsigned ng1) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ns0) B.send_slot[0][i] = B.inv_perm[B.send_pre[0][i]];
-    if (i < ns1) B.send_slot[1][i] = B.inv_perm[B.send_pre[1][i]];
+    // the ghost senders are the second-pass set of the direct halo (kBndFlag): everything a neighbour needs of this slab is
+    // computed behind the halo pick-up and can be sent while the first pass is still running
+    if (i < ns0) {
+        const unsigned sl = B.inv_perm[B.send_pre[0][i]];
+        B.send_slot[0][i] = sl;
+        atomicOr(&B.ncnt[sl], kBndFlag);
+    }
+    if (i < ns1) {
+        const unsigned sl = B.inv_perm[B.send_pre[1][i]];
+        B.send_slot[1][i] = sl;
+        atomicOr(&B.ncnt[sl], kBndFlag);
+    }
     if (i < ng0) B.ghost_slot[0][i] = B.inv_perm[n_own + i];
     if (i < ng1) B.ghost_slot[1][i] = B.inv_perm[n_own + ng0 + i];
+}
+
+// flagged spheres -> Buffers::bnd_list (each once, any order)
+__global__ void __launch_bounds__(256) k_mgpu_bnd_list(Params P, Buffers B) {
+    Ctrl& C = *B.ctrl;
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = s < P.N && (B.ncnt[s] & kBndFlag) != 0u;
+    const unsigned at = warp_alloc(&C.n_bnd, take);
+    if (take)
+        B.bnd_list[at] = s;
 }
 
 // per-step halo: current state of the ghost-senders -> message; message -> ghost slots of the live buffer
@@ -2935,10 +2968,11 @@ __global__ void __launch_bounds__(256) k_p2p_pack(Buffers B, P2PDev X, int dir, 
         o[0] = p.x; o[1] = p.y; o[2] = p.z;
         o[3] = r.v.x; o[4] = r.v.y; o[5] = r.v.z; o[6] = r.w.x; o[7] = r.w.y; o[8] = r.w.z;
     }
-    // the last block to finish publishes the step number on the receiver
-    __threadfence_system();
+    // the last block to finish publishes the step number on the receiver.  One system fence per block: the barrier orders every
+    // thread's stores before thread 0's fence, which is cumulative (PTX memory model: causality order through bar.sync)
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned prev = atomicAdd(&X.done[dir], 1u);
         if (prev == gridDim.x - 1) {
             X.done[dir] = 0u;
@@ -2971,11 +3005,19 @@ __global__ void __launch_bounds__(256) k_p2p_unpack(Buffers B, P2PDev X, int sid
     const unsigned s = B.ghost_slot[side][i];
     double4 p = B.pos[buf][s];
     p.x = __ldcv(o + 0); p.y = __ldcv(o + 1); p.z = __ldcv(o + 2);
+    const double2 v01 = make_double2(__ldcv(o + 3), __ldcv(o + 4)), v2w0 = make_double2(__ldcv(o + 5), __ldcv(o + 6)),
+                  w12 = make_double2(__ldcv(o + 7), __ldcv(o + 8));
     B.pos[buf][s] = p;
     double2* q = reinterpret_cast<double2*>(B.vel[buf] + s);
-    q[0] = make_double2(__ldcv(o + 3), __ldcv(o + 4));
-    q[1] = make_double2(__ldcv(o + 5), __ldcv(o + 6));
-    q[2] = make_double2(__ldcv(o + 7), __ldcv(o + 8));
+    q[0] = v01; q[1] = v2w0; q[2] = w12;
+    if (after_begin) {
+        // the step is under way and its first pass leaves the ghosts alone: their records of the output buffer are written here
+        // (a ghost is never integrated: same state in both buffers; id, flags and radius come along)
+        const double2 idm = q[3];
+        B.pos[buf ^ 1u][s] = p;
+        double2* qo = reinterpret_cast<double2*>(B.vel[buf ^ 1u] + s);
+        qo[0] = v01; qo[1] = v2w0; qo[2] = w12; qo[3] = idm;
+    }
 }
 
 // ---- device-driven rebuild (P2P mode): the same protocol as extract -> exchange -> append -> select_ghosts -> exchange

@@ -184,6 +184,8 @@ struct Ctrl {
     // search grid (cells >= 2 rmax + skin), x fastest
     double s_org[3], s_inv[3];
     int s_dim[3];
+    int s_perm[3];          // axis order of the cell numbering: s_perm[0] runs fastest.  (0,1,2) on one GPU; slab mode puts the slab axis x
+                            // last, so that ghosts and ghost senders (the layers next to the slab faces) are contiguous runs of the storage order
     int t_dim[3];           // tiles per axis (Params::tiled): ceil(s_dim / kTile); s_ncell then counts the padded cells
     unsigned s_ncell;
     GridDev mc;

@@ -69,11 +69,57 @@ def repose_angle(pos, radius):
     return math.degrees(math.atan(-slope))
 
 
-def test_angle_of_repose():
+def repose_physics(mod):
+    """config[2]-style material; mod = oracle.pyoracle or chrono_b200.dem (same constant names)"""
+    mat = common.settling_material(mu=0.6, mu_roll=0.2, cr=0.2)
+    return dict(dt=1e-4, mat=mat, force_model=mod.HERTZ, tangential_mode=mod.TANG_MULTISTEP, history_slots=24)
+
+
+def moment_angle(pos, radius):
+    """Angle of the cone that has the pile's mass moments: a cone of height h and base radius r has its centre of mass at
+    h / 4 and <rho^2> = 3 r^2 / 10, hence tan(angle) = h / r = 4 zbar / sqrt(10/3 <rho^2>).  Sums over ALL spheres: far less
+    scatter than a slope fitted to the few surface spheres (1.9 % against 7 % from pile to pile)."""
+    m = radius ** 3
+    cx, cy = np.average(pos[:, 0], weights=m), np.average(pos[:, 1], weights=m)
+    rho2 = np.average((pos[:, 0] - cx) ** 2 + (pos[:, 1] - cy) ** 2, weights=m)
+    zbar = np.average(pos[:, 2], weights=m)
+    return math.degrees(math.atan(4.0 * zbar / math.sqrt(10.0 / 3.0 * rho2))), float(zbar), float(math.sqrt(rho2))
+
+
+def test_angle_of_repose_ensemble_within_one_percent():
+    """BASELINE.json north_star: angle of repose within 1 %.  Trajectories of the two implementations diverge chaotically, so
+    the statement is about ensemble means (tests/golden/make_repose_golden.py explains the numbers): the GPU runs the piles of
+    the oracle's committed ensemble (128 scenes) and the two means are compared."""
+    import json
+    import os
+    from chrono_b200 import dem
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "repose_oracle.json")) as f:
+        gold = json.load(f)
+    angles, zbars, rhos = [], [], []
+    for row in gold["piles"]:
+        sc = repose_scene(row["seed"])
+        assert sc["n"] == row["n"]
+        g = common.make_gpu(sc, **repose_physics(dem))
+        g.step(gold["steps"])
+        p, v, _ = g.state()
+        g.close()
+        assert np.quantile(np.linalg.norm(v, axis=1), 0.99) < 0.05  # the pile has come to rest
+        a, zb, rr = moment_angle(p, sc["radius"])
+        angles.append(a); zbars.append(zb); rhos.append(rr)
+    a_g, a_o = float(np.mean(angles)), gold["mean_angle_deg"]
+    sem = math.hypot(np.std(angles, ddof=1) / math.sqrt(len(angles)), gold["sem_angle_deg"])
+    print("angle of repose: gpu %.3f deg, oracle %.3f deg (difference %.2f %%, standard error of the difference %.2f %%)"
+          % (a_g, a_o, 100 * (a_g - a_o) / a_o, 100 * sem / a_o))
+    assert 10.0 < a_o < 45.0
+    assert abs(a_g - a_o) / a_o < 0.01, (a_g, a_o)
+    assert abs(np.mean(zbars) - gold["mean_zbar"]) / gold["mean_zbar"] < 0.01
+    assert abs(np.mean(rhos) - gold["mean_rho_rms"]) / gold["mean_rho_rms"] < 0.01
+
+
+def test_angle_of_repose_single_pile():
     sc = repose_scene()
     assert sc["n"] > 1000
-    mat = common.settling_material(mu=0.6, mu_roll=0.2, cr=0.2)
-    kw = dict(dt=1e-4, mat=mat, force_model=po.HERTZ, tangential_mode=po.TANG_MULTISTEP, history_slots=24)
+    kw = repose_physics(po)
     o = common.make_oracle(sc, **kw)
     g = common.make_gpu(sc, **kw)
     steps = 14000
@@ -85,8 +131,7 @@ def test_angle_of_repose():
     ao, ag = repose_angle(po_[f:], sc["radius"]), repose_angle(pg, sc["radius"])
     print("angle of repose: oracle %.2f deg, gpu %.2f deg" % (ao, ag))
     assert 10.0 < ao < 45.0
-    # 1 % of the angle is below the run-to-run scatter of a 1300-sphere pile once the trajectories have diverged; the
-    # pile SHAPE statistics that define the angle are compared at 1 %: height and footprint radius
+    # one pile against one pile: the bars are the pile-to-pile scatter (the 1 % statement is the ensemble test above)
     hO, hG = (po_[f:, 2] + sc["radius"]).max(), (pg[:, 2] + sc["radius"]).max()
     rO = np.quantile(np.hypot(po_[f:, 0], po_[f:, 1]), 0.9)
     rG = np.quantile(np.hypot(pg[:, 0], pg[:, 1]), 0.9)
