@@ -711,7 +711,7 @@ def run_slabs(args):
     rec = measure_slabs(cfg_id, n_total, args, rank, world, local, dist, torch)
     n_total = rec["spheres"]
     strong = None
-    if cfg_id == 4 and not args.no_strong and not args.spheres:
+    if cfg_id == 4 and not args.no_strong and not args.spheres and STRONG_TOTAL != WEAK_PER_GPU * world:
         a2 = argparse.Namespace(**vars(args))
         a2.steps, a2.warmup = max(3, args.steps // 2), 2
         r2 = measure_slabs(4, STRONG_TOTAL, a2, rank, world, local, dist, torch)
@@ -737,6 +737,9 @@ def run_slabs(args):
         }
         if strong:
             line["strong"] = strong
+        elif cfg_id == 4 and not args.spheres and STRONG_TOTAL == WEAK_PER_GPU * world:
+            line["strong"] = {"what": "strong scaling: %d spheres in total over %d GPUs -- at this N the weak-scaling line above IS that run" % (n_total, world),
+                              "value": rec["value"], "unit": "sphere-steps/s", "spheres_total": n_total}
         for k in ("mesh_force", "mesh_facets"):
             if k in rec:
                 line[k] = rec[k]

@@ -1966,7 +1966,9 @@ int dem_b200_mgpu_want_rebuild(dem_b200_system* s, int* flag_dev) { return dem_b
 
 // ---- direct peer-to-peer halo -----------------------------------------------------------------------------------
 // region layout: control block | halo landing [2 sides][2 parities] | migrant landing [2 sides] | ghost landing [2 sides]
-static size_t p2p_mig_records(size_t records) { return std::max<size_t>(1024, records / 16); }
+// migrants per side and rebuild: a small fraction of the ghost layer in a settling bed, several times the usual in a colliding
+// flow (two streams meeting at a slab face) -- an eighth of the ghost capacity, at least 4096
+static size_t p2p_mig_records(size_t records) { return std::max<size_t>(4096, records / 8); }
 static size_t p2p_region_bytes(size_t records, int K) {
     return kP2PCtlBytes + sizeof(double) * (4 * records * kHaloDoubles + 2 * p2p_mig_records(records) * (size_t)migrant_doubles(K) +
                                             2 * records * kGhostDoubles);
@@ -2100,7 +2102,11 @@ int dem_b200_p2p_rebuild(dem_b200_system* s, double lo, double hi, size_t counts
     }
     if (s->mg_n_local == 0 || s->mg_n_local > s->mg_cap || std::max(sd.n_gsend[0], sd.n_gsend[1]) > X.cap_gho ||
         std::max(sd.n_out[0], sd.n_out[1]) > X.cap_mig) {
-        s->err = "p2p_rebuild: slab empty or a buffer capacity exceeded";
+        char msg[400];
+        snprintf(msg, sizeof(msg), "p2p_rebuild: slab empty or a buffer capacity exceeded: local %u (own %u + ghosts %u + %u) of capacity %zu, "
+                 "ghost senders %u / %u of %u, migrants out %u / %u of %u", s->mg_n_local, s->mg_n_own, s->mg_ng[0], s->mg_ng[1], s->mg_cap,
+                 sd.n_gsend[0], sd.n_gsend[1], X.cap_gho, sd.n_out[0], sd.n_out[1], X.cap_mig);
+        s->err = msg;
         return DEMB200_ECAPACITY;
     }
     s->P.N = s->mg_n_local;

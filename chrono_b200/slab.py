@@ -222,7 +222,7 @@ class EngineBackend:
         self.capacity = capacity
         self.max_records = max_records or max(1024, capacity // 4)
         f64 = dict(dtype=torch.float64, device=self.device)
-        self.mig = [torch.empty((max(1024, self.max_records // 16), self.migrant_doubles), **f64) for _ in range(2)]
+        self.mig = [torch.empty((max(4096, self.max_records // 8), self.migrant_doubles), **f64) for _ in range(2)]
         self.gho = [torch.empty((self.max_records, self.ghost_doubles), **f64) for _ in range(2)]
         self.hsend = [torch.empty((self.max_records, self.halo_doubles), **f64) for _ in range(2)]
         self.hrecv = [torch.empty((self.max_records, self.halo_doubles), **f64) for _ in range(2)]
