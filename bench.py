@@ -139,10 +139,19 @@ def build_scene(cfg_id, n):
     return sc
 
 
+PACKING = {
+    0: "jittered HCP lattice at 2R spacing in a five-wall box",
+    1: "jittered HCP bed in a five-wall box, 2R in-plane spacing, layer heights in static equilibrium under gravity (the bed starts at rest)",
+    2: "jittered lattice of polydisperse spheres in a five-wall box, relaxing under gravity (a slowly creeping bed: lists are rebuilt every ~25 steps)",
+    3: "HCP bed in the lower third of a closed drum (cylinder wall = triangle mesh, end caps = box walls) turning at 1 m/s wall speed; the bed rides up the wall",
+    4: "jittered HCP bed in a five-wall box, 2R in-plane spacing, layer heights in static equilibrium under gravity (the bed starts at rest), 44 layers deep at every size",
+}
+
+
 def workload_config(cfg_id, n_per_gpu, n_total, substeps, gpus, settle, extra=None):
-    d = {"workload": "%s -- %d spheres%s, jittered HCP bed (2R in-plane spacing, layer heights in static equilibrium under gravity), settled %d time steps before the timed region; "
+    d = {"workload": "%s -- %d spheres%s; %s; %d untimed time steps before the timed region; "
                      "R=0.02 rho=2000 Y=2e6 mu=0.4 cr=0.4 h=1e-4" % (CONFIG_NAMES[cfg_id], n_total,
-                                                                     (" (%d per GPU)" % n_per_gpu) if gpus > 1 else "", settle),
+                                                                     (" (%d per GPU)" % n_per_gpu) if gpus > 1 else "", PACKING[cfg_id], settle),
          "config_id": cfg_id, "spheres_total": n_total, "spheres_per_gpu": n_per_gpu, "timesteps_per_step": substeps,
          "settle_timesteps": settle,
          "l2_policy": "working set (>= 900 B/sphere-step of DRAM traffic x %d spheres) exceeds the 126 MB L2; no explicit flush" % n_per_gpu,
@@ -757,7 +766,7 @@ def main():
     ap.add_argument("--config", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 4], help="BASELINE.json configs[i]; default 1 on one GPU, 4 on several")
     ap.add_argument("--spheres", type=int, default=0, help="spheres per GPU (0 = the size the config names)")
     ap.add_argument("--substeps", type=int, default=100, help="DEM time steps per bench step")
-    ap.add_argument("--settle", type=int, default=4000, help="untimed time steps that settle the bed before warm-up")
+    ap.add_argument("--settle", type=int, default=-1, help="untimed time steps that settle the bed before warm-up (default: 3000; configs[2] 10000)")
     ap.add_argument("--ref-substeps", type=int, default=2, help="time steps per bench step of the reference arm")
     ap.add_argument("--cpu-steps", type=int, default=4, help="time steps of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-flowing", action="store_true", help="N = 1: skip the flowing-bed record")
@@ -774,6 +783,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.config < 0:
         args.config = 1 if world == 1 else 4
+    if args.settle < 0:
+        args.settle = 10000 if args.config == 2 else (0 if args.config == 0 else 3000)
     if args.impl == "reference":
         run_reference(args)
     elif world > 1:
