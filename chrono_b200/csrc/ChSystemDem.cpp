@@ -160,6 +160,20 @@ class ChSystemDem_impl {
         c.neighbor_slots = meshes.empty() ? 0 : 48;
         return c;
     }
+
+    // A setter called after Initialize: the reference stores into GranParams, which its kernels read every step
+    // (ChSystemDem.cpp:52-260); here the change is pushed through the ABI.  What the engine cannot change on a running system
+    // (friction mode, force model, to / from CHUNG, the slot counts) comes back as an error instead of being ignored.
+    void refresh(const char* what) {
+        if (!initialized)
+            return;
+        dem_b200_config cfg = make_config();
+        check(dem_b200_set_config(h, &cfg), what);
+        for (int k = 0; k < 3; k++) {
+            dem_b200_contact_class cc = make_class(k);
+            check(dem_b200_set_contact_class(h, k, &cc), what);
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -192,6 +206,7 @@ void* ChSystemDem::GetEngineHandle() const { return m_sys->h; }
 // ---- setters ---------------------------------------------------------------------------------------------------------
 void ChSystemDem::SetGravitationalAcceleration(const ChVector3f& g) {
     m_sys->grav[0] = g.x(); m_sys->grav[1] = g.y(); m_sys->grav[2] = g.z();
+    m_sys->refresh("SetGravitationalAcceleration");
 }
 
 void ChSystemDem::SetParticles(const std::vector<ChVector3f>& points, const std::vector<ChVector3f>& vels,
@@ -232,40 +247,68 @@ void ChSystemDem::SetParticleFixed(const std::vector<bool>& fixed) {
 }
 void ChSystemDem::SetParticleOutputMode(CHDEM_OUTPUT_MODE mode) { m_sys->out_mode = mode; }
 void ChSystemDem::SetParticleOutputFlags(unsigned int flags) { m_sys->out_flags = flags; }
-void ChSystemDem::SetFixedStepSize(float size_UU) { m_sys->step = size_UU; }
+void ChSystemDem::SetFixedStepSize(float size_UU) { m_sys->step = size_UU; m_sys->refresh("SetFixedStepSize"); }
 float ChSystemDem::GetFixedStepSize() const { return m_sys->step; }
 void ChSystemDem::SetDefragmentOnInitialize(bool defragment) { m_sys->defragment = defragment; }
 void ChSystemDem::EnableMinLength(bool useMinLen) { m_sys->use_min_length = useMinLen; }
-void ChSystemDem::SetTimeIntegrator(CHDEM_TIME_INTEGRATOR new_integrator) { m_sys->integrator = new_integrator; }
-void ChSystemDem::SetFrictionMode(CHDEM_FRICTION_MODE new_mode) { m_sys->friction = new_mode; }
+void ChSystemDem::SetTimeIntegrator(CHDEM_TIME_INTEGRATOR new_integrator) {
+    const auto old = m_sys->integrator;
+    m_sys->integrator = new_integrator;
+    try {
+        m_sys->refresh("SetTimeIntegrator");
+    } catch (...) {
+        m_sys->integrator = old;  // the engine refused (not changeable on a running system): keep the mirror consistent with it
+        throw;
+    }
+}
+void ChSystemDem::SetFrictionMode(CHDEM_FRICTION_MODE new_mode) {
+    const auto old = m_sys->friction;
+    m_sys->friction = new_mode;
+    try {
+        m_sys->refresh("SetFrictionMode");
+    } catch (...) {
+        m_sys->friction = old;  // the engine refused (not changeable on a running system): keep the mirror consistent with it
+        throw;
+    }
+}
 void ChSystemDem::SetRollingMode(CHDEM_ROLLING_MODE new_mode) {
     if (new_mode == CHDEM_ROLLING_MODE::ELASTIC_PLASTIC)
         fail("ELASTIC_PLASTIC rolling is not implemented (nor in the reference, ChDemHelpers.cuh:236-240)");
     m_sys->rolling = new_mode;
+    m_sys->refresh("SetRollingMode");
 }
-void ChSystemDem::SetStaticFrictionCoeff_SPH2SPH(float mu) { m_sys->mu[0] = mu; }
-void ChSystemDem::SetStaticFrictionCoeff_SPH2WALL(float mu) { m_sys->mu[1] = mu; }
-void ChSystemDem::SetRollingCoeff_SPH2SPH(float mu) { m_sys->mu_roll[0] = mu; }
-void ChSystemDem::SetRollingCoeff_SPH2WALL(float mu) { m_sys->mu_roll[1] = mu; }
-void ChSystemDem::SetSpinningCoeff_SPH2SPH(float mu) { m_sys->mu_spin[0] = mu; }
-void ChSystemDem::SetSpinningCoeff_SPH2WALL(float mu) { m_sys->mu_spin[1] = mu; }
-void ChSystemDem::SetKn_SPH2SPH(double v) { m_sys->Kn[0] = v; }
-void ChSystemDem::SetKn_SPH2WALL(double v) { m_sys->Kn[1] = v; }
-void ChSystemDem::SetGn_SPH2SPH(double v) { m_sys->Gn[0] = v; }
-void ChSystemDem::SetGn_SPH2WALL(double v) { m_sys->Gn[1] = v; }
-void ChSystemDem::SetKt_SPH2SPH(double v) { m_sys->Kt[0] = v; }
-void ChSystemDem::SetGt_SPH2SPH(double v) { m_sys->Gt[0] = v; }
-void ChSystemDem::SetKt_SPH2WALL(double v) { m_sys->Kt[1] = v; }
-void ChSystemDem::SetGt_SPH2WALL(double v) { m_sys->Gt[1] = v; }
-void ChSystemDem::SetCohesionRatio(float v) { m_sys->cohesion_over_g = v; }
-void ChSystemDem::SetAdhesionRatio_SPH2WALL(float v) { m_sys->adhesion_over_g[1] = v; }
-void ChSystemDem::UseMaterialBasedModel(bool val) { m_sys->use_mat_based = val; }
-void ChSystemDem::SetYoungModulus_SPH(double v) { m_sys->young[0] = v; }
-void ChSystemDem::SetYoungModulus_WALL(double v) { m_sys->young[1] = v; }
-void ChSystemDem::SetPoissonRatio_SPH(double v) { m_sys->poisson[0] = v; }
-void ChSystemDem::SetPoissonRatio_WALL(double v) { m_sys->poisson[1] = v; }
-void ChSystemDem::SetRestitution_SPH(double v) { m_sys->cor[0] = v; }
-void ChSystemDem::SetRestitution_WALL(double v) { m_sys->cor[1] = v; }
+void ChSystemDem::SetStaticFrictionCoeff_SPH2SPH(float mu) { m_sys->mu[0] = mu; m_sys->refresh("SetStaticFrictionCoeff_SPH2SPH"); }
+void ChSystemDem::SetStaticFrictionCoeff_SPH2WALL(float mu) { m_sys->mu[1] = mu; m_sys->refresh("SetStaticFrictionCoeff_SPH2WALL"); }
+void ChSystemDem::SetRollingCoeff_SPH2SPH(float mu) { m_sys->mu_roll[0] = mu; m_sys->refresh("SetRollingCoeff_SPH2SPH"); }
+void ChSystemDem::SetRollingCoeff_SPH2WALL(float mu) { m_sys->mu_roll[1] = mu; m_sys->refresh("SetRollingCoeff_SPH2WALL"); }
+void ChSystemDem::SetSpinningCoeff_SPH2SPH(float mu) { m_sys->mu_spin[0] = mu; m_sys->refresh("SetSpinningCoeff_SPH2SPH"); }
+void ChSystemDem::SetSpinningCoeff_SPH2WALL(float mu) { m_sys->mu_spin[1] = mu; m_sys->refresh("SetSpinningCoeff_SPH2WALL"); }
+void ChSystemDem::SetKn_SPH2SPH(double v) { m_sys->Kn[0] = v; m_sys->refresh("SetKn_SPH2SPH"); }
+void ChSystemDem::SetKn_SPH2WALL(double v) { m_sys->Kn[1] = v; m_sys->refresh("SetKn_SPH2WALL"); }
+void ChSystemDem::SetGn_SPH2SPH(double v) { m_sys->Gn[0] = v; m_sys->refresh("SetGn_SPH2SPH"); }
+void ChSystemDem::SetGn_SPH2WALL(double v) { m_sys->Gn[1] = v; m_sys->refresh("SetGn_SPH2WALL"); }
+void ChSystemDem::SetKt_SPH2SPH(double v) { m_sys->Kt[0] = v; m_sys->refresh("SetKt_SPH2SPH"); }
+void ChSystemDem::SetGt_SPH2SPH(double v) { m_sys->Gt[0] = v; m_sys->refresh("SetGt_SPH2SPH"); }
+void ChSystemDem::SetKt_SPH2WALL(double v) { m_sys->Kt[1] = v; m_sys->refresh("SetKt_SPH2WALL"); }
+void ChSystemDem::SetGt_SPH2WALL(double v) { m_sys->Gt[1] = v; m_sys->refresh("SetGt_SPH2WALL"); }
+void ChSystemDem::SetCohesionRatio(float v) { m_sys->cohesion_over_g = v; m_sys->refresh("SetCohesionRatio"); }
+void ChSystemDem::SetAdhesionRatio_SPH2WALL(float v) { m_sys->adhesion_over_g[1] = v; m_sys->refresh("SetAdhesionRatio_SPH2WALL"); }
+void ChSystemDem::UseMaterialBasedModel(bool val) {
+    const auto old = m_sys->use_mat_based;
+    m_sys->use_mat_based = val;
+    try {
+        m_sys->refresh("UseMaterialBasedModel");
+    } catch (...) {
+        m_sys->use_mat_based = old;  // the engine refused (not changeable on a running system): keep the mirror consistent with it
+        throw;
+    }
+}
+void ChSystemDem::SetYoungModulus_SPH(double v) { m_sys->young[0] = v; m_sys->refresh("SetYoungModulus_SPH"); }
+void ChSystemDem::SetYoungModulus_WALL(double v) { m_sys->young[1] = v; m_sys->refresh("SetYoungModulus_WALL"); }
+void ChSystemDem::SetPoissonRatio_SPH(double v) { m_sys->poisson[0] = v; m_sys->refresh("SetPoissonRatio_SPH"); }
+void ChSystemDem::SetPoissonRatio_WALL(double v) { m_sys->poisson[1] = v; m_sys->refresh("SetPoissonRatio_WALL"); }
+void ChSystemDem::SetRestitution_SPH(double v) { m_sys->cor[0] = v; m_sys->refresh("SetRestitution_SPH"); }
+void ChSystemDem::SetRestitution_WALL(double v) { m_sys->cor[1] = v; m_sys->refresh("SetRestitution_WALL"); }
 void ChSystemDem::SetMaxSafeVelocity_SU(float max_vel) { m_sys->max_safe_vel = max_vel; }
 void ChSystemDem::SetPsiFactors(unsigned int psi_T, unsigned int psi_L, float psi_R) {
     m_sys->psi_T = psi_T; m_sys->psi_L = psi_L; m_sys->psi_R = psi_R;  // no simulation-unit system: recorded only

@@ -1734,7 +1734,7 @@ int dem_b200_get_history(dem_b200_system* s, uint32_t* owner, uint32_t* other, d
         for (size_t k = 0; k < Kn; k++) {
             if (!((vr[i].amask >> k) & 1ull))
                 continue;
-            const uint32_t jo = nl[k * Np + i] & ~kHiFlag;
+            const uint32_t jo = nl[k * Np + i] & ~kEntryFlags;
             const uint32_t key = (jo & kTriFlag) ? (uint32_t)s->P.nW + (jo & ~kTriFlag) : s->P.shape_base + vr[jo].sid;
             if (key < me)
                 emit(me, key, k * Np + i);
@@ -1991,7 +1991,11 @@ int dem_b200_p2p_export(dem_b200_system* s, size_t max_records, void* handle64) 
 }
 
 int dem_b200_p2p_import(dem_b200_system* s, int rank, int world, const void* handles, int steps_ahead) {
-    if (!s || !s->p2p_region || !handles || world < 2 || world > kMaxRanks || rank < 0 || rank >= world || steps_ahead < 1)
+    if (s && world > kMaxRanks) {
+        s->err = "p2p_import: the direct halo holds at most 8 ranks (one NVSwitch box); use the NCCL halo (SlabDriver without enable_p2p) beyond that";
+        return DEMB200_EINVAL;
+    }
+    if (!s || !s->p2p_region || !handles || world < 2 || rank < 0 || rank >= world || steps_ahead < 1)
         return DEMB200_EINVAL;
     if (!s->mg_remap_pending) {
         s->err = "p2p_import: switch to the direct halo right after a slab rebuild, before the next step (the first direct step "

@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P, Buffers B) {
             amask &= amask - 1;
             const size_t si = (size_t)k * P.Np + src;
             if (cnt < (unsigned)P.K) {
-                const unsigned jo = B.nl[si] & ~kHiFlag;  // old storage slot of the partner, or kTriFlag | triangle
+                const unsigned jo = B.nl[si] & ~kEntryFlags;  // old storage slot of the partner, or kTriFlag | triangle
                 double4 r = B.hist[si];
                 r.w = pack_key((jo & kTriFlag) ? (unsigned)P.nW + (jo & ~kTriFlag) : P.shape_base + B.vel[a][jo].sid, (unsigned)r.w);
                 B.stage[(size_t)cnt * P.Np + s] = r;
@@ -1789,7 +1789,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 jj[u] = jn[u];
 #pragma unroll
             for (int u = 0; u < kP1; u++)
-                pp[u] = ld256(pos_in + (jj[u] & ~kHiFlag));
+                pp[u] = ld256(pos_in + (jj[u] & ~kEntryFlags));
 #pragma unroll
             for (int u = 0; u < kP1; u++)
                 jn[u] = (k0 + kP1 + u < nc) ? nl[(size_t)(k0 + kP1 + u) * P.Np] : s;
@@ -1802,11 +1802,11 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
                     continue;
                 if (cnt < kMaxSlots) {
-                    clist[cnt * kForceThreads + tid] = jj[u] & ~kHiFlag;
+                    clist[cnt * kForceThreads + tid] = jj[u] & ~kEntryFlags;
                     cslot[cnt * kForceThreads + tid] = (unsigned char)((k0 + u) | ((jj[u] & kHiFlag) ? kSlotHi : 0u));
                 }
 #if DEMB200_EARLYPF
-                prefetch_l1(vel_in + (jj[u] & ~kHiFlag));  // the partner's velocity record is needed in phase 2
+                prefetch_l1(vel_in + (jj[u] & ~kEntryFlags));  // the partner's velocity record is needed in phase 2
 #endif
                 cnt++;
             }
@@ -2447,7 +2447,7 @@ __global__ void __launch_bounds__(kTileThreads, DEMB200_TILE_MINBLOCKS) k_force_
             } else {
                 if (r != kCodeNoRank && idx < (unsigned)kTileCap)
                     return true;
-                idx = (r != kCodeNoRank) ? s_gstart[c] + r : (B.nl[(size_t)slot * P.Np + s] & ~(kHiFlag | kTriFlag));
+                idx = (r != kCodeNoRank) ? s_gstart[c] + r : (B.nl[(size_t)slot * P.Np + s] & ~(kEntryFlags | kTriFlag));
                 return false;
             }
         };
@@ -2660,7 +2660,7 @@ __device__ __forceinline__ unsigned walk_history(const Params& P, const Buffers&
         amask &= amask - 1;
         const size_t si = (size_t)k * P.Np + src;
         if (cnt < (unsigned)P.K) {
-            const unsigned jo = B.nl[si] & ~kHiFlag;
+            const unsigned jo = B.nl[si] & ~kEntryFlags;
             double4 r = B.hist[si];
             r.w = pack_key((jo & kTriFlag) ? (unsigned)P.nW + (jo & ~kTriFlag) : P.shape_base + vel_old[jo].sid, (unsigned)r.w);
             emit(cnt, r, B.hrel ? B.hrel[si] : 0.0);
@@ -3186,7 +3186,7 @@ __global__ void __launch_bounds__(256) k_find_contact(Params P, Buffers B, unsig
         for (unsigned k = 0; k < nc + tc; k++) {
             if (!((vel[s].amask >> k) & 1ull))
                 continue;
-            const unsigned e = B.nl[(size_t)k * P.Np + s] & ~kHiFlag;
+            const unsigned e = B.nl[(size_t)k * P.Np + s] & ~kEntryFlags;
             const unsigned key = (e & kTriFlag) ? (unsigned)P.nW + (e & ~kTriFlag) : P.shape_base + vel[e].sid;
             if (key == other_shape)
                 slot = (int)k;
@@ -3218,7 +3218,7 @@ __global__ void __launch_bounds__(256) k_export_contacts(Params P, Buffers B, un
         if (at >= cap)
             continue;
         bi[at] = vel[s].sid;
-        bj[at] = vel[e & ~kHiFlag].sid;
+        bj[at] = vel[e & ~kEntryFlags].sid;
         const double* src = B.cinfo + ((size_t)k * P.Np + s) * kCInfo;
         for (int c = 0; c < kCInfo; c++)
             info[(size_t)at * kCInfo + c] = src[c];

@@ -47,6 +47,7 @@ constexpr unsigned kCodeRankBits = 6;     // nl16 entry = hi << 15 | box cell <<
 constexpr unsigned kCodeNoRank = 63u;
 constexpr int kCInfo = 13;                  // doubles per recorded contact (Buffers::cinfo)
 constexpr unsigned kBndFlag = 0x80u;        // Buffers::ncnt bit 7: a candidate of this sphere is a ghost (slab mode) -> its forces wait for the halo
+constexpr unsigned kEntryFlags = kHiFlag;  // flag bits of a sphere entry (everything that is not the storage slot)
 constexpr unsigned kSlotHi = 0x80u;         // the same bit in the force kernel's shared-memory contact list (slot byte: slot < 64)
 
 // device error bits (dem_b200 error codes are derived from these at sync points)

@@ -134,5 +134,28 @@ void demContactInfo(int argc, char** argv) {
         third.AdvanceSimulation(0.01f);
         ASSERT_TRUE(third.GetParticlePosition(1).z() > floor_z);
     }
+    // ---- setters after Initialize reach the engine (gravity, step size) or fail loudly (friction mode), never silently diverge
+    {
+        ChSystemDem sys(radius, density, ChVector3f(100.f, 100.f, 100.f));
+        common_setup(sys, CHDEM_FRICTION_MODE::MULTI_STEP);
+        std::vector<ChVector3f> pts = {ChVector3f(0, 0, 0)};
+        sys.SetParticles(pts);
+        sys.Initialize();
+        sys.AdvanceSimulation(0.01f);
+        const float vz1 = sys.GetParticleVelocity(0).z();
+        ASSERT_NEAR(vz1, -980.f * 0.01f, 1e-3);
+        sys.SetGravitationalAcceleration(ChVector3d(0, 0, 0));
+        sys.AdvanceSimulation(0.01f);
+        ASSERT_NEAR(sys.GetParticleVelocity(0).z(), vz1, 1e-6);  // free flight without gravity: the velocity stays
+        sys.SetGravitationalAcceleration(ChVector3d(0, 0, -980));
+        sys.SetFixedStepSize(5e-5f);
+        const float t0 = sys.GetSimTime();
+        sys.AdvanceSimulation(0.01f);  // 200 steps of the new size
+        ASSERT_NEAR(sys.GetSimTime() - t0, 0.01, 1e-6);
+        ASSERT_NEAR(sys.GetParticleVelocity(0).z(), vz1 - 980.f * 0.01f, 2e-3);
+        bool threw = false;
+        try { sys.SetFrictionMode(CHDEM_FRICTION_MODE::FRICTIONLESS); } catch (const std::exception&) { threw = true; }
+        ASSERT_TRUE(threw);
+    }
 }
 RUN_TEST(demContactInfo)
