@@ -231,10 +231,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(cfg_id, n, n, sample_steps, args.gpus, 0,
-                                  {"note": "CPU arm: a %d-sphere volume of the same packing, NOT settled first (fewer contacts per "
-                                           "sphere than the GPU arm's settled bed: the comparison favours the CPU)" % n}),
+                                  {"note": "CPU arm: a %d-sphere volume of the GPU arm's packing from its initial state (configs[1] / [4]: the bed "
+                                           "is generated in static equilibrium, so the contacts per sphere are those of the GPU's timed region; "
+                                           "configs[2]: before the bed has relaxed, i.e. fewer contacts than the GPU arm sees)" % n}),
         "cpu_baseline": {"value": val, "unit": "sphere-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d spheres x %d time steps per bench step (same packing as the GPU arm, before settling)" % (n, sample_steps)},
+                         "sample": "%d spheres x %d time steps per bench step (same packing as the GPU arm, from its initial state)" % (n, sample_steps)},
         "e2e": {"value": val, "unit": "sphere-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
