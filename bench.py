@@ -739,6 +739,8 @@ def run_slabs(args):
             "config": workload_config(cfg_id, n_total // world, n_total, S, world, args.settle),
             "contacts_per_sphere": rec["contacts_per_sphere"], "settle": rec["settle"],
             "parity": parity,
+            "scaling_note": "weak scaling: every GPU holds %d spheres; the like-for-like one-GPU figure is `weak_base` of the "
+                            "`bench.py --gpus 1` line (same generator, same per-GPU size), not its configs[1] headline" % (n_total // world),
             "roofline": roofline_record(rec, n_total // world, world),
             "halo": rec["halo"], "cpu_baseline": None, "e2e": rec["e2e"],
             "gpu_launches": int(args.steps * S * (KERNELS_PER_TIMESTEP_SLAB + (5 if cfg_id == 3 else 0))),
