@@ -874,6 +874,73 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     const int lo0 = max(cc[a0] - 1, 0), hi0 = min(cc[a0] + 1, C.s_dim[a0] - 1);
     int cnt = 0;
     bool overflow = false, has_ghost = false;
+    if (!P.tiled) {
+        // plain grid.  The scan is a chain of dependent gathers if written naively (cell range -> position -> id of every
+        // accepted candidate); here the nine row ranges are fetched together, the positions of a row four at a time, and the
+        // ids / flags of the accepted candidates in a second sweep, four at a time as well.
+        unsigned rb[9], re[9];
+        int nrow = 0;
+        for (int e2 = -1; e2 <= 1; e2++) {
+            const int v2 = cc[a2] + e2;
+            if (v2 < 0 || v2 >= C.s_dim[a2])
+                continue;
+            for (int e1 = -1; e1 <= 1; e1++) {
+                const int v1 = cc[a1] + e1;
+                if (v1 < 0 || v1 >= C.s_dim[a1])
+                    continue;
+                const unsigned row = (unsigned)((v2 * C.s_dim[a1] + v1) * C.s_dim[a0]);
+                rb[nrow] = B.cell_start[row + lo0];   // the three cells of a row are one run of the storage order
+                re[nrow] = B.cell_start[row + hi0 + 1];
+                nrow++;
+            }
+        }
+        for (int r = 0; r < nrow; r++) {
+            for (unsigned j0 = rb[r]; j0 < re[r]; j0 += 4u) {
+                double4 pj[4];
+#pragma unroll
+                for (unsigned u = 0; u < 4u; u++)
+                    pj[u] = (j0 + u < re[r]) ? pos[j0 + u] : me;
+#pragma unroll
+                for (unsigned u = 0; u < 4u; u++) {
+                    const unsigned j = j0 + u;
+                    if (j >= re[r] || j == s)
+                        continue;
+                    const double dx = pj[u].x - me.x, dy2 = pj[u].y - me.y, dz2 = pj[u].z - me.z;
+                    const double d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
+                    const double rs = me.w + pj[u].w + C.skin;
+                    if (d2 > rs * rs * (1.0 + 1e-12))
+                        continue;
+                    if (cnt < P.Kn)
+                        tj[cnt++] = j;
+                    else
+                        overflow = true;
+                }
+            }
+        }
+        // ids and flags of the accepted candidates; two fixed bodies make no contact: drop those pairs here
+        int keep = 0;
+        for (int k0 = 0; k0 < cnt; k0 += 4) {
+            unsigned sidk[4], metak[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k0 + u < cnt) {
+                    sidk[u] = vel[tj[k0 + u]].sid;
+                    metak[u] = vel[tj[k0 + u]].meta;
+                }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k0 + u < cnt) {
+                    if (me_fixed && (metak[u] & FLAG_FIXED))
+                        continue;
+                    has_ghost |= (metak[u] & FLAG_GHOST) != 0;
+                    tj[keep] = tj[k0 + u];
+                    ts[keep] = sidk[u];
+                    tc[keep] = 0;
+                    keep++;
+                }
+        }
+        cnt = keep;
+    } else {
     for (int e2 = -1; e2 <= 1; e2++) {
         const int v2 = cc[a2] + e2;
         if (v2 < 0 || v2 >= C.s_dim[a2])
@@ -882,20 +949,11 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
             const int v1 = cc[a1] + e1;
             if (v1 < 0 || v1 >= C.s_dim[a1])
                 continue;
-            // plain grid: the three cells of a row are one run of the storage order; tiled grid: cell by cell
-            for (int v0 = lo0; v0 <= hi0; v0 += P.tiled ? 1 : 3) {
-                unsigned jb, je, box = 0u;
-                if (P.tiled) {
-                    const int x = v0, y = v1, z = v2;  // tiled: a0, a1, a2 = x, y, z
-                    const unsigned ci = cell_index(P, C, x, y, z);
-                    jb = B.cell_start[ci];
-                    je = B.cell_start[ci + 1];
-                    box = (unsigned)(((z - tz0 + 1) * kBox + (y - ty0 + 1)) * kBox + (x - tx0 + 1));
-                } else {
-                    const unsigned row = (unsigned)((v2 * C.s_dim[a1] + v1) * C.s_dim[a0]);
-                    jb = B.cell_start[row + lo0];
-                    je = B.cell_start[row + hi0 + 1];
-                }
+            for (int v0 = lo0; v0 <= hi0; v0++) {  // tiled grid (a0, a1, a2 = x, y, z): cell by cell
+                const int x = v0, y = v1, z = v2;
+                const unsigned ci = cell_index(P, C, x, y, z);
+                const unsigned jb = B.cell_start[ci], je = B.cell_start[ci + 1];
+                const unsigned box = (unsigned)(((z - tz0 + 1) * kBox + (y - ty0 + 1)) * kBox + (x - tx0 + 1));
                 for (unsigned j = jb; j < je; j++) {
                     if (j == s)
                         continue;
@@ -919,6 +977,7 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
                 }
             }
         }
+    }
     }
     if (overflow)
         atomicOr(&C.err, ERR_NEIGHBOR_OVERFLOW);
