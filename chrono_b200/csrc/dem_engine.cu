@@ -1476,6 +1476,20 @@ int dem_b200_set_state(dem_b200_system* s, const double* pos3, const double* vel
     return 0;
 }
 
+int dem_b200_request_rebuild(dem_b200_system* s) {
+    if (!s || !s->initialized)
+        return DEMB200_EINVAL;
+    if (s->mgpu) {
+        s->err = "slab engines rebuild through the slab protocol (dem_b200_p2p_rebuild / mgpu_finish_rebuild)";
+        return DEMB200_EINVAL;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    const unsigned one = 1;
+    CU(cudaMemcpyAsync(&s->B.ctrl->need_rebuild, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));  // `one` is on the stack
+    return 0;
+}
+
 namespace {
 int export_accel(dem_b200_system* s) {
     if (s->mgpu)

@@ -96,21 +96,65 @@ struct VelVal {
 // 32 L1 wavefronts instead of two; the force kernel is bound by the L1 data pipe (ncu r01o: 74 % of its peak), not DRAM.
 // ld256: arrays that the running kernel only reads (the compiler may schedule it freely); ld256v: locations the same
 // thread also writes (history rows) -- ordered with respect to st256.
+// Cache-policy qualifiers of the force kernel's access classes (PTX .level::eviction_priority; "" = default policy).
+// History rows and candidate ids are pure streams (each byte is used once per step by one thread); partner records are
+// gathered ~14 times per step by neighbouring threads.
+#ifndef DEMB200_Q_HLD
+#define DEMB200_Q_HLD ""   /* history rows, load */
+#endif
+#ifndef DEMB200_Q_HST
+#define DEMB200_Q_HST ""   /* history rows, store */
+#endif
+#ifndef DEMB200_Q_GLD
+#define DEMB200_Q_GLD ""   /* partner position / velocity gathers */
+#endif
+#ifndef DEMB200_Q_NL
+#define DEMB200_Q_NL ""    /* candidate list entries */
+#endif
+#ifndef DEMB200_Q_SST
+#define DEMB200_Q_SST ""   /* new state of the sphere, store */
+#endif
 __device__ __forceinline__ double4 ld256(const void* p) {
     double4 r;
     asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ double4 ld256g(const void* p) {  // gathered partner record
+    double4 r;
+    asm("ld.global" DEMB200_Q_GLD ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ double4 ld256v(const void* p) {
     double4 r;
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    asm volatile("ld.global" DEMB200_Q_HLD ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ void st256(void* p, double4 v) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
+__device__ __forceinline__ void st256h(void* p, double4 v) {  // history row
+    asm volatile("st.global" DEMB200_Q_HST ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void st256s(void* p, double4 v) {  // new state of a sphere
+    asm volatile("st.global" DEMB200_Q_SST ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned ld_nl(const uint32_t* p) {  // candidate list entry
+    unsigned r;
+    asm("ld.global" DEMB200_Q_NL ".u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ VelVal load_vel(const VelRec* __restrict__ a, size_t i) {
     const double4 q0 = ld256(a + i), q1 = ld256(reinterpret_cast<const char*>(a + i) + 32);
+    VelVal r;
+    r.v = mk(q0.x, q0.y, q0.z);
+    r.w = mk(q0.w, q1.x, q1.y);
+    r.sid = (unsigned)__double2loint(q1.z);
+    r.meta = (unsigned)__double2hiint(q1.z);
+    r.amask = (unsigned long long)__double_as_longlong(q1.w);
+    return r;
+}
+__device__ __forceinline__ VelVal load_vel_g(const VelRec* __restrict__ a, size_t i) {
+    const double4 q0 = ld256g(a + i), q1 = ld256g(reinterpret_cast<const char*>(a + i) + 32);
     VelVal r;
     r.v = mk(q0.x, q0.y, q0.z);
     r.w = mk(q0.w, q1.x, q1.y);
@@ -123,6 +167,12 @@ __device__ __forceinline__ void store_vel(VelRec* a, size_t i, V3 v, V3 w, unsig
                                           unsigned long long amask) {
     st256(a + i, make_double4(v.x, v.y, v.z, w.x));
     st256(reinterpret_cast<char*>(a + i) + 32,
+          make_double4(w.y, w.z, __hiloint2double((int)meta, (int)sid), __longlong_as_double((long long)amask)));
+}
+__device__ __forceinline__ void store_vel_s(VelRec* a, size_t i, V3 v, V3 w, unsigned sid, unsigned meta,
+                                          unsigned long long amask) {
+    st256s(a + i, make_double4(v.x, v.y, v.z, w.x));
+    st256s(reinterpret_cast<char*>(a + i) + 32,
           make_double4(w.y, w.z, __hiloint2double((int)meta, (int)sid), __longlong_as_double((long long)amask)));
 }
 // history record: (disp xyz, packed key | steps << 32); the key is only meaningful in the staging buffers
@@ -259,6 +309,10 @@ __device__ __forceinline__ void step_begin_body(const Params& P, const Buffers& 
     C.max_dx2 = 0ull;
     C.travel += dx;
     C.last_dx = dx;
+    // positions the host replaced since the last step (k_import_state) moved the spheres as well: the largest such jump counts
+    // like one more step's displacement.  A host that hands back what it was given (a co-simulation round trip) costs no rebuild.
+    C.travel += sqrt(__longlong_as_double((long long)C.import_dx2));
+    C.import_dx2 = 0ull;
     if (!P.skin_adaptive || !(C.skin > 0))
         C.skin = P.skin;
     const bool mesh_used_up = P.nT && !(C.travel + C.travel_mesh < 0.499 * P.skin_tri);
@@ -982,7 +1036,25 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
     if (overflow)
         atomicOr(&C.err, ERR_NEIGHBOR_OVERFLOW);
     // insertion sort by stable id: the per-step contact order (= summation order, history column order) becomes
-    // independent of the storage order
+    // independent of the storage order.  Plain grid: one array of packed (stable id, storage slot) keys instead of three.
+    if (!P.tiled) {
+        unsigned long long tk[kMaxNeighbors];
+        for (int a = 0; a < cnt; a++)
+            tk[a] = ((unsigned long long)ts[a] << 32) | tj[a];
+        for (int a = 1; a < cnt; a++) {
+            const unsigned long long ka = tk[a];
+            int b = a - 1;
+            while (b >= 0 && tk[b] > ka) {
+                tk[b + 1] = tk[b];
+                b--;
+            }
+            tk[b + 1] = ka;
+        }
+        for (int a = 0; a < cnt; a++) {
+            tj[a] = (unsigned)tk[a];
+            ts[a] = (unsigned)(tk[a] >> 32);
+        }
+    } else
     for (int a = 1; a < cnt; a++) {
         const unsigned kj = tj[a], ks = ts[a];
         const unsigned short kc = tc[a];
@@ -1079,27 +1151,49 @@ __global__ void __launch_bounds__(kListThreads) k_build_list(Params P, Buffers B
         unsigned long long amask = 0ull;
         unsigned wmask = 0u;
         const unsigned sc = B.stage_cnt[s];
-        for (unsigned c = 0; c < sc; c++) {
-            double4 r = B.stage[(size_t)c * P.Np + s];
-            const unsigned key = rec_key(r.w);
-            r.w = (double)rec_steps(r.w);  // in the candidate slots the 4th component is the step count as a double
-            size_t di;
-            if (key < (unsigned)P.nW) {
-                di = (size_t)(P.Kn + key) * P.Np + s;
-                wmask |= 1u << key;
-            } else {
-                const unsigned ps = key - P.shape_base;  // triangles: wraps, as stored in ts[]
-                int k = 0;
-                while (k < cnt + tcnt && ts[k] != ps)
-                    k++;
-                if (k == cnt + tcnt)
+        // The staged records come in the order of the old list (spheres by stable id, then facets): the same order as the new
+        // list, so the search for a record's slot resumes where the last one ended (and wraps, for records staged in any other
+        // order: checkpoints, migrants).  Four records are in flight at a time.
+        const int nk = cnt + tcnt;
+        int kp = 0;
+        for (unsigned c0 = 0; c0 < sc; c0 += 4u) {
+            double4 rr[4];
+#pragma unroll
+            for (unsigned u = 0; u < 4u; u++)
+                if (c0 + u < sc)
+                    rr[u] = B.stage[(size_t)(c0 + u) * P.Np + s];
+#pragma unroll
+            for (unsigned u = 0; u < 4u; u++) {
+                if (c0 + u >= sc)
                     continue;
-                di = (size_t)k * P.Np + s;
-                amask |= 1ull << k;
+                const unsigned c = c0 + u;
+                double4 r = rr[u];
+                const unsigned key = rec_key(r.w);
+                r.w = (double)rec_steps(r.w);  // in the candidate slots the 4th component is the step count as a double
+                size_t di;
+                if (key < (unsigned)P.nW) {
+                    di = (size_t)(P.Kn + key) * P.Np + s;
+                    wmask |= 1u << key;
+                } else {
+                    const unsigned ps = key - P.shape_base;  // triangles: wraps, as stored in ts[]
+                    int k = kp;
+                    while (k < nk && ts[k] != ps)
+                        k++;
+                    if (k == nk) {
+                        k = 0;
+                        while (k < kp && ts[k] != ps)
+                            k++;
+                        if (k == kp)
+                            continue;
+                    }
+                    kp = k + 1;
+                    di = (size_t)k * P.Np + s;
+                    amask |= 1ull << k;
+                }
+                B.hist[di] = r;
+                if (B.hrel)
+                    B.hrel[di] = B.stage_rel[(size_t)c * P.Np + s];
             }
-            B.hist[di] = r;
-            if (B.hrel)
-                B.hrel[di] = B.stage_rel[(size_t)c * P.Np + s];
         }
         VelRec* vr = B.vel[C.f_src] + s;
         vr->meta = (vr->meta & 0xFFu) | (wmask << 8);
@@ -1776,6 +1870,16 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #ifndef DEMB200_PF2
 #define DEMB200_PF2 0
 #endif
+// bounding experiments (wrong physics, same arithmetic; never the shipped build): 1 = history rows addressed by contact index
+// (coalesced), 2 = no history traffic, 3 = partner state of phase 2 from the own record (no gathers), 5 = 1 + 3
+#ifndef DEMB200_DIAG
+#define DEMB200_DIAG 0
+#endif
+#define DEMB200_DIAG_HROW(k_, slot_) ((DEMB200_DIAG == 1 || DEMB200_DIAG == 5) ? (size_t)(k_) : (size_t)((slot_) & 63u))
+#define DEMB200_DIAG_PARTNER(j_) ((DEMB200_DIAG == 3 || DEMB200_DIAG == 5) ? s : (j_))
+// 6 = body 2 of a pair does not write its history copy; 7 = 6 + body 2 reads a row of the PARTNER's column (the access pattern of a
+// single history copy kept by body 1)
+#define DEMB200_DIAG_HCOL(j_, hi_flag_) ((DEMB200_DIAG == 7 && !(hi_flag_)) ? B.hist + (j_) : hcol)
 // the rolling / spinning instantiations carry more live state: 12 warps per SM at 168 registers (no spills) beat 16 warps
 // at 128 registers with 172 B of spills (350 vs 400 us on the polydisperse + rolling-friction variant of the bench)
 #ifndef DEMB200_ROLL_MINBLOCKS
@@ -1839,7 +1943,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         unsigned jn[kP1];
 #pragma unroll
         for (int u = 0; u < kP1; u++)
-            jn[u] = ((unsigned)u < nc) ? nl[(size_t)u * P.Np] : s;
+            jn[u] = ((unsigned)u < nc) ? ld_nl(nl + (size_t)u * P.Np) : s;
         for (unsigned k0 = 0; k0 < nc; k0 += kP1) {
             unsigned jj[kP1];
             double4 pp[kP1];
@@ -1848,10 +1952,10 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 jj[u] = jn[u];
 #pragma unroll
             for (int u = 0; u < kP1; u++)
-                pp[u] = ld256(pos_in + (jj[u] & ~kEntryFlags));
+                pp[u] = ld256g(pos_in + (jj[u] & ~kEntryFlags));
 #pragma unroll
             for (int u = 0; u < kP1; u++)
-                jn[u] = (k0 + kP1 + u < nc) ? nl[(size_t)(k0 + kP1 + u) * P.Np] : s;
+                jn[u] = (k0 + kP1 + u < nc) ? ld_nl(nl + (size_t)(k0 + kP1 + u) * P.Np) : s;
 #pragma unroll
             for (int u = 0; u < kP1; u++) {
                 const V3 d = mk(__dsub_rn(pp[u].x, me.x), __dsub_rn(pp[u].y, me.y), __dsub_rn(pp[u].z, me.z));
@@ -1963,7 +2067,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 atomicAdd(&C.wall_force[w][2], -F.z);
             }
             if (HIST) {
-                st256(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
+                st256h(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
                 if (rcol)
                     rcol[hi] = h.relvel0;
                 wmask_new |= 1u << w;
@@ -1990,15 +2094,19 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
     if (cnt > 0) {
         const unsigned j0 = clist[tid];
         slot_next = cslot[tid];  // slot | kSlotHi
-        pj_next = ld256(pos_in + j0);
-        ov_next = load_vel(vel_in, j0);
-        if (HIST && ((amask_old >> (slot_next & 63u)) & 1ull))
-            hr_next = ld256v(hcol + (size_t)(slot_next & 63u) * P.Np);
+        pj_next = ld256g(pos_in + DEMB200_DIAG_PARTNER(j0));
+        ov_next = load_vel_g(vel_in, DEMB200_DIAG_PARTNER(j0));
+        if (HIST && DEMB200_DIAG != 2 && ((amask_old >> (slot_next & 63u)) & 1ull))
+            hr_next = ld256v(DEMB200_DIAG_HCOL(j0, slot_next & kSlotHi) + DEMB200_DIAG_HROW(0, slot_next) * P.Np);
     }
     for (int k = 0; k < maxc; k++) {
         if (k >= cnt)
             continue;
+#if DEMB200_DIAG == 3 || DEMB200_DIAG == 5
+        const double4 pj = make_double4(pj_next.x + ((k & 1) ? 1.999 : -1.999) * me.w, pj_next.y, pj_next.z, pj_next.w);
+#else
         const double4 pj = pj_next;
+#endif
         const VelVal ov = ov_next;
         double4 hr = hr_next;
         // Keep the consumer of the prefetched record HERE: without this the compiler copies the freshly loaded
@@ -2021,14 +2129,14 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         if (k + 1 < cnt) {
             const unsigned jn = clist[(k + 1) * kForceThreads + tid];
             slot_next = cslot[(k + 1) * kForceThreads + tid];
-            pj_next = ld256(pos_in + jn);
-            ov_next = load_vel(vel_in, jn);
-            if (HIST && ((amask_old >> (slot_next & 63u)) & 1ull))
-                hr_next = ld256v(hcol + (size_t)(slot_next & 63u) * P.Np);
+            pj_next = ld256g(pos_in + DEMB200_DIAG_PARTNER(jn));
+            ov_next = load_vel_g(vel_in, DEMB200_DIAG_PARTNER(jn));
+            if (HIST && DEMB200_DIAG != 2 && ((amask_old >> (slot_next & 63u)) & 1ull))
+                hr_next = ld256v(DEMB200_DIAG_HCOL(jn, slot_next & kSlotHi) + DEMB200_DIAG_HROW(k + 1, slot_next) * P.Np);
         }
         const unsigned sj = REC ? ov.sid : 0u;
         const bool had = HIST && ((amask_old >> slot) & 1ull);
-        const size_t hi = (size_t)slot * P.Np;
+        const size_t hi = DEMB200_DIAG_HROW(k, slot) * P.Np;
         ncontacts++;
         if (REC && !me1) {
             unsigned long long at = atomicAdd(&C.pair_count, 1ull);
@@ -2060,7 +2168,17 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             if (HIST) {
                 if (!me1)
                     disp = -disp;
-                st256(hcol + hi, make_double4(disp.x, disp.y, disp.z, steps));
+                if (DEMB200_DIAG != 2 && !((DEMB200_DIAG == 6 || DEMB200_DIAG == 7) && !me1))
+                    st256h(hcol + hi, make_double4(disp.x, disp.y, disp.z, steps));
+#if DEMB200_DIAG == 8 || DEMB200_DIAG == 9
+                {   // marginal cost of one more 32-byte read + write per contact on a scratch array (the rebuild's staging rows):
+                    // 8 = addressed by contact index (coalesced across the warp), 9 = by candidate slot (scattered like the history)
+                    double4* const q = B.stage + s + (size_t)(DEMB200_DIAG == 8 ? (unsigned)k & 15u : slot & 15u) * P.Np;
+                    double4 t = ld256v(q);
+                    t.x += disp.x;
+                    st256h(q, t);
+                }
+#endif
                 amask_new |= 1ull << slot;
             }
         } else {
@@ -2119,7 +2237,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 Tsum = Tsum + T2;
             }
             if (HIST) {
-                st256(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
+                st256h(hcol + hi, make_double4(h.disp.x, h.disp.y, h.disp.z, steps));
                 if (rcol)
                     rcol[hi] = h.relvel0;
                 amask_new |= 1ull << slot;
@@ -2189,8 +2307,8 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         }
         if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z)))
             atomicOr(&C.err, ERR_NAN);
-        st256(B.pos[dst] + s, make_double4(x.x, x.y, x.z, me.w));
-        store_vel(B.vel[dst], s, vn, wn, sid, flags | (wmask_new << 8), amask_new);
+        st256s(B.pos[dst] + s, make_double4(x.x, x.y, x.z, me.w));
+        store_vel_s(B.vel[dst], s, vn, wn, sid, flags | (wmask_new << 8), amask_new);
         if (!ghost) {
             nmnx = x.x - me.w; nmny = x.y - me.w; nmnz = x.z - me.w;
             nmxx = x.x + me.w; nmxy = x.y + me.w; nmxz = x.z + me.w;
@@ -2636,7 +2754,8 @@ __global__ void __launch_bounds__(kTileThreads, DEMB200_TILE_MINBLOCKS) k_force_
             if (HIST) {
                 if (!me1)
                     disp = -disp;
-                st256(hcol + hi, make_double4(disp.x, disp.y, disp.z, steps));
+                if (DEMB200_DIAG != 2 && !((DEMB200_DIAG == 6 || DEMB200_DIAG == 7) && !me1))
+                    st256(hcol + hi, make_double4(disp.x, disp.y, disp.z, steps));
                 amask_new |= 1ull << slot;
             }
         }
@@ -3381,6 +3500,17 @@ __global__ void __launch_bounds__(256) k_import_state(Params P, Buffers B, const
     const size_t o = 3 * (size_t)r.sid;
     if (pos3) {
         double4 p = B.pos[C.cur][i];
+        // how far the host moved this sphere: the candidate lists stay valid while the jumps fit into the Verlet skin
+        // (Ctrl::import_dx2 -> k_step_begin); anything that is not a finite distance asks for the rebuild outright
+        const double ex = pos3[o] - p.x, ey = pos3[o + 1] - p.y, ez = pos3[o + 2] - p.z;
+        const double e2 = ex * ex + ey * ey + ez * ez;
+        if (!(e2 < 1e300))
+            C.need_rebuild = 1u;
+        else if (e2 > 0.0) {
+            const unsigned long long e = (unsigned long long)__double_as_longlong(e2);  // non-negative: raw bits are ordered
+            if (e > *(volatile unsigned long long*)&C.import_dx2)  // (the running maximum soon filters out almost every thread)
+                atomicMax(&C.import_dx2, e);
+        }
         p.x = pos3[o]; p.y = pos3[o + 1]; p.z = pos3[o + 2];
         B.pos[C.cur][i] = p;
     }
@@ -3388,8 +3518,6 @@ __global__ void __launch_bounds__(256) k_import_state(Params P, Buffers B, const
     if (om3) r.w = mk(om3[o], om3[o + 1], om3[o + 2]);
     if (vel3 || om3)
         store_vel(B.vel[C.cur], i, r.v, r.w, r.sid, r.meta, r.amask);
-    if (i == 0 && pos3)
-        C.need_rebuild = 1u;  // positions were replaced: the candidate lists are stale
 }
 
 }  // namespace demb200

@@ -173,6 +173,7 @@ struct Ctrl {
     unsigned long long sbox_next[6];  // search grid covers this box (+ the meshes), not the walls: a slab of a long box must not
     unsigned sbox_pending, sbox_pad_; // bin the whole box.  sbox_next is gathered by k_bin_count while it reads every position anyway.
     unsigned long long max_dx2;   // raw bits of max |x_new - x_old|^2 over the spheres, last step
+    unsigned long long import_dx2;  // same, for positions replaced by the host since the last step (dem_b200_set_state): uses up skin like a step
     double travel;                // sum of per-step max displacements since the last rebuild
     double last_dx;               // max displacement of the step before the last one (growth estimate of the slab vote)
     double skin;                  // Verlet skin the current lists were built with (Params::skin unless adaptive)

@@ -222,6 +222,10 @@ class DemSystem:
         pos, vel, omega = _f64(pos, (n, 3)), _f64(vel, (n, 3)), _f64(omega, (n, 3))
         self._ck(self.L.dem_b200_set_state(self.h, _dp(pos), _dp(vel), _dp(omega)))
 
+    def request_rebuild(self):
+        """The next step rebuilds the neighbour lists (no result depends on it)."""
+        self._ck(self.L.dem_b200_request_rebuild(self.h))
+
     def sphere(self, i):
         p, v, w = np.empty(3), np.empty(3), np.empty(3)
         self._ck(self.L.dem_b200_get_sphere(self.h, C.c_size_t(i), _dp(p), _dp(v), _dp(w)))

@@ -164,7 +164,11 @@ int dem_b200_advance_host(dem_b200_system* s, size_t n, const double* pos3_in, c
 /* ---- state access (user order) -- GetParticlePosition / Velocity / AngVelocity ------------------------------- */
 size_t dem_b200_num_spheres(const dem_b200_system* s);
 int dem_b200_get_state(dem_b200_system* s, double* pos3, double* vel3, double* omega3);
+/* New positions use up Verlet skin like a time step does: the largest jump of a sphere is added to the travel since the last
+ * neighbour-list rebuild, so handing back positions that did not move (a co-simulation round trip) costs no rebuild. */
 int dem_b200_set_state(dem_b200_system* s, const double* pos3, const double* vel3, const double* omega3);
+/* The next step rebuilds the neighbour lists whatever the travel (no result depends on it; used by profiling scripts). */
+int dem_b200_request_rebuild(dem_b200_system* s);
 int dem_b200_get_sphere(dem_b200_system* s, size_t i, double pos[3], double vel[3], double omega[3]);
 /* Linear acceleration (gravity included) each sphere had in the last step, user order -- GetParticleLinAcc
  * (ChSystemDem.h:273, ChSystemDem_impl.cpp:1290-1296) and the fx,fy,fz columns of WriteParticleFile (:322-327).  Zero

@@ -1,6 +1,5 @@
 """Run under ncu with --profile-from-start off: the 1 M-sphere settled bed of the default bench line, then, inside
-cudaProfilerStart/Stop, `--rebuilds` time steps that rebuild the neighbour lists (requested through set_state with unchanged
-positions, so the Verlet skin and the list lengths are the ones of a normal run) and `--steady` steps that do not.
+cudaProfilerStart/Stop, `--rebuilds` time steps that rebuild the neighbour lists (requested through dem_b200_request_rebuild, so the Verlet skin and the list lengths are the ones of a normal run) and `--steady` steps that do not.
 
   ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/TAG/kernels \
       python scripts/profile_kernels.py --rebuilds 2 --steady 2
@@ -31,14 +30,13 @@ def main():
     scene = bench.build_scene(args.config, args.spheres)
     g = scenes.make_gpu(scene, **bench.physics(args.config))
     g.step(args.settle)
-    pos, vel, om = g.state()
-    g.set_state(pos=pos)
+    g.request_rebuild()
     g.step(1)  # one rebuild outside the capture: the storage order is the settled one from here on
     g.step(1)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     for _ in range(args.rebuilds):
-        g.set_state(pos=pos)  # positions unchanged: only the "lists are stale" flag is raised
+        g.request_rebuild()  # the Verlet skin and the list lengths are those of a normal run
         g.step(1)
     for _ in range(args.steady):
         g.step(1)

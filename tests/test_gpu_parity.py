@@ -251,6 +251,61 @@ def test_verlet_skin_does_not_change_a_bit(skin):
     assert np.array_equal(hr["owner"][kr], hg["owner"][kg]) and np.array_equal(hr["disp"][kr], hg["disp"][kg])
 
 
+def test_host_round_trip_costs_no_rebuild_and_no_bit():
+    """dem_b200_set_state / dem_b200_advance_host: positions handed back unchanged use up no Verlet skin (no rebuild: the
+    co-simulation round trip of the e2e bench figure); positions that jumped count like a step's displacement, so the lists
+    are only rebuilt once the jumps no longer fit into the skin; dem_b200_request_rebuild forces a rebuild.  None of it
+    changes a bit of the trajectory."""
+    n = 3000
+    scene = scenes.settling_scene(n, sep_factor=1.99, seed=13)
+    vel, om = kinematics(n, 9, vscale=0.2)
+    ref = common.make_gpu(scene, vel=vel, omega=om, dt=1e-4)
+    ref.step(40)
+    g = common.make_gpu(scene, vel=vel, omega=om, dt=1e-4)
+    g.step(10)
+    r0 = g.stats()["rebuilds"]
+    p, v, w = g.state()
+    g.set_state(pos=p, vel=v, omega=w)
+    g.step(1)
+    assert g.stats()["rebuilds"] == r0, "unchanged positions must not rebuild"
+    po, vo, wo = np.empty_like(p), np.empty_like(p), np.empty_like(p)
+    p, v, w = g.state()
+    g.advance_host(p, v, w, 9, po, vo, wo)  # steps 12 .. 20 through the host-buffer call
+    g.request_rebuild()
+    r1 = g.stats()["rebuilds"]
+    g.step(1)
+    assert g.stats()["rebuilds"] == r1 + 1
+    g.step(19)
+    for x, y in zip(ref.state(), g.state()):
+        assert np.array_equal(x, y)
+    # both engines are in the same state now (history included).  Small jumps of every sphere: one engine keeps its lists,
+    # the other is told to rebuild; five steps later they still agree bit for bit
+    ref.request_rebuild()
+    g.request_rebuild()
+    ref.step(1)
+    g.step(1)  # travel starts from zero in both
+    p, v, w = g.state()
+    p2 = p + np.random.default_rng(3).normal(size=p.shape) * 1e-5
+    ra, rb = g.stats()["rebuilds"], ref.stats()["rebuilds"]
+    g.set_state(pos=p2)
+    ref.set_state(pos=p2)
+    ref.request_rebuild()
+    g.step(1)
+    ref.step(1)
+    assert g.stats()["rebuilds"] == ra and ref.stats()["rebuilds"] == rb + 1
+    g.step(4)
+    ref.step(4)
+    for x, y in zip(ref.state(), g.state()):
+        assert np.array_equal(x, y)
+    # a jump far beyond the skin: the next step rebuilds on its own
+    p, v, w = g.state()
+    p[5, 2] += 3.0
+    ra = g.stats()["rebuilds"]
+    g.set_state(pos=p)
+    g.step(1)
+    assert g.stats()["rebuilds"] == ra + 1
+
+
 def test_history_overflow_is_reported():
     """More simultaneous contacts than history_slots must fail loudly, not silently drop a contact."""
     from chrono_b200 import dem
