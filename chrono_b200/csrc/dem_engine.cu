@@ -271,6 +271,23 @@ bool use_tile_kernel(const dem_b200_system* s) {
     return s->P.tiled && !s->P.nT && fast_path(s) && !s->recording;
 }
 
+// Shared-memory carve-out of the force kernel: just what its resident blocks need (16 one-warp blocks x (2.5 KB contact list + 1 KB
+// reserved) -> the 64 KB configuration), so that the rest of the 256 KB stays L1 for the partner gathers; the driver's default keeps
+// the 100 KB configuration (r02dyn: 281.2 -> 277.4 us).  DEMB200_CARVEOUT=<percent> overrides (tuning experiments).
+template <bool H, bool R, int F, bool REC, bool MESH>
+void force_kernel_attrs(const Params& P) {
+    static int last = -1;
+    const int blocks = R ? DEMB200_ROLL_MINBLOCKS : DEMB200_FORCE_MINBLOCKS;
+    int pct = (int)((100.0 * blocks * (double)(force_smem_bytes(P, H) + 1024u)) / (228.0 * 1024.0) + 0.999);
+    if (const char* e = getenv("DEMB200_CARVEOUT"))
+        pct = atoi(e);
+    pct = pct > 100 ? 100 : pct;
+    if (pct == last)
+        return;
+    last = pct;
+    cudaFuncSetAttribute(k_force_integrate<H, R, F, REC, MESH>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 // pass 0: all spheres; 1 / 2: the spheres without / with a ghost among their candidates (slab mode, direct halo: see enqueue_post)
 template <bool REC>
 void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks, unsigned pass = 0u) {
@@ -296,9 +313,13 @@ void launch_force(dem_b200_system* s, const Buffers& B, unsigned blocks, unsigne
 #define LF(H, R, F)                                                                                  \
     do {                                                                                             \
         if (P.nT)                                                                                    \
-            k_force_integrate<H, R, F, REC, true><<<blocks, kForceThreads, 0, s->stream>>>(P, B, pass);    \
+            force_kernel_attrs<H, R, F, REC, true>(P);                                               \
         else                                                                                         \
-            k_force_integrate<H, R, F, REC, false><<<blocks, kForceThreads, 0, s->stream>>>(P, B, pass);   \
+            force_kernel_attrs<H, R, F, REC, false>(P);                                              \
+        if (P.nT)                                                                                    \
+            k_force_integrate<H, R, F, REC, true><<<blocks, kForceThreads, force_smem_bytes(P, H), s->stream>>>(P, B, pass);    \
+        else                                                                                         \
+            k_force_integrate<H, R, F, REC, false><<<blocks, kForceThreads, force_smem_bytes(P, H), s->stream>>>(P, B, pass);   \
     } while (0)
     switch (sel) {
         case 0: LF(false, false, 0); break;

@@ -1889,12 +1889,30 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #define DEMB200_FORCE_MINBLOCKS (512 / DEMB200_FORCE_THREADS)  /* 16 warps per SM: 128 registers per thread */
 #endif
 
+// rows of the force kernel's shared-memory contact list: K with MultiStep history (more contacts than history slots is an
+// error in any case), else the upper bound of K
+__host__ __device__ __forceinline__ int force_list_slots(const Params& P, bool hist) {
+    return hist ? (P.K < kMaxSlots ? P.K : kMaxSlots) : kMaxSlots;
+}
+__host__ __device__ __forceinline__ size_t force_smem_bytes(const Params& P, bool hist) {
+    return (size_t)force_list_slots(P, hist) * kForceThreads * 5u;
+}
+
 // FAST: 0 = generic law (contact_force), 1 = Hertz with material properties, 2 = Hertz with user coefficients
 template <bool HIST, bool ROLL, int FAST, bool REC, bool MESH>
-__global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS : DEMB200_FORCE_MINBLOCKS) k_force_integrate(const __grid_constant__ Params P,
+#ifdef DEMB200_FORCE_MAXNREG  /* experiment: registers per thread set directly (17 / 18 one-warp blocks per SM = 120 / 112) */
+__global__ void __launch_bounds__(kForceThreads) __maxnreg__(ROLL ? 168 : DEMB200_FORCE_MAXNREG) k_force_integrate(
+#else
+__global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS : DEMB200_FORCE_MINBLOCKS) k_force_integrate(
+#endif
+    const __grid_constant__ Params P,
                                                                       const __grid_constant__ Buffers B, const unsigned pass) {
-    __shared__ unsigned clist[kMaxSlots * kForceThreads];      // storage slot of the k-th touching candidate
-    __shared__ unsigned char cslot[kMaxSlots * kForceThreads];  // its index in the candidate list (= history slot)
+    // contact list of the block, dynamic shared memory sized by the launch (force_list_slots): with MultiStep history a sphere may
+    // not have more than K contacts anyway, and 16 rows instead of 32 let the driver pick the 64 KB carve-out (192 KB of L1)
+    extern __shared__ unsigned force_smem[];
+    const int cap = force_list_slots(P, HIST);
+    unsigned* const clist = force_smem;                                                        // storage slot of the k-th touching candidate
+    unsigned char* const cslot = reinterpret_cast<unsigned char*>(clist + cap * kForceThreads);  // its index in the candidate list (= history slot)
     Ctrl& C = *B.ctrl;
     const unsigned src = C.f_src, dst = src ^ 1u;
     const double4* __restrict__ pos_in = B.pos[src];
@@ -1964,7 +1982,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 // (a padding lane compares the sphere with itself: dist2 = 0 < 1e-12, rejected)
                 if (dist2 >= __dmul_rn(rs, rs) || dist2 < 1e-12)
                     continue;
-                if (cnt < kMaxSlots) {
+                if (cnt < cap) {
                     clist[cnt * kForceThreads + tid] = jj[u] & ~kEntryFlags;
                     cslot[cnt * kForceThreads + tid] = (unsigned char)((k0 + u) | ((jj[u] & kHiFlag) ? kSlotHi : 0u));
                 }
@@ -1974,9 +1992,9 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 cnt++;
             }
         }
-        if (cnt > kMaxSlots) {
+        if (cnt > cap) {
             atomicOr(&C.err, ERR_HISTORY_OVERFLOW);
-            cnt = kMaxSlots;
+            cnt = cap;
         }
     }
     const unsigned sid = mv.sid;
