@@ -1865,7 +1865,7 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #define DEMB200_P1_BATCH 4
 #endif
 #ifndef DEMB200_EARLYPF
-#define DEMB200_EARLYPF 0  /* L1 prefetch of history rows / partner records at first sight: a loss since the 256-bit gathers (r01v) */
+#define DEMB200_EARLYPF 0  /* prefetch of history rows (1, 2) and partner records (1) at first sight: a loss since the 256-bit gathers (r01v) */
 #endif
 #ifndef DEMB200_PF2
 #define DEMB200_PF2 0
@@ -1986,7 +1986,7 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                     clist[cnt * kForceThreads + tid] = jj[u] & ~kEntryFlags;
                     cslot[cnt * kForceThreads + tid] = (unsigned char)((k0 + u) | ((jj[u] & kHiFlag) ? kSlotHi : 0u));
                 }
-#if DEMB200_EARLYPF
+#if DEMB200_EARLYPF == 1
                 prefetch_l1(vel_in + (jj[u] & ~kEntryFlags));  // the partner's velocity record is needed in phase 2
 #endif
                 cnt++;
@@ -2129,7 +2129,9 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         double4 hr = hr_next;
         // Keep the consumer of the prefetched record HERE: without this the compiler copies the freshly loaded
         // registers into their loop-carried homes right behind the load below and stalls on it (ncu r01d).
+#ifndef DEMB200_NO_HRPIN
         asm volatile("" : "+d"(hr.x), "+d"(hr.y), "+d"(hr.z), "+d"(hr.w));
+#endif
         const unsigned slot = slot_next & 63u;
         // canonical orientation: body 1 = lower stable id.  Decided by k_build_list (kHiFlag) and carried in the slot
         // byte: the partner's id is not gathered for it (the only other use of that id is the recorded pair key).
