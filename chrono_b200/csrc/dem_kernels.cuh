@@ -1870,13 +1870,13 @@ constexpr int kForceThreads = DEMB200_FORCE_THREADS;
 #ifndef DEMB200_PF2
 #define DEMB200_PF2 0
 #endif
-// bounding experiments (wrong physics, same arithmetic; never the shipped build): 1 = history rows addressed by contact index
-// (coalesced), 2 = no history traffic, 3 = partner state of phase 2 from the own record (no gathers), 5 = 1 + 3
+// bounding experiments (wrong physics, same arithmetic; never the shipped build; results in profiles/README.md): 1 = history rows
+// addressed by contact index (coalesced), 2 = no history traffic, 8 / 9 = one more read-modify-write per contact on a scratch row
+// (by contact index / by slot)
 #ifndef DEMB200_DIAG
 #define DEMB200_DIAG 0
 #endif
-#define DEMB200_DIAG_HROW(k_, slot_) ((DEMB200_DIAG == 1 || DEMB200_DIAG == 5) ? (size_t)(k_) : (size_t)((slot_) & 63u))
-#define DEMB200_DIAG_PARTNER(j_) ((DEMB200_DIAG == 3 || DEMB200_DIAG == 5) ? s : (j_))
+#define DEMB200_DIAG_HROW(k_, slot_) ((DEMB200_DIAG == 1) ? (size_t)(k_) : (size_t)((slot_) & 63u))
 // 6 = body 2 of a pair does not write its history copy; 7 = 6 + body 2 reads a row of the PARTNER's column (the access pattern of a
 // single history copy kept by body 1)
 #define DEMB200_DIAG_HCOL(j_, hi_flag_) ((DEMB200_DIAG == 7 && !(hi_flag_)) ? B.hist + (j_) : hcol)
@@ -2112,19 +2112,15 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
     if (cnt > 0) {
         const unsigned j0 = clist[tid];
         slot_next = cslot[tid];  // slot | kSlotHi
-        pj_next = ld256g(pos_in + DEMB200_DIAG_PARTNER(j0));
-        ov_next = load_vel_g(vel_in, DEMB200_DIAG_PARTNER(j0));
+        pj_next = ld256g(pos_in + j0);
+        ov_next = load_vel_g(vel_in, j0);
         if (HIST && DEMB200_DIAG != 2 && ((amask_old >> (slot_next & 63u)) & 1ull))
             hr_next = ld256v(DEMB200_DIAG_HCOL(j0, slot_next & kSlotHi) + DEMB200_DIAG_HROW(0, slot_next) * P.Np);
     }
     for (int k = 0; k < maxc; k++) {
         if (k >= cnt)
             continue;
-#if DEMB200_DIAG == 3 || DEMB200_DIAG == 5
-        const double4 pj = make_double4(pj_next.x + ((k & 1) ? 1.999 : -1.999) * me.w, pj_next.y, pj_next.z, pj_next.w);
-#else
         const double4 pj = pj_next;
-#endif
         const VelVal ov = ov_next;
         double4 hr = hr_next;
         // Keep the consumer of the prefetched record HERE: without this the compiler copies the freshly loaded
@@ -2149,8 +2145,8 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
         if (k + 1 < cnt) {
             const unsigned jn = clist[(k + 1) * kForceThreads + tid];
             slot_next = cslot[(k + 1) * kForceThreads + tid];
-            pj_next = ld256g(pos_in + DEMB200_DIAG_PARTNER(jn));
-            ov_next = load_vel_g(vel_in, DEMB200_DIAG_PARTNER(jn));
+            pj_next = ld256g(pos_in + jn);
+            ov_next = load_vel_g(vel_in, jn);
             if (HIST && DEMB200_DIAG != 2 && ((amask_old >> (slot_next & 63u)) & 1ull))
                 hr_next = ld256v(DEMB200_DIAG_HCOL(jn, slot_next & kSlotHi) + DEMB200_DIAG_HROW(k + 1, slot_next) * P.Np);
         }
