@@ -1948,6 +1948,15 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 prefetch_l1(hp + (size_t)k * P.Np);
             }
         }
+        const uint32_t* __restrict__ nl = B.nl + s;
+        // batches of kP1 candidates: the ids of the next batch and the positions of this batch are in flight together.  The first
+        // batch of ids does not wait for the candidate count (rows beyond it hold stale but readable entries, discarded below):
+        // count, ids, own position and own velocity record are one round trip instead of two
+        constexpr int kP1 = DEMB200_P1_BATCH;
+        unsigned jn[kP1];
+#pragma unroll
+        for (int u = 0; u < kP1; u++)
+            jn[u] = (u < P.Kn) ? ld_nl(nl + (size_t)u * P.Np) : 0u;
         const unsigned ncw = B.ncnt[s];
         const unsigned nc = ncw & 0x7Fu;
         wcand = (ncw >> 8) & 0xFFFFu;
@@ -1955,13 +1964,9 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
             tfirst = nc;
             tcand = ncw >> 24;
         }
-        const uint32_t* __restrict__ nl = B.nl + s;
-        // batches of kP1 candidates: the ids of the next batch and the positions of this batch are in flight together
-        constexpr int kP1 = DEMB200_P1_BATCH;
-        unsigned jn[kP1];
 #pragma unroll
         for (int u = 0; u < kP1; u++)
-            jn[u] = ((unsigned)u < nc) ? ld_nl(nl + (size_t)u * P.Np) : s;
+            jn[u] = ((unsigned)u < nc) ? jn[u] : s;
         for (unsigned k0 = 0; k0 < nc; k0 += kP1) {
             unsigned jj[kP1];
             double4 pp[kP1];
