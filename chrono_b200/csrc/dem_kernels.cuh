@@ -1938,7 +1938,8 @@ __global__ void __launch_bounds__(kForceThreads, ROLL ? DEMB200_ROLL_MINBLOCKS :
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(B.ncnt + sa));
 #pragma unroll
                 for (int u = 0; u < DEMB200_P1_BATCH; u++)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(B.nl + (size_t)u * P.Np + sa));
+                    if (u < P.Kn)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(B.nl + (size_t)u * P.Np + sa));
             }
         }
     }
