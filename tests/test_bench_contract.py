@@ -32,3 +32,26 @@ def test_reference_arm_other_ranks_are_silent():
     out = run_bench("--impl", "reference", "--gpus", "2", "--spheres", "20000", "--steps", "1", "--warmup", "1",
                     env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.strip() == ""
+
+
+def test_roofline_record_arithmetic_and_traffic_file():
+    """The roofline object of the bench line: achieved = SURVEY 8(d) bytes x spheres / kernel time, frac = achieved / peak,
+    traffic = the committed ncu capture of the same workload (configs[1], ~1 M spheres) and nothing for any other size."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rec = {"contacts_per_sphere": 8.45, "value": 3.4e9,
+           "kernel_ms_per_timestep": {"k_step_begin": 0.015, "k_force_integrate": 0.277}}
+    n = 997920
+    r = bench.roofline_record(rec, n)
+    peak, _ = bench.peaks()
+    assert r["kernel"] == "k_force_integrate" and r["unit"] == "GB/s" and r["bound"] == "hbm"
+    want = (160.0 + 32.0 * 8.45) * n / 0.277e-3 / 1e9
+    assert abs(r["achieved"] - want) < 1e-6 * want and abs(r["frac"] - want / peak) < 1e-9
+    assert abs(r["whole_step_frac"] - (176.0 + 32.0 * 8.45) * 3.4e9 / 1e9 / peak) < 1e-9
+    with open(os.path.join(ROOT, "profiles", "force_traffic.json")) as f:
+        t = json.load(f)
+    assert r["traffic"] == t["dram_bytes_read"] + t["dram_bytes_write"] and r["traffic_source"]
+    assert os.path.exists(os.path.join(ROOT, t["capture"].split(" ")[0])), "the capture the traffic figure cites is committed"
+    # measured traffic is well above the algorithmic bytes (duplicate history, candidate ids): the line must show it
+    assert 1.5 < r["traffic"] / ((160.0 + 32.0 * 8.45) * n) < 2.5
+    assert bench.roofline_record(rec, 4000000)["traffic"] is None
